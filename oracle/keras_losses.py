@@ -1,0 +1,194 @@
+"""Oracle restatement of tensorflow_ranking/python/keras/losses.py (hot-path subset).
+
+Test infrastructure only (see oracle/__init__.py).  Reproduces the Keras
+`Loss.__call__` reduction semantics the reference inherits from tf.keras:
+`losses = call(y_true, y_pred)`; `losses *= sample_weight` (rank-aligned);
+AUTO / SUM_OVER_BATCH_SIZE -> sum / numel(losses); SUM -> sum; NONE -> as is.
+"""
+import torch
+
+from oracle import losses_impl
+
+
+class Reduction(object):
+  AUTO = 'auto'
+  NONE = 'none'
+  SUM = 'sum'
+  SUM_OVER_BATCH_SIZE = 'sum_over_batch_size'
+
+
+def _keras_compute_weighted_loss(losses, sample_weight, reduction):
+  if sample_weight is not None:
+    sample_weight = torch.as_tensor(sample_weight, dtype=losses.dtype)
+    # squeeze_or_expand_dimensions: align the weight rank to the loss rank.
+    if sample_weight.dim() == losses.dim() + 1 and sample_weight.shape[-1] == 1:
+      sample_weight = sample_weight.squeeze(-1)
+    elif sample_weight.dim() == losses.dim() - 1:
+      sample_weight = sample_weight.unsqueeze(-1)
+    losses = losses * sample_weight
+  if reduction == Reduction.NONE:
+    return losses
+  total = losses.sum()
+  if reduction == Reduction.SUM:
+    return total
+  return total / float(losses.numel())   # AUTO == SUM_OVER_BATCH_SIZE
+
+
+# LambdaWeights with the Keras defaults (keras/losses.py:114-231).
+class LabelDiffLambdaWeight(losses_impl.LabelDiffLambdaWeight):
+  pass
+
+
+class DCGLambdaWeight(losses_impl.DCGLambdaWeight):
+
+  def __init__(self, topn=None, gain_fn=None, rank_discount_fn=None,
+               normalized=False, smooth_fraction=0., **kwargs):
+    super().__init__(topn, gain_fn or losses_impl.identity,
+                     rank_discount_fn or losses_impl.inverse, normalized,
+                     smooth_fraction)
+
+
+class NDCGLambdaWeight(DCGLambdaWeight):
+
+  def __init__(self, topn=None, gain_fn=None, rank_discount_fn=None,
+               smooth_fraction=0., **kwargs):
+    super().__init__(topn, gain_fn or losses_impl.pow_minus_1,
+                     rank_discount_fn or losses_impl.log2_inverse,
+                     normalized=True, smooth_fraction=smooth_fraction)
+
+
+class NDCGLambdaWeightV2(losses_impl.DCGLambdaWeightV2):
+
+  def __init__(self, topn=None, gain_fn=None, rank_discount_fn=None, **kwargs):
+    super().__init__(topn, gain_fn or losses_impl.pow_minus_1,
+                     rank_discount_fn or losses_impl.log2_inverse,
+                     normalized=True)
+
+
+class YetiDCGLambdaWeight(losses_impl.YetiDCGLambdaWeight):
+
+  def __init__(self, topn=None, gain_fn=None, rank_discount_fn=None,
+               normalized=False, **kwargs):
+    super().__init__(topn, gain_fn or losses_impl.pow_minus_1,
+                     rank_discount_fn or losses_impl.log2_inverse,
+                     normalized=normalized)
+
+
+class PrecisionLambdaWeight(losses_impl.PrecisionLambdaWeight):
+
+  def __init__(self, topn=None, positive_fn=None, **kwargs):
+    super().__init__(topn, positive_fn or losses_impl.is_greater_equal_1)
+
+
+class _RankingLoss(object):
+  """keras/losses.py:247-285."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None):
+    self.reduction = reduction
+    self.name = name
+    self._loss = None
+
+  def __call__(self, y_true, y_pred, sample_weight=None):
+    y_pred = torch.as_tensor(y_pred)
+    y_true = torch.as_tensor(y_true, dtype=y_pred.dtype)
+    sample_weight = self._loss.normalize_weights(y_true, sample_weight)
+    losses = self.call(y_true, y_pred)
+    return _keras_compute_weighted_loss(losses, sample_weight, self.reduction)
+
+  def call(self, y_true, y_pred):
+    y_pred = self._loss.get_logits(y_pred)
+    losses, weights = self._loss.compute_unreduced_loss(
+        labels=y_true, logits=y_pred)
+    return losses * weights
+
+
+class _PairwiseLoss(_RankingLoss):
+  """keras/losses.py:288-335."""
+
+  _impl = None
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, lambda_weight=None,
+               temperature=1.0):
+    super().__init__(reduction, name)
+    self._loss = self._impl(name=name, lambda_weight=lambda_weight,
+                            temperature=temperature)
+
+  def call(self, y_true, y_pred):
+    y_pred = self._loss.get_logits(y_pred)
+    losses, weights = self._loss.compute_unreduced_loss(
+        labels=y_true, logits=y_pred)
+    return (losses * weights).sum(dim=2)
+
+
+class PairwiseHingeLoss(_PairwiseLoss):
+  _impl = losses_impl.PairwiseHingeLoss
+
+
+class PairwiseLogisticLoss(_PairwiseLoss):
+  _impl = losses_impl.PairwiseLogisticLoss
+
+
+class PairwiseSoftZeroOneLoss(_PairwiseLoss):
+  _impl = losses_impl.PairwiseSoftZeroOneLoss
+
+
+class PairwiseMSELoss(_PairwiseLoss):
+  _impl = losses_impl.PairwiseMSELoss
+
+
+class _ListwiseLoss(_RankingLoss):
+  _impl = None
+  _default_temperature = 1.0
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, lambda_weight=None,
+               temperature=None):
+    super().__init__(reduction, name)
+    if temperature is None:
+      temperature = self._default_temperature
+    self._loss = self._impl(name=name, lambda_weight=lambda_weight,
+                            temperature=temperature)
+
+
+class SoftmaxLoss(_ListwiseLoss):
+  """keras/losses.py:758-832."""
+  _impl = losses_impl.SoftmaxLoss
+
+  def __call__(self, y_true, y_pred, sample_weight=None):
+    y_pred = torch.as_tensor(y_pred)
+    y_true = torch.as_tensor(y_true, dtype=y_pred.dtype)
+    if sample_weight is not None:
+      sample_weight = torch.as_tensor(sample_weight, dtype=y_pred.dtype)
+    losses, sw = self._loss.compute_per_list(y_true, y_pred, sample_weight)
+    return _keras_compute_weighted_loss(losses, sw, self.reduction)
+
+
+class ApproxNDCGLoss(_ListwiseLoss):
+  """keras/losses.py:1164-1237."""
+  _impl = losses_impl.ApproxNDCGLoss
+  _default_temperature = 0.1
+
+
+class ApproxMRRLoss(_ListwiseLoss):
+  _impl = losses_impl.ApproxMRRLoss
+  _default_temperature = 0.1
+
+
+_KEY_TO_CLS = {
+    'pairwise_hinge_loss': PairwiseHingeLoss,
+    'pairwise_logistic_loss': PairwiseLogisticLoss,
+    'pairwise_soft_zero_one_loss': PairwiseSoftZeroOneLoss,
+    'pairwise_mse_loss': PairwiseMSELoss,
+    'softmax_loss': SoftmaxLoss,
+    'approx_ndcg_loss': ApproxNDCGLoss,
+    'approx_mrr_loss': ApproxMRRLoss,
+}
+
+
+def get(loss, reduction=Reduction.AUTO, lambda_weight=None, name=None, **kwargs):
+  """keras/losses.py:51-111 (hot-path keys)."""
+  if loss not in _KEY_TO_CLS:
+    raise ValueError('unsupported loss: {}'.format(loss))
+  kw = dict(reduction=reduction, name=name, **kwargs)
+  if loss not in ('approx_ndcg_loss', 'approx_mrr_loss'):
+    kw['lambda_weight'] = lambda_weight
+  return _KEY_TO_CLS[loss](**kw)

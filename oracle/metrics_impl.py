@@ -1,0 +1,135 @@
+"""Oracle restatement of tensorflow_ranking/python/metrics_impl.py (NDCG, MRR)
+and of the Keras `Mean`-based wrappers in keras/metrics.py:156-193.
+
+Test infrastructure only (see oracle/__init__.py).
+"""
+import torch
+
+from oracle import losses_impl as L
+from oracle import utils
+
+_DEFAULT_GAIN_FN = L.pow_minus_1                  # metrics_impl.py:31
+_DEFAULT_RANK_DISCOUNT_FN = L.log2_inverse        # metrics_impl.py:33 (ln2/log1p)
+
+
+def _per_example_weights_to_per_list_weights(weights, relevance):
+  """metrics_impl.py:63-119."""
+  nonzero_weights = weights.sum(1, keepdim=True) > 0.0
+  per_list_relevance = relevance.sum(1, keepdim=True)
+  nonzero_relevance = torch.where(
+      nonzero_weights, (per_list_relevance > 0.0).to(weights.dtype),
+      torch.zeros_like(per_list_relevance))
+  nonzero_relevance_count = nonzero_relevance.sum(0, keepdim=True)
+  per_list_weights = L._divide_no_nan(
+      (weights * relevance).sum(1, keepdim=True), per_list_relevance)
+  sum_weights = per_list_weights.sum(0, keepdim=True)
+  avg_weight = torch.where(
+      nonzero_relevance_count > 0.0,
+      L._divide_no_nan(sum_weights, nonzero_relevance_count),
+      torch.ones_like(nonzero_relevance_count))
+  return torch.where(
+      nonzero_weights,
+      torch.where(per_list_relevance > 0.0, per_list_weights,
+                  torch.ones_like(per_list_weights) * avg_weight),
+      torch.zeros_like(per_list_weights))
+
+
+def _discounted_cumulative_gain(labels, weights, gain_fn, rank_discount_fn):
+  """metrics_impl.py:122-151."""
+  list_size = labels.shape[1]
+  position = torch.arange(1, list_size + 1).to(labels.dtype)
+  gain = gain_fn(labels)
+  discount = rank_discount_fn(position)
+  return (weights * gain * discount).sum(1, keepdim=True)
+
+
+class _RankingMetric(object):
+
+  def _prepare_and_validate_params(self, labels, predictions, weights, mask):
+    """metrics_impl.py:228-266."""
+    predictions = torch.as_tensor(predictions)
+    labels = torch.as_tensor(labels, dtype=predictions.dtype)
+    weights = 1.0 if weights is None else torch.as_tensor(
+        weights, dtype=predictions.dtype)
+    example_weights = torch.ones_like(labels) * weights
+    assert predictions.dim() == 2
+    if mask is None:
+      mask = utils.is_label_valid(labels)
+    mask = torch.logical_and(torch.as_tensor(mask), example_weights > 0.0)
+    labels = torch.where(mask, labels, torch.zeros_like(labels))
+    predictions = torch.where(
+        mask, predictions, -1e-6 * torch.ones_like(predictions) +
+        predictions.min(dim=1, keepdim=True).values)
+    return labels, predictions, example_weights, mask
+
+  def compute(self, labels, predictions, weights=None, mask=None):
+    """metrics_impl.py:268-291."""
+    labels, predictions, weights, mask = self._prepare_and_validate_params(
+        labels, predictions, weights, mask)
+    return self._compute_impl(labels, predictions, weights, mask)
+
+
+class MRRMetric(_RankingMetric):
+  """metrics_impl.py:429-459."""
+
+  def __init__(self, name=None, topn=None):
+    self._topn = topn
+
+  def _compute_impl(self, labels, predictions, weights, mask):
+    topn = predictions.shape[1] if self._topn is None else self._topn
+    sorted_labels, = utils.sort_by_scores(predictions, [labels], topn=topn,
+                                          mask=mask)
+    n = sorted_labels.shape[1]
+    relevance = (sorted_labels >= 1.0).to(predictions.dtype)
+    reciprocal_rank = 1.0 / torch.arange(1, n + 1).to(predictions.dtype)
+    mrr = (relevance * reciprocal_rank).max(dim=1, keepdim=True).values
+    per_list_weights = _per_example_weights_to_per_list_weights(
+        weights=weights, relevance=(labels >= 1.0).to(predictions.dtype))
+    return mrr, per_list_weights
+
+
+class NDCGMetric(_RankingMetric):
+  """metrics_impl.py:631-670."""
+
+  def __init__(self, name=None, topn=None, gain_fn=_DEFAULT_GAIN_FN,
+               rank_discount_fn=_DEFAULT_RANK_DISCOUNT_FN):
+    self._topn = topn
+    self._gain_fn = gain_fn
+    self._rank_discount_fn = rank_discount_fn
+
+  def _compute_impl(self, labels, predictions, weights, mask):
+    topn = predictions.shape[1] if self._topn is None else self._topn
+    sorted_labels, sorted_weights = utils.sort_by_scores(
+        predictions, [labels, weights], topn=topn, mask=mask)
+    dcg = _discounted_cumulative_gain(sorted_labels, sorted_weights,
+                                      self._gain_fn, self._rank_discount_fn)
+    weighted_gains = weights * self._gain_fn(labels)
+    ideal_sorted_labels, ideal_sorted_weights = utils.sort_by_scores(
+        weighted_gains, [labels, weights], topn=topn, mask=mask)
+    ideal_dcg = _discounted_cumulative_gain(
+        ideal_sorted_labels, ideal_sorted_weights, self._gain_fn,
+        self._rank_discount_fn)
+    per_list_ndcg = L._divide_no_nan(dcg, ideal_dcg)
+    per_list_weights = _per_example_weights_to_per_list_weights(
+        weights=weights, relevance=self._gain_fn(labels))
+    return per_list_ndcg, per_list_weights
+
+
+class KerasMean(object):
+  """tf.keras.metrics.Mean over (values, sample_weight): keras/metrics.py:171-193."""
+
+  def __init__(self, metric):
+    self._metric = metric
+    self.reset_state()
+
+  def reset_state(self):
+    self.total = 0.0
+    self.count = 0.0
+
+  def update_state(self, y_true, y_pred, sample_weight=None):
+    v, w = self._metric.compute(y_true, y_pred, sample_weight)
+    self.total += float((v * w).sum())
+    self.count += float(w.sum())
+
+  def result(self):
+    return self.total / self.count if self.count != 0 else 0.0

@@ -1,0 +1,388 @@
+"""Known-answer tests for the loss cores, ported from the reference's own tests.
+
+Every expected value is the closed-form expression the reference asserts
+(cited per test); the same cases run against the CPU oracle and, under
+`-m gpu`, against the CUDA kernels through the C-ABI.
+"""
+import math
+
+import pytest
+import torch
+
+ln = math.log
+
+
+def _close(actual, expected, tol=1e-5):
+  a = torch.as_tensor(actual).detach().double().cpu()
+  e = torch.as_tensor(expected).double()
+  assert a.shape == e.shape or a.numel() == e.numel(), (a.shape, e.shape)
+  torch.testing.assert_close(a.reshape(e.shape), e, rtol=tol, atol=tol)
+
+
+def _softmax(values):
+  total = sum(math.exp(v) for v in values)
+  return [math.exp(v) / total for v in values]
+
+
+def _logloss(x):
+  return ln(1. + math.exp(-x))
+
+
+# ---------------------------------------------------------------------------
+# helper functions: losses_impl_test.py:164-196
+# ---------------------------------------------------------------------------
+def test_approx_ranks(oracle_api):
+  L = oracle_api.losses_impl
+  logits = oracle_api.t([[100., 300., 200., 0.], [400., 200., 150., 300.]])
+  _close(L.approx_ranks(logits), [[3., 1., 2., 4.], [1., 3., 4., 2.]])
+
+
+def test_inverse_max_dcg(oracle_api):
+  L = oracle_api.losses_impl
+  labels = oracle_api.t([[1., 4., 1., 0.], [4., 2., 0., 3.], [0., 0., 0., 0.]])
+  _close(L.inverse_max_dcg(labels), [[0.04297], [0.033139], [0.]])
+  _close(L.inverse_max_dcg(labels, topn=1), [[0.04621], [0.04621], [0.]])
+
+
+def test_ndcg_helper(oracle_api):
+  L = oracle_api.losses_impl
+  labels = oracle_api.t([[1., 4., 1., 0.], [4., 2., 0., 3.], [0., 0., 0., 0.]])
+  ranks = torch.tensor([[1, 2, 3, 4], [1, 3, 4, 2], [1, 2, 3, 4]])
+  _close(L.ndcg(labels), [[0.679685], [0.95176], [0.]])
+  _close(L.ndcg(labels, ranks), [[0.679685], [1.], [0.]])
+
+
+# ---------------------------------------------------------------------------
+# LambdaWeight pair weights: losses_impl_test.py:323-512
+# ---------------------------------------------------------------------------
+LABELS3 = [[2.0, 1.0, 0.0]]
+RANKS3 = [[1, 2, 3]]
+
+
+def _pw(api, lw, labels, ranks):
+  return lw.pair_weights(api.t(labels), api.t(ranks, dtype=torch.int32)
+                         if api.name == 'cuda' else torch.tensor(ranks))
+
+
+def test_label_diff_lambda_weight(api):
+  lw = api.losses_impl.LabelDiffLambdaWeight()
+  _close(_pw(api, lw, LABELS3, RANKS3),
+         [[[0., 1., 2.], [1., 0., 1.], [2., 1., 0.]]])
+
+
+def test_dcg_lambda_weight_default(api):
+  lw = api.losses_impl.DCGLambdaWeight()
+  _close(_pw(api, lw, LABELS3, RANKS3) / 3.,
+         [[[0., 1. / 2., 2. * 1. / 6.], [1. / 2., 0., 1. / 2.],
+           [2. * 1. / 6., 1. / 2., 0.]]])
+
+
+def test_dcg_lambda_weight_smooth_fraction(api):
+  lw = api.losses_impl.DCGLambdaWeight(smooth_fraction=1.0)
+  _close(_pw(api, lw, LABELS3, RANKS3) / 3.,
+         [[[0., 1. / 2., 2. * 2. / 3.], [1. / 2., 0., 1. / 6.],
+           [2. * 2. / 3., 1. / 6., 0.]]])
+  lw = api.losses_impl.DCGLambdaWeight(topn=1, smooth_fraction=1.0)
+  _close(_pw(api, lw, LABELS3, RANKS3) / 3.,
+         [[[0., 1., 2.], [1., 0., 0.], [2., 0., 0.]]])
+
+
+def test_dcg_lambda_weight_topn(api):
+  lw = api.losses_impl.DCGLambdaWeight(topn=1)
+  _close(_pw(api, lw, LABELS3, RANKS3) / 3.,
+         [[[0., 1. / 2., 1. / 3.], [1. / 2., 0., 0.], [1. / 3., 0., 0.]]])
+
+
+def test_dcg_lambda_weight_invalid_labels(api):
+  lw = api.losses_impl.DCGLambdaWeight()
+  _close(_pw(api, lw, [[2.0, 1.0, -1.0]], RANKS3) / 3.,
+         [[[0., 1. / 2., 0.], [1. / 2., 0., 0.], [0., 0., 0.]]])
+
+
+def test_dcg_lambda_weight_gain_and_discount(api):
+  lw = api.losses_impl.DCGLambdaWeight(gain_fn=api.fns.pow_minus_1,
+                                       rank_discount_fn=api.fns.log1p_inverse)
+  e = 2. * (1. / ln(2.) - 1. / ln(3.))
+  _close(_pw(api, lw, [[2.0, 1.0]], [[1, 2]]) / 2., [[[0., e], [e, 0.]]])
+
+
+def test_dcg_lambda_weight_normalized(api):
+  lw = api.losses_impl.DCGLambdaWeight(normalized=True)
+  max_dcg = 2.5
+  _close(_pw(api, lw, [[1.0, 2.0]], [[1, 2]]) / 2.,
+         [[[0., 1. / 2. / max_dcg], [1. / 2. / max_dcg, 0.]]])
+
+
+def test_dcg_lambda_weight_individual_weights(oracle_api):
+  lw = oracle_api.losses_impl.DCGLambdaWeight(normalized=True)
+  out = lw.individual_weights(oracle_api.t([[1.0, 2.0]]),
+                              torch.tensor([[1, 2]]))
+  _close(out, [[1. / 2.5 / 1., 2. / 2.5 / 2.]])
+
+
+def test_dcg_lambda_weight_v2(api):
+  lw = api.losses_impl.DCGLambdaWeightV2()
+  _close(_pw(api, lw, LABELS3, RANKS3) / 3.,
+         [[[0., 1. / 2., 2. * 1. / 6.], [1. / 2., 0., 1. / 2.],
+           [2. * 1. / 6., 1. / 2., 0.]]])
+  lw = api.losses_impl.DCGLambdaWeightV2(topn=1)
+  _close(_pw(api, lw, LABELS3, RANKS3) / 3.,
+         [[[0., 1., 1. / 2.], [1., 0., 3. / 4.], [1. / 2., 3. / 4., 0.]]])
+
+
+def test_yeti_dcg_lambda_weight(api):
+  lw = api.losses_impl.YetiDCGLambdaWeight()
+  _close(_pw(api, lw, LABELS3, RANKS3) / 3.,
+         [[[0., 1. / 2., 0.], [1. / 2., 0., 1. / 2.], [0., 1. / 2., 0.]]])
+  lw = api.losses_impl.YetiDCGLambdaWeight(topn=1)
+  _close(_pw(api, lw, LABELS3, RANKS3) / 3.,
+         [[[0., 1., 0.], [1., 0., 3. / 4.], [0., 3. / 4., 0.]]])
+
+
+def test_precision_lambda_weight(api):
+  lw = api.losses_impl.PrecisionLambdaWeight(topn=5)
+  _close(_pw(api, lw, LABELS3, RANKS3), [[[0.] * 3] * 3])
+  lw = api.losses_impl.PrecisionLambdaWeight(topn=1)
+  _close(_pw(api, lw, LABELS3, RANKS3),
+         [[[0., 0., 1.], [0., 0., 0.], [1., 0., 0.]]])
+
+
+def test_smooth_fraction_out_of_range_raises(api):
+  with pytest.raises(ValueError):
+    api.losses_impl.DCGLambdaWeight(smooth_fraction=1.5)
+
+
+# ---------------------------------------------------------------------------
+# compute_per_list: losses_impl_test.py:517-554
+# ---------------------------------------------------------------------------
+SCORES = [[1., 3., 2.], [1., 2., 3.]]
+LABELS = [[0., 0., 1.], [0., 0., 2.]]
+ITEM_W = [[2., 3., 4.], [1., 1., 1.]]
+
+
+def test_pairwise_compute_per_list(api):
+  loss_fn = api.losses_impl.PairwiseHingeLoss(name=None)
+  losses, weights = loss_fn.compute_per_list(api.t(LABELS), api.t(SCORES),
+                                             api.t(ITEM_W))
+  _close(losses, [1., 0.])
+  _close(weights, [4. + 4., 1. + 1.])
+
+
+def test_listwise_compute_per_list(api):
+  loss_fn = api.losses_impl.ApproxNDCGLoss(name=None)
+  losses, weights = loss_fn.compute_per_list(api.t(LABELS), api.t(SCORES),
+                                             api.t(ITEM_W))
+  _close(losses, [-0.63093, -0.796248])
+  _close(weights, [4., 1.])
+
+
+def test_softmax_compute_per_list(api):
+  """losses_impl_test.py:1150-1160."""
+  loss_fn = api.losses_impl.SoftmaxLoss(name=None)
+  losses, weights = loss_fn.compute_per_list(api.t(LABELS), api.t(SCORES),
+                                             api.t(ITEM_W))
+  _close(losses, [1.407606, 0.407606])
+  _close(weights, [4., 2.])
+
+
+# ragged table of losses_impl_test.py:556-587, expressed with -1 padding
+# (what utils.ragged_to_dense produces: utils.py:437-443).
+RAGGED_SCORES = [[1., 3., 2.], [1., 3., -1e6]]
+RAGGED_LABELS = [[0., 0., 1.], [0., 2., -1.]]
+RAGGED_W = [[2., 3., 4.], [1., 1., 0.]]
+
+
+@pytest.mark.parametrize('cls,expected_losses,expected_weights', [
+    ('PairwiseHingeLoss', [1., 0.], [8., 1.]),
+    ('PairwiseLogisticLoss', [0.813262, 0.126928], [8., 1.]),
+    ('PairwiseSoftZeroOneLoss', [0.5, 0.119203], [8., 1.]),
+    ('SoftmaxLoss', [1.407606, 0.126928], [4., 2.]),
+    ('ApproxNDCGLoss', [-0.63093, -0.922917], [4., 1.]),
+    ('ApproxMRRLoss', [-0.5, -0.893493], [4., 1.]),
+])
+def test_compute_per_list_padded(api, cls, expected_losses, expected_weights):
+  loss_fn = getattr(api.losses_impl, cls)(name=None)
+  losses, weights = loss_fn.compute_per_list(
+      api.t(RAGGED_LABELS), api.t(RAGGED_SCORES), api.t(RAGGED_W))
+  _close(losses, expected_losses)
+  _close(weights, expected_weights)
+
+
+# ---------------------------------------------------------------------------
+# Pairwise losses, estimator-style reductions: losses_impl_test.py:639-999
+# ---------------------------------------------------------------------------
+_PHI = {
+    'PairwiseLogisticLoss': _logloss,
+    'PairwiseHingeLoss': lambda x: max(0., 1. - x),
+    'PairwiseSoftZeroOneLoss': lambda x: 1. / (1. + math.exp(x)),
+}
+
+
+@pytest.mark.parametrize('cls', sorted(_PHI))
+def test_pairwise_loss_mean(api, cls):
+  phi = _PHI[cls]
+  loss_fn = getattr(api.losses_impl, cls)(name=None)
+  R = api.Reduction.MEAN
+  result = loss_fn.compute(api.t(LABELS), api.t(SCORES), None, R)
+  _close(result, (phi(3. - 2.) + phi(1. - 2.) + phi(3. - 1.) + phi(3. - 2.)) / 4.)
+  # per-list weights
+  result = loss_fn.compute(api.t(LABELS), api.t(SCORES), api.t([[1.], [2.]]), R)
+  _close(result, (1. * (phi(3. - 2.) + phi(1. - 2.)) + 2. *
+                  (phi(3. - 2.) + phi(3. - 1.))) / 6.)
+  # per-example weights
+  result = loss_fn.compute(api.t(LABELS), api.t(SCORES),
+                           api.t([[1., 1., 2.], [1., 1., 1.]]), R)
+  _close(result, ((2. * phi(3. - 2.) + 2. * phi(1. - 2.)) +
+                  (phi(3. - 1.) + phi(3. - 2.))) / 6.)
+  # lambda weights
+  loss_fn = getattr(api.losses_impl, cls)(
+      name=None, lambda_weight=api.losses_impl.DCGLambdaWeight())
+  result = loss_fn.compute(api.t(LABELS), api.t(SCORES), None, R)
+  _close(result,
+         (((3. / 2.) * phi(3. - 2.) + (3. / 2.) * phi(1. - 2.)) +
+          ((1. / 1.) * phi(3. - 1.) + (3. / 1.) * phi(3. - 2.))) /
+         ((3. / 2.) + (3. / 2.) + (1. / 1.) + (3. / 1.)))
+  # invalid labels
+  loss_fn = getattr(api.losses_impl, cls)(name=None)
+  result = loss_fn.compute(api.t([[0., -1., 1.]]), api.t([[1., 3., 2.]]), None, R)
+  _close(result, phi(2. - 1.))
+  # explicit mask
+  result = loss_fn.compute(
+      api.t([[1., 0., 0.], [0., 0., 2.]]), api.t(SCORES), None, R,
+      api.t([[True, False, True], [True, True, True]], dtype=torch.bool))
+  _close(result, (phi(1. - 2.) + phi(3. - 1.) + phi(3. - 2.)) / 3.)
+
+
+def test_pairwise_logistic_sum_by_nonzero_weights(api):
+  """losses_test.py estimator default reduction (losses.py:66-67)."""
+  loss_fn = api.losses_impl.PairwiseLogisticLoss(name=None)
+  result = loss_fn.compute(api.t(LABELS), api.t(SCORES),
+                           api.t([[1.], [2.]]),
+                           api.Reduction.SUM_BY_NONZERO_WEIGHTS)
+  _close(result, (1. * (_logloss(1.) + _logloss(-1.)) + 2. *
+                  (_logloss(1.) + _logloss(2.))) / 4.)
+
+
+# ---------------------------------------------------------------------------
+# Softmax: losses_impl_test.py:1089-1205
+# ---------------------------------------------------------------------------
+S3 = [[1., 3., 2.], [1., 2., 3.], [1., 2., 3.]]
+
+
+def test_softmax_loss(api):
+  R = api.Reduction.SUM_BY_NONZERO_WEIGHTS
+  L = api.losses_impl
+  labels = [[0., 0., 1.], [0., 0., 2.], [0., 0., 0.]]
+  result = L.SoftmaxLoss(name=None).compute(api.t(labels), api.t(S3), None, R)
+  _close(result, -(ln(_softmax(S3[0])[2]) + ln(_softmax(S3[1])[2]) * 2.) / 2.)
+
+  probs = [_softmax(s) for s in S3]
+  labels = [[0., 0., 1.], [1., 1., 2.], [0., 0., 0.]]
+  ew = [[1., 1., 1.], [1., 2., 3.], [1., 0., 1.]]
+  result = L.SoftmaxLoss(name=None).compute(api.t(labels), api.t(S3),
+                                            api.t(ew), R)
+  _close(result, -(ln(probs[0][2]) * 1. + ln(probs[1][0]) * 1. * 1. +
+                   ln(probs[1][1]) * 1. * 2. + ln(probs[1][2]) * 2. * 3.) / 2.)
+
+  labels = [[1., 2., 1.], [0., 0., 2.], [0., 0., 0.]]
+  lw = [[2.], [1.], [1.]]
+  result = L.SoftmaxLoss(name=None).compute(api.t(labels), api.t(S3),
+                                            api.t(lw), R)
+  _close(result, -(ln(probs[0][0]) * 1. * 2. + ln(probs[0][1]) * 2. * 2. +
+                   ln(probs[0][2]) * 1. * 2. + ln(probs[1][2]) * 2. * 1.) / 2.)
+
+
+def test_softmax_loss_lambda_weights(api):
+  R = api.Reduction.SUM_BY_NONZERO_WEIGHTS
+  L = api.losses_impl
+  labels = [[0., 0., 1.], [0., 0., 2.], [0., 0., 0.]]
+  lw = L.DCGLambdaWeight(rank_discount_fn=api.fns.log1p_inverse)
+  result = L.SoftmaxLoss(name=None, lambda_weight=lw).compute(
+      api.t(labels), api.t(S3), None, R)
+  _close(result, -(ln(_softmax(S3[0])[2]) / ln(1. + 2.) +
+                   ln(_softmax(S3[1])[2]) * 2. / ln(1. + 1.)) / 2.)
+
+
+def test_softmax_loss_invalid_and_mask(api):
+  R = api.Reduction.SUM_BY_NONZERO_WEIGHTS
+  L = api.losses_impl
+  result = L.SoftmaxLoss(name=None).compute(
+      api.t([[0., -1., 1.]]), api.t([[1., 3., 2.]]), None, R)
+  _close(result, -(ln(_softmax([1, 2])[1])))
+  result = L.SoftmaxLoss(name=None).compute(
+      api.t([[0., 1., 1.]]), api.t([[1., 2., 3.]]), None, R,
+      api.t([[True, False, True]], dtype=torch.bool))
+  _close(result, -(ln(_softmax([1, 3])[1])))
+
+
+def test_softmax_zero_and_fully_padded_labels(api):
+  L = api.losses_impl
+  loss_fn = L.SoftmaxLoss(name=None)
+  padded = loss_fn.compute_per_list(api.t([[0., -1.]]), api.t([[0., 0.]]),
+                                    None)[0]
+  single = loss_fn.compute_per_list(api.t([[0.]]), api.t([[0.]]), None)[0]
+  _close(padded, single.detach().cpu())
+  full = loss_fn.compute_per_list(api.t([[-1., -1.]]), api.t([[0., 0.]]),
+                                  None)[0]
+  _close(full, [0.0])
+
+
+# ---------------------------------------------------------------------------
+# ApproxNDCG / ApproxMRR: losses_impl_test.py:1663-1755
+# ---------------------------------------------------------------------------
+A_SCORES = [[1.4, -2.8, -0.4], [0., 1.8, 10.2], [1., 1.2, -3.2]]
+
+
+def test_approx_ndcg_loss(api):
+  L = api.losses_impl
+  labels = [[0., 2., 1.], [1., 0., -1.], [0., 0., 0.]]
+  weights = [[2.], [1.], [1.]]
+  example_weights = [[1., 2., 3.], [4., 5., 6.], [7., 8., 9.]]
+  norm_weights = []
+  for weight, label in zip(example_weights, labels):
+    sum_label = sum(max(0, l) for l in label)
+    norm_weights.append(
+        sum(w * max(0, l) for w, l in zip(weight, label)) /
+        sum_label if sum_label else 0)
+  R = api.Reduction.SUM
+  loss_fn = L.ApproxNDCGLoss(name=None, temperature=0.1)
+  l0 = (1 / (3 / ln(2) + 1 / ln(3))) * (3 / ln(4) + 1 / ln(3))
+  l1 = ln(2) * (1 / ln(3))
+  _close(loss_fn.compute(api.t(labels), api.t(A_SCORES), None, R), -(l0 + l1))
+  _close(loss_fn.compute(api.t(labels), api.t(A_SCORES), api.t(weights), R),
+         -(2 * l0 + 1 * l1))
+  _close(loss_fn.compute(api.t(labels), api.t(A_SCORES),
+                         api.t(example_weights), R),
+         -(norm_weights[0] * l0 + norm_weights[1] * l1))
+
+
+@pytest.mark.parametrize('top_label', [1., 1000.])
+def test_approx_ndcg_loss_mask_and_extreme_labels(api, top_label):
+  L = api.losses_impl
+  loss_fn = L.ApproxNDCGLoss(name=None, temperature=1.)
+  result = loss_fn.compute(
+      api.t([[0., 0., top_label]]), api.t([[1., 3., 2.]]), None,
+      api.Reduction.SUM_BY_NONZERO_WEIGHTS,
+      api.t([[True, False, True]], dtype=torch.bool))
+  approxrank = 1. + 1. / (1. + math.exp(-(1. - 2.)))
+  ndcg = (1. / ln(1. + approxrank)) * ln(1. + 1.)
+  _close(result, -ndcg)
+
+
+def test_approx_mrr_loss(api):
+  L = api.losses_impl
+  labels = [[0., 0., 1.], [1., 0., 1.], [0., 0., 0.]]
+  weights = [[2.], [1.], [1.]]
+  R = api.Reduction.SUM
+  loss_fn = L.ApproxMRRLoss(name=None)
+  _close(loss_fn.compute(api.t(labels), api.t(A_SCORES), None, R),
+         -((1 / 2.) + 1 / 2. * (1 / 3. + 1 / 1.)))
+  _close(loss_fn.compute(api.t(labels), api.t(A_SCORES), api.t(weights), R),
+         -(2 * 1 / 2. + 1 * 1 / 2. * (1 / 3. + 1 / 1.)))
+  loss_fn = L.ApproxMRRLoss(name=None, temperature=1.)
+  result = loss_fn.compute(
+      api.t([[0., 0., 1.]]), api.t([[1., 3., 2.]]), None,
+      api.Reduction.SUM_BY_NONZERO_WEIGHTS,
+      api.t([[True, False, True]], dtype=torch.bool))
+  approxrank = 1. + 1. / (1. + math.exp(-(1. - 2.)))
+  _close(result, -1. / approxrank)
