@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — lists/sec of the LTR training hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): ApproxNDCG loss + 3-layer MLP scorer
+(hidden 256-128-64, relu), B=1024 lists x N=200 items x D=136 features, fp32,
+per GPU (weak scaling across GPUs: every rank steps its own 1024 lists; the
+flat scorer gradient is all-reduced once per step over NCCL).
+
+One "step" = scorer fwd -> loss fwd+bwd -> scorer bwd -> grad all-reduce ->
+Adagrad, on synthetic data.  Prints ONE JSON line:
+  value        whole-job lists/s with inputs resident in HBM (CUDA events, max
+               over ranks, barrier + synchronize on both sides)
+  e2e          same metric through the public API from pinned HOST batches
+               (H2D of every batch + D2H of every loss inside the timed region)
+  roofline     scorer GEMM kernels: algorithmic FLOPs / their measured time
+  cpu_baseline the oracle's CPU step on a bounded sample, same run
+`--impl reference` times the reference algorithm's CPU path (oracle port: the
+reference needs TensorFlow, which cannot be installed here) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+B, N, D = 1024, 200, 136
+HIDDEN = [256, 128, 64]
+LOSS_KEY = 'approx_ndcg_loss'
+LEARNING_RATE = 0.05
+N_RESIDENT = 4     # distinct resident batches cycled so X (111 MB) never sits in L2
+
+
+def make_batch(seed, b=B, n=N, d=D):
+  """Synthetic ELWC-shaped batch: X ~ N(0,1); graded labels 0-4
+  with MSLR-like frequencies; list lengths U[ceil(N/2), N], tail padded with -1."""
+  g = torch.Generator().manual_seed(seed)
+  x = torch.randn(b, n, d, generator=g)
+  probs = torch.tensor([.55, .25, .12, .06, .02])
+  y = torch.multinomial(probs, b * n, replacement=True, generator=g).reshape(
+      b, n).float()
+  lens = torch.randint((n + 1) // 2, n + 1, (b,), generator=g)
+  y = torch.where(torch.arange(n).unsqueeze(0) < lens.unsqueeze(1), y,
+                  torch.full_like(y, -1.))
+  return x, y
+
+
+def mlp_flops_per_list(n=N, d=D, hidden=HIDDEN):
+  """Algorithmic FLOPs of one training step of the scorer per list:
+  forward 2*N*sum(in*out); backward dW for every layer + dH for all but the
+  first layer."""
+  dims = [d] + list(hidden) + [1]
+  fwd = sum(2 * n * dims[i] * dims[i + 1] for i in range(len(dims) - 1))
+  dw = fwd
+  dh = sum(2 * n * dims[i] * dims[i + 1] for i in range(1, len(dims) - 1))
+  return fwd, fwd + dw + dh
+
+
+def load_peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    p = json.load(open(path))
+    return {'hbm_gbs': p['hbm_gbs'], 'bf16_tflops': p['bf16_tflops'],
+            'bf16_tflops_sustained': p.get('bf16_tflops_sustained',
+                                           p['bf16_tflops']),
+            'source': 'measured'}
+  return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0,
+          'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler(threading.Thread):
+  """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+  def __init__(self, index):
+    super().__init__(daemon=True)
+    self.index = index
+    self.stop_flag = threading.Event()
+    self.samples = []
+    self.max_mhz = None
+    self.reasons = set()
+
+  def run(self):
+    q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+             'sw_power_cap']
+    while not self.stop_flag.is_set():
+      try:
+        out = subprocess.run(
+            ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+             '--format=csv,noheader,nounits'], capture_output=True, text=True,
+            timeout=5).stdout.strip().split(',')
+        self.samples.append(float(out[0]))
+        self.max_mhz = float(out[1])
+        for nm, v in zip(names, out[2:]):
+          if v.strip().lower().startswith('active'):
+            self.reasons.add(nm)
+      except Exception:   # nvidia-smi missing / parse error: report nothing
+        pass
+      self.stop_flag.wait(0.1)
+
+  def summary(self):
+    s = sorted(self.samples)
+    return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz,
+            'reasons': sorted(self.reasons), 'samples': len(s)}
+
+
+# ------------------------------------------------------------------------------
+def cpu_reference_step_time(steps, warmup, sample_lists, threads):
+  """Times the oracle's CPU training step on `sample_lists` lists of the workload."""
+  from oracle.train_step import OracleTrainer
+  torch.set_num_threads(threads)
+  tr = OracleTrainer(D, HIDDEN, LOSS_KEY, activation='relu',
+                     learning_rate=LEARNING_RATE)
+  batches = [make_batch(1234 + i, b=sample_lists) for i in range(2)]
+  for i in range(warmup):
+    tr.train_step(*batches[i % 2])
+  t0 = time.perf_counter()
+  for i in range(steps):
+    tr.train_step(*batches[i % 2])
+  dt = time.perf_counter() - t0
+  return dt / steps
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  threads = os.cpu_count() or 1
+  sample = args.cpu_sample_lists
+  ms = cpu_reference_step_time(args.steps, max(args.warmup, 1), sample, threads)
+  value = sample / ms
+  line = {
+      'impl': 'reference', 'metric': 'lists_per_sec', 'value': value,
+      'unit': 'lists/s', 'n_gpus': args.gpus, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': ms * 1e3, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32',
+      'data': 'synthetic',
+      'config': workload_config(args.gpus, extra={
+          'reference_arm': 'oracle port of the tensorflow_ranking CPU path '
+                           '(TensorFlow is not installable offline), torch CPU '
+                           'fp32, [B,N,N] formulation',
+          'sample': '%d lists per step (bounded sample of the %d-list batch; '
+                    'lists are independent so lists/s is additive)' % (sample, B)}),
+      'cpu_baseline': {'value': value, 'unit': 'lists/s', 'cores': threads,
+                       'kind': 'port',
+                       'sample': '%d lists/step x %d steps' % (sample, args.steps)},
+      'e2e': {'value': value, 'unit': 'lists/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, extra=None):
+  cfg = {
+      'workload': 'BASELINE.json configs[1]: approx_ndcg_loss + 3-layer MLP '
+                  'scorer (256-128-64 relu), fp32',
+      'batch_lists_per_gpu': B, 'list_size': N, 'feature_dim': D,
+      'global_batch_lists': B * n_gpus, 'hidden_layer_dims': HIDDEN,
+      'optimizer': 'adagrad', 'parallelism': 'dp%d' % n_gpus,
+      'padding': 'list lengths U[N/2, N], label -1',
+      'l2_policy': 'inputs rotate over %d resident batches (%d MB > 126 MB L2)'
+                   % (N_RESIDENT, N_RESIDENT * B * N * D * 4 // 2**20),
+  }
+  if extra:
+    cfg.update(extra)
+  return cfg
+
+
+def run_gpu(args):
+  import torch.distributed as dist
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  import __graft_entry__ as entry
+  if rank == 0:
+    entry.build()
+  if world > 1:
+    dist.barrier()
+  import ranking_b200 as tfr
+  from ranking_b200 import _C
+
+  tower = tfr.keras.layers.create_tower(HIDDEN, 1, activation='relu',
+                                        use_batch_norm=False, dropout=0,
+                                        input_dim=D, seed=1238,
+                                        precision=args.precision)
+  if world > 1:   # identical replicas
+    dist.broadcast(tower.flat.data, src=0)
+  loss_obj = tfr.keras.losses.get(LOSS_KEY)
+  trainer = tfr.train.RankingTrainer(tower, loss_obj, optimizer='adagrad',
+                                     learning_rate=LEARNING_RATE)
+  host = [make_batch(1234 + 17 * rank + i) for i in range(N_RESIDENT)]
+  resident = [(x.to(dev), y.to(dev)) for x, y in host]
+  stream = torch.cuda.current_stream()
+
+  def sync_all():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize()
+
+  # ---- value: inputs resident, device-timed ----------------------------------
+  for i in range(args.warmup):
+    trainer.train_step(*resident[i % N_RESIDENT])
+  sync_all()
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  launches0 = _C.lib.tfr_launch_count()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ev0.record(stream)
+  for i in range(args.steps):
+    loss = trainer.train_step(*resident[i % N_RESIDENT])
+  ev1.record(stream)
+  sync_all()
+  launches = _C.lib.tfr_launch_count() - launches0
+  ms_total = ev0.elapsed_time(ev1)
+  if rank == 0:
+    sampler.stop_flag.set()
+  t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_step = float(t) / args.steps
+  value = B * world / (ms_step * 1e-3)
+  final_loss = float(loss)
+
+  # ---- per-phase device time (same process, CUDA events on the launch stream) --
+  phase = phase_times(trainer, resident, args.steps, stream)
+
+  # ---- e2e: pinned host batches through the public API --------------------------
+  pinned = [(x.pin_memory(), y.pin_memory()) for x, y in host]
+  pipe = tfr.train.HostBatchPipeline(trainer, B, N, D)
+  pipe.run([pinned[i % N_RESIDENT] for i in range(max(args.warmup, 3))])
+  sync_all()
+  t0 = time.perf_counter()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record(stream)
+  losses = pipe.run([pinned[i % N_RESIDENT] for i in range(args.steps)])
+  e1.record(stream)
+  sync_all()
+  wall = time.perf_counter() - t0
+  e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+  t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  e2e_value = B * world * args.steps / (float(t) * 1e-3)
+
+  if rank == 0:
+    peaks = load_peaks()
+    fwd_fl, step_fl = mlp_flops_per_list()
+    gemm_ms = phase['mlp_fwd_ms'] + phase['mlp_bwd_ms']
+    achieved = step_fl * B / (gemm_ms * 1e-3) / 1e12
+    peak = peaks['bf16_tflops_sustained']
+    loss_bytes = (12 * N + 16) * B
+    line = {
+        'metric': 'lists_per_sec', 'value': value, 'unit': 'lists/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'fp32' if args.precision == 'fp32' else args.precision,
+        'data': 'synthetic',
+        'config': workload_config(world, extra={'scorer_precision': args.precision,
+                                                'final_loss': final_loss}),
+        'roofline': {
+            'kernel': 'scorer tower GEMMs (tfr_mlp_fwd + tfr_mlp_bwd)',
+            'bound': 'tensor', 'achieved': achieved, 'peak': peak,
+            'unit': 'TFLOP/s', 'frac': achieved / peak,
+            'peak_source': peaks['source'] + ' bf16 sustained',
+            'traffic': None,
+            'algorithmic_flops_per_step': step_fl * B,
+            'kernel_ms_per_step': gemm_ms,
+        },
+        'roofline_loss': {
+            'kernel': 'approx_loss_kernel', 'bound': 'hbm',
+            'achieved': loss_bytes / (phase['loss_ms'] * 1e-3) / 1e9,
+            'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+            'frac': loss_bytes / (phase['loss_ms'] * 1e-3) / 1e9 / peaks['hbm_gbs'],
+            'pair_evals_per_s': 2.0 * N * N * B / (phase['loss_ms'] * 1e-3),
+            'kernel_ms_per_step': phase['loss_ms'],
+        },
+        'phases_ms': phase,
+        'e2e': {'value': e2e_value, 'unit': 'lists/s',
+                'h2d_bytes_per_step': pipe.h2d_bytes,
+                'd2h_bytes_per_step': pipe.d2h_bytes,
+                'ms_per_step': float(t) / args.steps,
+                'last_loss': losses[-1]},
+        'gpu_launches': int(launches),
+        'clocks': sampler.summary(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+      threads = os.cpu_count() or 1
+      sample = args.cpu_sample_lists
+      ms = cpu_reference_step_time(args.cpu_steps, 1, sample, threads)
+      line['cpu_baseline'] = {
+          'value': sample / ms, 'unit': 'lists/s', 'cores': threads,
+          'kind': 'port',
+          'sample': '%d lists/step x %d steps of the same workload (oracle: '
+                    'torch-CPU restatement of the reference algorithm)' %
+                    (sample, args.cpu_steps)}
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def phase_times(trainer, resident, steps, stream):
+  """Average device time of each C-ABI call of the step, by CUDA events recorded
+  on the launching stream around every call (same process as the timed run)."""
+  import ctypes
+  from ranking_b200 import _C
+  t = trainer.tower
+  names = ['mlp_fwd_ms', 'loss_ms', 'mlp_bwd_ms', 'opt_ms']
+  acc = dict.fromkeys(names, 0.0)
+  steps = max(3, min(steps, 20))
+  for i in range(steps):
+    x, y = resident[i % len(resident)]
+    b, n, d = x.shape
+    m = b * n
+    trainer._ensure(b, n)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    st = _C.stream()
+    cfg = ctypes.byref(t._cfg)
+    evs[0].record(stream)
+    _C.check(_C.lib.tfr_mlp_fwd(_C.ptr(x), m, cfg, _C.ptr(t.flat.data), None,
+                                _C.ptr(trainer.ws), _C.ptr(trainer.scores),
+                                t._precision, st))
+    evs[1].record(stream)
+    trainer.loss.fused_fwd_bwd(y, trainer.scores, None, trainer.dscores,
+                               trainer.per_list, trainer.total2)
+    evs[2].record(stream)
+    _C.check(_C.lib.tfr_mlp_bwd(_C.ptr(x), m, cfg, _C.ptr(t.flat.data),
+                                _C.ptr(trainer.dscores), None, _C.ptr(trainer.ws),
+                                _C.ptr(trainer.grads), t._precision, st))
+    evs[3].record(stream)
+    _C.check(_C.lib.tfr_optimizer_step(
+        _C.ptr(t.flat.data), _C.ptr(trainer.grads), _C.ptr(trainer.accum),
+        trainer.grads.numel(), trainer.opt_kind, trainer.lr, trainer.eps, 1.0, st))
+    evs[4].record(stream)
+    torch.cuda.synchronize()
+    for k, nm in enumerate(names):
+      acc[nm] += evs[k].elapsed_time(evs[k + 1])
+  return {k: v / steps for k, v in acc.items()}
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=5)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--precision', default='fp32',
+                  choices=['fp32', 'tf32x3', 'tf32', 'bf16'])
+  ap.add_argument('--cpu-sample-lists', type=int, default=256)
+  ap.add_argument('--cpu-steps', type=int, default=5)
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3)
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_gpu(args)
+
+
+if __name__ == '__main__':
+  main()

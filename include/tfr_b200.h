@@ -1,0 +1,236 @@
+/*
+ * tfr_b200.h — C ABI of the B200-native learning-to-rank hot path.
+ *
+ * The reference (tensorflow/ranking) has no FFI: its seam is the Python class
+ * surface `tfr.keras.losses / tfr.keras.metrics / tfr.keras.model`
+ * (SURVEY.md §8b).  This header is the C boundary a replacement for that path
+ * binds to; `ranking_b200/_C.py` is the ctypes binding, and INTEGRATION.md shows
+ * the stub a tensorflow_ranking maintainer would add.  Each entry point cites
+ * the reference code it replaces (paths relative to tensorflow_ranking/python/).
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller unless the
+ *     name ends in `_host`; the library never allocates or frees caller memory
+ *   - config structs are HOST pointers, read during the call
+ *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered,
+ *     re-entrant and keep no global state besides the last-error string
+ *   - return value: 0 on success, a tfr_status otherwise; tfr_last_error() gives
+ *     the message (argument errors map to Python ValueError, as the reference
+ *     raises for bad keys / shapes: keras/losses.py:108-109, losses_impl.py:52-58)
+ *   - scores/labels/weights are row-major fp32 [B, N]; a label < 0 marks padding
+ *     (utils.py:78-81) unless an explicit `mask` (uint8, 1 = valid) is given
+ */
+#ifndef TFR_B200_H_
+#define TFR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  TFR_OK = 0,
+  TFR_INVALID_ARGUMENT = 1,
+  TFR_UNSUPPORTED = 2,
+  TFR_CUDA_ERROR = 3
+} tfr_status;
+
+/* phi of the pairwise family: losses_impl.py:933-998 */
+typedef enum {
+  TFR_PHI_LOGISTIC = 0,      /* PairwiseLogisticLoss  :933-940 */
+  TFR_PHI_HINGE = 1,         /* PairwiseHingeLoss     :943-948 */
+  TFR_PHI_SOFT_ZERO_ONE = 2, /* PairwiseSoftZeroOneLoss :951-958 */
+  TFR_PHI_MSE = 3            /* PairwiseMSELoss       :961-998 */
+} tfr_phi;
+
+/* LambdaWeight family: losses_impl.py:170-454 */
+typedef enum {
+  TFR_LAMBDA_NONE = 0,
+  TFR_LAMBDA_LABEL_DIFF = 1, /* :210-216 */
+  TFR_LAMBDA_DCG = 2,        /* :299-369 (NDCG = normalized) */
+  TFR_LAMBDA_DCG_V2 = 3,     /* :372-394 */
+  TFR_LAMBDA_YETI = 4,       /* :397-407 */
+  TFR_LAMBDA_PRECISION = 5   /* :410-454 */
+} tfr_lambda_kind;
+
+/* gain functions: keras/utils.py:50-91 */
+typedef enum {
+  TFR_GAIN_IDENTITY = 0,
+  TFR_GAIN_POW2_MINUS_1 = 1,
+  TFR_GAIN_TABLE = 2         /* caller supplies gain_fn(cleaned labels) [B, N] */
+} tfr_gain_fn;
+
+/* rank discount functions: keras/utils.py:65-107, losses_impl.py:111 */
+typedef enum {
+  TFR_DISC_INVERSE = 0,       /* divide_no_nan(1, r) */
+  TFR_DISC_LOG2_INVERSE = 1,  /* ln2 / ln(1 + r) */
+  TFR_DISC_LOG1P_INVERSE = 2, /* 1 / ln(1 + r) */
+  TFR_DISC_TABLE = 3          /* caller supplies disc[r], r = 0 .. N+1 */
+} tfr_disc_fn;
+
+typedef struct {
+  int32_t kind;            /* tfr_lambda_kind */
+  int32_t topn;            /* <= 0 means list_size */
+  int32_t gain_fn;         /* tfr_gain_fn; for PRECISION: table = positive_fn(labels) or
+                              IDENTITY meaning labels >= 1 */
+  int32_t disc_fn;         /* tfr_disc_fn */
+  int32_t normalized;      /* multiply gains by inverse_max_dcg (:261-266) */
+  float smooth_fraction;   /* alpha of :365-367 */
+  const float* gain_table; /* device [B, N] or NULL */
+  const float* disc_table; /* device [N + 2] or NULL */
+} tfr_lambda_cfg;
+
+const char* tfr_last_error(void);
+int tfr_version(void);
+/* number of CUDA kernels this library has launched so far in this process */
+unsigned long long tfr_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * K1  pairwise loss family, fused forward + backward, one CTA per list.
+ * Replaces _PairwiseLoss._compute_unreduced_loss_impl and everything under it
+ * (losses_impl.py:61-74, 483-537, 863-998) plus the LambdaWeight pair weights
+ * (:170-454) without materialising any [B, N, N] tensor.
+ *   W_ij = [l_i > l_j] valid_i valid_j lambda_ij w_i           (constant)
+ *   loss_sum[b] = sum_ij W_ij phi((s_i - s_j)/T),  w_sum[b] = sum_ij W_ij,
+ *   nnz[b] = #{W_ij != 0},  row_loss[b,i] = sum_j W_ij phi(.),
+ *   grad[b,k] = grad_scale * d loss_sum[b] / d s_k
+ * item_w: NULL, or [B, N] (w_per_item = 1), or [B] per-list (w_per_item = 0).
+ * Any output pointer except loss_sum may be NULL.
+ * ------------------------------------------------------------------------- */
+int tfr_pairwise_loss_fwd_bwd(const float* scores, const float* labels,
+                              const float* item_w, int w_per_item,
+                              const uint8_t* mask, int B, int N,
+                              float temperature, int phi,
+                              const tfr_lambda_cfg* lam_host, float grad_scale,
+                              float* grad, float* row_loss, float* loss_sum,
+                              float* w_sum, float* nnz, int32_t* ranks_out,
+                              void* stream);
+
+/* Parity helper: materialise lambda pair weights [B, N, N] for given ranks
+ * (_LambdaWeight.pair_weights, losses_impl.py:181-193).  Small N only. */
+int tfr_lambda_pair_weights(const float* labels, const int32_t* ranks, int B,
+                            int N, const tfr_lambda_cfg* lam_host, float* out,
+                            void* stream);
+
+/* 1-based ranks of scores, descending, ties by index, invalid entries last
+ * (losses_impl.py:483-500 + utils.py:167-195 with shuffle_ties=False). */
+int tfr_sorted_ranks(const float* scores, const float* labels,
+                     const uint8_t* mask, int B, int N, int32_t* ranks,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K2  ApproxNDCG (mode 0) / ApproxMRR (mode 1), fused forward + backward.
+ * Replaces approx_ranks, ndcg, inverse_max_dcg, _safe_default_gain_fn and the
+ * two loss classes (losses_impl.py:33-49, 77-167, 1579-1632).
+ *   loss[b]   = -ndcg_b (or -mrr_b)                       (unweighted)
+ *   weight[b] = [sum l > 0] * (item_w ? sum(w l)/sum(l) : 1)   (:1004-1015,1602)
+ *   grad[b,k] = grad_scale * (scale_by_weight ? weight[b] : 1) * d loss[b]/d s_k
+ * ------------------------------------------------------------------------- */
+int tfr_approx_loss_fwd_bwd(const float* scores, const float* labels,
+                            const float* item_w, int w_per_item,
+                            const uint8_t* mask, int B, int N,
+                            float temperature, int mode, float grad_scale,
+                            int scale_by_weight, float* grad, float* loss,
+                            float* weight, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K3  Softmax loss, fused forward + backward (losses_impl.py:1119-1197, with
+ * DCGLambdaWeight.individual_weights :281-296 when lam_host->kind == DCG).
+ *   loss[b] = xent(l'/sum l', s/T masked to ln 1e-10), weight[b] = sum l'
+ *   where l' = (lambda individual weight or label) * item weight
+ * ------------------------------------------------------------------------- */
+int tfr_softmax_loss_fwd_bwd(const float* scores, const float* labels,
+                             const float* item_w, int w_per_item,
+                             const uint8_t* mask, int B, int N,
+                             float temperature, const tfr_lambda_cfg* lam_host,
+                             float grad_scale, int scale_by_weight, float* grad,
+                             float* loss, float* weight, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K4  NDCG@k and MRR@k for several cut-offs in one launch; per-list shared-memory
+ * bitonic sort, ties by index, invalid entries last.  Replaces
+ * metrics_impl.py:63-151, 228-266, 429-459, 631-670 and utils.py:115-164.
+ *   topns_host[n_topn]: cut-offs (<= 0 means list_size)
+ *   ndcg/mrr: [B, n_topn];  ndcg_w / mrr_w: [B] per-list weights after the
+ *   batch-average rule of metrics_impl.py:63-119 (single-process batch);
+ *   raw: [B, 5] = {sum w, sum w*gain, sum gain, sum w*rel, sum rel} per list,
+ *   rel = [label >= 1] — required scratch; data-parallel callers all-reduce the
+ *   batch statistics derived from it (the rule couples lists across ranks)
+ * gain_fn / disc_fn as above (tables: gain_table [B,N] of cleaned labels,
+ * disc_table [N+2]).  Any of ndcg/mrr may be NULL.
+ * ------------------------------------------------------------------------- */
+int tfr_rank_metrics(const float* scores, const float* labels,
+                     const float* item_w, int w_per_item, const uint8_t* mask,
+                     int B, int N, const int32_t* topns_host, int n_topn,
+                     int gain_fn, int disc_fn, const float* gain_table,
+                     const float* disc_table, float* ndcg, float* ndcg_w,
+                     float* mrr, float* mrr_w, float* raw, void* stream);
+
+/* out2[0] = scale * sum_i v[i] * (w ? w[i] : 1); out2[1] = sum_i (w ? w[i] : 1).
+ * Deterministic single-CTA reduction (Keras Mean state / loss reduction). */
+int tfr_weighted_sum(const float* v, const float* w, int n, float scale,
+                     float* out2, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K5/K6  scorer tower: create_tower (keras/layers.py:26-77) over the flattened
+ * [M = B*N, D] matrix + RestoreList fill (keras/layers.py:231-265).
+ * Parameters live in ONE flat fp32 buffer (so data-parallel training needs a
+ * single all-reduce): for each Dense i: W_i [in, out] row-major (Keras kernel
+ * layout) then b_i [out].  Gradients use the same layout.
+ * precision: how the GEMMs are evaluated
+ *   TFR_PREC_FP32   fp32 CUDA-core FFMA
+ *   TFR_PREC_TF32X3 tcgen05 kind::tf32, 3-pass error-compensated split (~fp32)
+ *   TFR_PREC_TF32   tcgen05 kind::tf32, 1 pass
+ *   TFR_PREC_BF16   tcgen05 kind::f16 (bf16 operands, fp32 accumulate)
+ * ------------------------------------------------------------------------- */
+typedef enum {
+  TFR_PREC_FP32 = 0,
+  TFR_PREC_TF32X3 = 1,
+  TFR_PREC_TF32 = 2,
+  TFR_PREC_BF16 = 3
+} tfr_precision;
+
+typedef enum { TFR_ACT_NONE = 0, TFR_ACT_RELU = 1 } tfr_activation;
+
+#define TFR_MLP_MAX_LAYERS 8
+
+typedef struct {
+  int32_t n_dense;                        /* Dense layers incl. the output one */
+  int32_t dims[TFR_MLP_MAX_LAYERS + 1];   /* dims[0] = D, dims[i] = units of Dense i */
+  int32_t activation;                     /* tfr_activation, hidden layers */
+} tfr_mlp_cfg;
+
+size_t tfr_mlp_param_count(const tfr_mlp_cfg* cfg);
+/* bytes of caller-provided workspace that carries activations from fwd to bwd */
+size_t tfr_mlp_workspace_bytes(const tfr_mlp_cfg* cfg, int M);
+
+/* scores_out [M, dims[n_dense]]; if mask (uint8 [M]) is given and the output
+ * width is 1, masked-out rows are set to ln(1e-10) (RestoreList). */
+int tfr_mlp_fwd(const float* X, int M, const tfr_mlp_cfg* cfg,
+                const float* params, const uint8_t* mask, void* workspace,
+                float* scores_out, int precision, void* stream);
+
+/* dscores [M, dims[n_dense]] -> grads (flat, same layout as params).
+ * Must follow a tfr_mlp_fwd on the same X / workspace. */
+int tfr_mlp_bwd(const float* X, int M, const tfr_mlp_cfg* cfg,
+                const float* params, const float* dscores, const uint8_t* mask,
+                void* workspace, float* grads, int precision, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Fused optimizer over the flat parameter buffer (the reference delegates to
+ * tf.keras.optimizers; Adagrad is what its examples use:
+ * examples/tf_ranking_libsvm.py:386-387).  grad_scale multiplies the gradient
+ * first (1/world_size for data parallel, extension/task.py:259).
+ *   kind 0: SGD          p -= lr * g
+ *   kind 1: Adagrad      a += g^2; p -= lr * g / (sqrt(a) + eps)   (Keras form)
+ * ------------------------------------------------------------------------- */
+int tfr_optimizer_step(float* params, const float* grads, float* accum, size_t n,
+                       int kind, float lr, float eps, float grad_scale,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* TFR_B200_H_ */

@@ -1,0 +1,162 @@
+// C-ABI glue: error string, scorer-tower dispatch, fused optimizer.
+#include <cstring>
+
+#include "common.cuh"
+#include "mlp.h"
+
+namespace tfr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int make_mlp_plan(const tfr_mlp_cfg* cfg, int M, MlpPlan* p) {
+  TFR_REQUIRE(cfg != nullptr, "cfg must not be NULL");
+  TFR_REQUIRE(cfg->n_dense >= 1 && cfg->n_dense <= TFR_MLP_MAX_LAYERS,
+              "n_dense %d must be in [1, %d]", cfg->n_dense, TFR_MLP_MAX_LAYERS);
+  TFR_REQUIRE(M >= 0, "M must be >= 0");
+  TFR_REQUIRE(cfg->activation == TFR_ACT_NONE || cfg->activation == TFR_ACT_RELU,
+              "activation %d unsupported", cfg->activation);
+  for (int i = 0; i <= cfg->n_dense; ++i)
+    TFR_REQUIRE(cfg->dims[i] >= 1, "dims[%d] = %d must be >= 1", i, cfg->dims[i]);
+  const int L = cfg->n_dense - 1;
+  TFR_REQUIRE(cfg->dims[L] <= 1024, "width %d feeding the output layer exceeds 1024", cfg->dims[L]);
+  TFR_REQUIRE(cfg->dims[L + 1] <= 8, "output_units %d exceeds 8", cfg->dims[L + 1]);
+  std::memset(p, 0, sizeof(*p));
+  p->n_dense = cfg->n_dense;
+  p->activation = cfg->activation;
+  size_t off = 0, max_wb = 0;
+  int max_hidden = 1;
+  for (int d = 0; d <= cfg->n_dense; ++d) p->dims[d] = cfg->dims[d];
+  for (int d = 0; d < cfg->n_dense; ++d) {
+    p->w_off[d] = off;
+    off += (size_t)p->dims[d] * p->dims[d + 1];
+    p->b_off[d] = off;
+    off += p->dims[d + 1];
+    const size_t wb = (size_t)p->dims[d] * p->dims[d + 1] + p->dims[d + 1];
+    if (wb > max_wb) max_wb = wb;
+    if (d < L && p->dims[d + 1] > max_hidden) max_hidden = p->dims[d + 1];
+  }
+  p->n_params = off;
+  // workspace
+  size_t w = 0;
+  for (int d = 0; d < L; ++d) {
+    p->act_off[d] = w;
+    w += align_up((size_t)M * p->dims[d + 1], 64);
+  }
+  for (int i = 0; i < 2; ++i) {
+    p->dz_off[i] = w;
+    w += align_up((size_t)M * max_hidden, 64);
+  }
+  p->rows_per_split = 2048;
+  p->splits = M > 0 ? (M + p->rows_per_split - 1) / p->rows_per_split : 1;
+  p->partial_stride = align_up(max_wb, 64);
+  p->partial_off = w;
+  w += (size_t)p->splits * p->partial_stride;
+  p->ws_floats = w;
+  return TFR_OK;
+}
+
+__global__ void __launch_bounds__(256)
+optimizer_kernel(float* __restrict__ params, const float* __restrict__ grads,
+                 float* __restrict__ accum, size_t n, int kind, float lr, float eps,
+                 float grad_scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float g = grads[i] * grad_scale;
+  if (kind == 0) {
+    params[i] -= lr * g;
+  } else {
+    // tf.keras.optimizers.Adagrad: accum += g^2; var -= lr * g / (sqrt(accum) + eps)
+    const float a = accum[i] + g * g;
+    accum[i] = a;
+    params[i] -= lr * g / (sqrtf(a) + eps);
+  }
+}
+
+}  // namespace tfr
+
+using namespace tfr;
+
+extern "C" const char* tfr_last_error(void) { return g_err; }
+extern "C" int tfr_version(void) { return 1; }
+extern "C" unsigned long long tfr_launch_count(void) {
+  return __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+}
+
+extern "C" size_t tfr_mlp_param_count(const tfr_mlp_cfg* cfg) {
+  MlpPlan p;
+  if (make_mlp_plan(cfg, 0, &p)) return 0;
+  return p.n_params;
+}
+
+extern "C" size_t tfr_mlp_workspace_bytes(const tfr_mlp_cfg* cfg, int M) {
+  MlpPlan p;
+  if (make_mlp_plan(cfg, M, &p)) return 0;
+  return p.ws_floats * sizeof(float) + 256;
+}
+
+static float* ws_base(void* workspace) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(workspace);
+  a = (a + 255) & ~(uintptr_t)255;
+  return reinterpret_cast<float*>(a);
+}
+
+extern "C" int tfr_mlp_fwd(const float* X, int M, const tfr_mlp_cfg* cfg,
+                           const float* params, const uint8_t* mask, void* workspace,
+                           float* scores_out, int precision, void* stream) {
+  MlpPlan p;
+  int rc = make_mlp_plan(cfg, M, &p);
+  if (rc) return rc;
+  TFR_REQUIRE(X && params && workspace && scores_out, "NULL argument");
+  if (M == 0) return TFR_OK;
+  switch (precision) {
+    case TFR_PREC_FP32:
+      return mlp_simt_fwd(X, M, p, params, mask, ws_base(workspace), scores_out,
+                          (cudaStream_t)stream);
+    default:
+      set_error("precision %d is not available in this build", precision);
+      return TFR_UNSUPPORTED;
+  }
+}
+
+extern "C" int tfr_mlp_bwd(const float* X, int M, const tfr_mlp_cfg* cfg,
+                           const float* params, const float* dscores, const uint8_t* mask,
+                           void* workspace, float* grads, int precision, void* stream) {
+  MlpPlan p;
+  int rc = make_mlp_plan(cfg, M, &p);
+  if (rc) return rc;
+  TFR_REQUIRE(X && params && workspace && dscores && grads, "NULL argument");
+  if (M == 0) return TFR_OK;
+  switch (precision) {
+    case TFR_PREC_FP32:
+      return mlp_simt_bwd(X, M, p, params, dscores, mask, ws_base(workspace), grads,
+                          (cudaStream_t)stream);
+    default:
+      set_error("precision %d is not available in this build", precision);
+      return TFR_UNSUPPORTED;
+  }
+}
+
+extern "C" int tfr_optimizer_step(float* params, const float* grads, float* accum, size_t n,
+                                  int kind, float lr, float eps, float grad_scale,
+                                  void* stream) {
+  TFR_REQUIRE(params && grads, "NULL argument");
+  TFR_REQUIRE(kind == 0 || kind == 1, "optimizer kind %d unsupported", kind);
+  TFR_REQUIRE(kind == 0 || accum != nullptr, "Adagrad needs an accumulator");
+  if (n == 0) return TFR_OK;
+  optimizer_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      params, grads, accum, n, kind, lr, eps, grad_scale);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}

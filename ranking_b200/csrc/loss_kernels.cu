@@ -1,0 +1,776 @@
+// K1 / K2 / K3: fused forward+backward loss kernels, one CTA per list.
+//
+// Each list's scores, labels and weights are staged once into shared memory;
+// every O(N^2) pairwise quantity the reference materialises as a [B, N, N]
+// tensor (losses_impl.py:61-64) exists only in registers here.  A warp owns a
+// row k and its lanes stride over the partners j; the per-item gradient is
+// reduced with warp shuffles.  Each unordered pair is visited from both of its
+// ends, so no scatter/atomic is needed and results are deterministic.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace tfr {
+
+constexpr int kLossThreads = 256;
+constexpr int kMaxListSize = 8192;
+
+struct LamDev {
+  int kind, topn, gain_fn, disc_fn, normalized;
+  float alpha;
+  const float* gain_table;
+  const float* disc_table;
+};
+
+static LamDev make_lam(const tfr_lambda_cfg* h) {
+  LamDev d;
+  if (h == nullptr) {
+    d = LamDev{TFR_LAMBDA_NONE, 0, 0, 0, 0, 0.f, nullptr, nullptr};
+  } else {
+    d = LamDev{h->kind, h->topn, h->gain_fn, h->disc_fn, h->normalized,
+               h->smooth_fraction, h->gain_table, h->disc_table};
+  }
+  return d;
+}
+
+static int check_lam(const tfr_lambda_cfg* h) {
+  if (h == nullptr) return TFR_OK;
+  TFR_REQUIRE(h->kind >= TFR_LAMBDA_NONE && h->kind <= TFR_LAMBDA_PRECISION,
+              "lambda kind %d is not a tfr_lambda_kind", h->kind);
+  TFR_REQUIRE(h->smooth_fraction >= 0.f && h->smooth_fraction <= 1.f,
+              "smooth_fraction %g should be in range [0, 1].", h->smooth_fraction);
+  TFR_REQUIRE(h->gain_fn >= 0 && h->gain_fn <= TFR_GAIN_TABLE, "bad gain_fn %d", h->gain_fn);
+  TFR_REQUIRE(h->disc_fn >= 0 && h->disc_fn <= TFR_DISC_TABLE, "bad disc_fn %d", h->disc_fn);
+  TFR_REQUIRE(h->gain_fn != TFR_GAIN_TABLE || h->gain_table != nullptr,
+              "gain_fn TABLE needs gain_table");
+  TFR_REQUIRE(h->disc_fn != TFR_DISC_TABLE || h->disc_table != nullptr,
+              "disc_fn TABLE needs disc_table");
+  return TFR_OK;
+}
+
+__host__ __device__ inline bool lam_needs_rank(int kind) {
+  return kind >= TFR_LAMBDA_DCG;
+}
+
+// Shared-memory view of one list.
+struct ListView {
+  float* z;     // [N] logits / temperature
+  float* l;     // [N] raw labels
+  float* w;     // [N] row-item weight (0 where the label is invalid)
+  float* g;     // [N] lambda gains
+  float* disc;  // [N + 2] rank discount table, disc[r] = d(r)
+  int* rank;    // [N] 1-based ranks
+  float* red;   // [32] reduction scratch
+  unsigned char* mv;  // [N] valid per mask (or label >= 0)
+  unsigned char* lv;  // [N] label >= 0
+};
+
+__host__ __device__ inline size_t list_smem_bytes(int N) {
+  return (size_t)(4 * N + (N + 2) + N + 32) * 4 + 2 * (size_t)N + 16;
+}
+
+__device__ inline ListView carve(unsigned char* base, int N) {
+  ListView v;
+  float* f = reinterpret_cast<float*>(base);
+  v.z = f; f += N;
+  v.l = f; f += N;
+  v.w = f; f += N;
+  v.g = f; f += N;
+  v.disc = f; f += N + 2;
+  v.rank = reinterpret_cast<int*>(f); f += N;
+  v.red = f; f += 32;
+  v.mv = reinterpret_cast<unsigned char*>(f);
+  v.lv = v.mv + N;
+  return v;
+}
+
+// rank_i = 1 + #{j that precede i}, where j precedes i if it is valid and i is not,
+// or (same validity) s_j > s_i, or s_j == s_i and j < i.  The reference gives
+// invalid entries the score zmin - 1e-6 (losses_impl.py:497-499) so that they
+// sort last; in fp32 that sentinel can be absorbed (|zmin| >= 16) and then ties
+// with the worst valid item are broken randomly.  Here invalid entries are
+// strictly last and ties are broken by index (shuffle_ties=False semantics).
+__device__ inline void compute_ranks(const ListView& v, int N, float /*zmin*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  for (int i = warp; i < N; i += nwarps) {
+    const bool vi = v.mv[i];
+    const float si = v.z[i];
+    int cnt = 0;
+    for (int j = lane; j < N; j += 32) {
+      const bool vj = v.mv[j];
+      const float sj = v.z[j];
+      bool before;
+      if (vi != vj) before = vj;
+      else if (!vi) before = j < i;
+      else before = (sj > si) || (sj == si && j < i);
+      cnt += before;
+    }
+    cnt = warp_sum_int(cnt);
+    if (lane == 0) v.rank[i] = cnt + 1;
+  }
+}
+
+// sum_{k <= topn} gain(l_(k)) * disc(k) over labels sorted descending
+// (inverse_max_dcg, losses_impl.py:109-134); `gain` holds per-item gains of the
+// cleaned labels `cl`.  Returns the sum to every thread.
+template <typename DiscFn>
+__device__ inline float ideal_dcg(const float* cl, const float* gain, int N,
+                                  int topn, float* red, DiscFn disc) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  float part = 0.f;
+  for (int i = warp; i < N; i += nwarps) {
+    const float li = cl[i];
+    int cnt = 0;
+    for (int j = lane; j < N; j += 32) {
+      const float lj = cl[j];
+      cnt += (lj > li) || (lj == li && j < i);
+    }
+    cnt = warp_sum_int(cnt);
+    if (lane == 0 && cnt + 1 <= topn) part += gain[i] * disc(cnt + 1);
+  }
+  return block_sum(part, red);
+}
+
+template <int LAM>
+__device__ __forceinline__ float pair_lambda(const LamDev& lam, const ListView& v,
+                                             int N, int topn, int i, int j) {
+  if (LAM == TFR_LAMBDA_NONE) return 1.f;
+  if (LAM == TFR_LAMBDA_LABEL_DIFF) return fabsf(v.l[i] - v.l[j]);
+  if (!(v.lv[i] && v.lv[j])) return 0.f;
+  const int ri = v.rank[i], rj = v.rank[j];
+  const float dg = fabsf(v.g[i] - v.g[j]);
+  if (LAM == TFR_LAMBDA_PRECISION) {
+    return ((ri <= topn) != (rj <= topn)) ? dg : 0.f;
+  }
+  const int d = ri > rj ? ri - rj : rj - ri;
+  float pd;
+  if (LAM == TFR_LAMBDA_DCG) {
+    const bool in_top = (ri <= topn) || (rj <= topn);
+    const float u = (d > 0 && in_top) ? fabsf(v.disc[d] - v.disc[d + 1]) : 0.f;
+    const float di = ri > topn ? 0.f : v.disc[ri];
+    const float dj = rj > topn ? 0.f : v.disc[rj];
+    pd = (1.f - lam.alpha) * u + lam.alpha * fabsf(di - dj);
+    if (!in_top) pd = 0.f;
+  } else {  // V2 / YETI
+    const int mx = ri > rj ? ri : rj;
+    const float mult = mx > topn ? 1.f / (1.f - v.disc[mx]) : 1.f;
+    pd = d > 0 ? fabsf(v.disc[d] - v.disc[d + 1]) * mult : 0.f;
+    if (LAM == TFR_LAMBDA_YETI && d != 1) pd = 0.f;
+  }
+  return dg * pd * (float)N;
+}
+
+// Fill disc table, gains (and inverse max DCG normalisation) for a lambda.
+__device__ inline void setup_lambda(const LamDev& lam, const ListView& v, int b,
+                                    int N, int tid) {
+  if (!lam_needs_rank(lam.kind)) return;
+  for (int r = tid; r < N + 2; r += blockDim.x)
+    v.disc[r] = lam.disc_fn == TFR_DISC_TABLE ? lam.disc_table[r]
+                                              : disc_of(lam.disc_fn, (float)r);
+  for (int i = tid; i < N; i += blockDim.x) {
+    const float cl = v.lv[i] ? v.l[i] : 0.f;
+    float g;
+    if (lam.gain_fn == TFR_GAIN_TABLE) g = lam.gain_table[(size_t)b * N + i];
+    else if (lam.kind == TFR_LAMBDA_PRECISION) g = cl >= 1.f ? 1.f : 0.f;
+    else g = gain_of(lam.gain_fn, cl);
+    v.g[i] = g;
+  }
+  __syncthreads();
+  if (lam.normalized && lam.kind != TFR_LAMBDA_PRECISION) {
+    // cleaned labels are needed for the ideal ordering; reuse rank[] as scratch
+    // is not possible (ranks may already be there), so recompute cl on the fly
+    // through a small lambda over v.l / v.lv.
+    const int topn = lam.topn > 0 ? min(lam.topn, N) : N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    float part = 0.f;
+    for (int i = warp; i < N; i += nwarps) {
+      const float li = v.lv[i] ? v.l[i] : 0.f;
+      int cnt = 0;
+      for (int j = lane; j < N; j += 32) {
+        const float lj = v.lv[j] ? v.l[j] : 0.f;
+        cnt += (lj > li) || (lj == li && j < i);
+      }
+      cnt = warp_sum_int(cnt);
+      if (lane == 0 && cnt + 1 <= topn) part += v.g[i] * v.disc[cnt + 1];
+    }
+    const float s = block_sum(part, v.red);
+    const float inv = s > 0.f ? 1.f / s : 0.f;
+    for (int i = tid; i < N; i += blockDim.x) v.g[i] *= inv;
+    __syncthreads();
+  }
+}
+
+// Load one list into shared memory.  Returns the row minimum of z (all entries).
+__device__ inline float load_list(const ListView& v, const float* scores,
+                                  const float* labels, const float* item_w,
+                                  int w_per_item, const uint8_t* mask, int b,
+                                  int N, float temperature) {
+  float zmin = CUDART_INF_F;
+  const size_t off = (size_t)b * N;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const float z = scores[off + i] / temperature;
+    const float lab = labels[off + i];
+    const bool lvalid = lab >= 0.f;
+    const bool mvalid = mask ? (mask[off + i] != 0) : lvalid;
+    float wv = 1.f;
+    if (item_w) wv = w_per_item ? item_w[off + i] : item_w[b];
+    v.z[i] = z;
+    v.l[i] = lab;
+    v.w[i] = lvalid ? wv : 0.f;
+    v.mv[i] = mvalid;
+    v.lv[i] = lvalid;
+    zmin = fminf(zmin, z);
+  }
+  zmin = block_min(zmin, v.red);  // includes the barrier that publishes the loads
+  return zmin;
+}
+
+// ---------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------
+template <int PHI>
+__device__ __forceinline__ void phi_eval(float x, float& f, float& df) {
+  if (PHI == TFR_PHI_LOGISTIC) {
+    // relu(-x) + log1p(exp(-|x|)); d/dx = -sigmoid(-x)   (losses_impl.py:936-940)
+    const float e = expf(-fabsf(x));
+    f = fmaxf(-x, 0.f) + log1pf(e);
+    df = -(x >= 0.f ? e / (1.f + e) : 1.f / (1.f + e));
+  } else if (PHI == TFR_PHI_HINGE) {
+    const float m = 1.f - x;  // relu(1 - x)            (losses_impl.py:946-948)
+    f = fmaxf(m, 0.f);
+    df = m > 0.f ? -1.f : 0.f;
+  } else {
+    // sigmoid(-x); d/dx = -sigmoid(x) sigmoid(-x)       (losses_impl.py:954-958)
+    const float e = expf(-fabsf(x));
+    const float inv = 1.f / (1.f + e);
+    f = x > 0.f ? e * inv : inv;
+    df = -e * inv * inv;
+  }
+}
+
+template <int PHI, int LAM>
+__global__ void __launch_bounds__(kLossThreads)
+pairwise_loss_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                     const float* __restrict__ item_w, int w_per_item,
+                     const uint8_t* __restrict__ mask, int N, float temperature,
+                     LamDev lam, float grad_scale, float* __restrict__ grad,
+                     float* __restrict__ row_loss, float* __restrict__ loss_sum,
+                     float* __restrict__ w_sum, float* __restrict__ nnz,
+                     int32_t* __restrict__ ranks_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ListView v = carve(smem_raw, N);
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+  const float zmin = load_list(v, scores, labels, item_w, w_per_item, mask, b, N,
+                               temperature);
+  const bool need_rank = lam_needs_rank(LAM) || ranks_out != nullptr;
+  if (need_rank) {
+    compute_ranks(v, N, zmin);
+    __syncthreads();
+    if (ranks_out)
+      for (int i = tid; i < N; i += blockDim.x) ranks_out[(size_t)b * N + i] = v.rank[i];
+  }
+  setup_lambda(lam, v, b, N, tid);
+  const int topn = lam.topn > 0 ? lam.topn : N;
+  const float inv_t = grad_scale / temperature;
+
+  float part_l = 0.f, part_w = 0.f, part_n = 0.f;
+  for (int k = warp; k < N; k += nwarps) {
+    float acc_g = 0.f, acc_l = 0.f, acc_w = 0.f, acc_n = 0.f;
+    if (v.mv[k]) {
+      const float zk = v.z[k], lk = v.l[k], wk = v.w[k];
+      for (int j = lane; j < N; j += 32) {
+        if (!v.mv[j] || j == k) continue;
+        const float lj = v.l[j], zj = v.z[j];
+        if (PHI == TFR_PHI_MSE) {
+          // all ordered valid pairs i != j (losses_impl.py:972-998)
+          const float lm = pair_lambda<LAM>(lam, v, N, topn, k, j);
+          const float wkj = lm * wk, wjk = lm * v.w[j];
+          const float d = (zk - zj) - (lk - lj);
+          acc_l += wkj * d * d;
+          acc_w += wkj;
+          acc_n += wkj != 0.f ? 1.f : 0.f;
+          acc_g += 2.f * d * (wkj + wjk);
+        } else if (lk > lj) {  // k is the preferred item of pair (k, j)
+          const float W = pair_lambda<LAM>(lam, v, N, topn, k, j) * wk;
+          float f, df;
+          phi_eval<PHI>(zk - zj, f, df);
+          acc_l += W * f;
+          acc_w += W;
+          acc_n += W != 0.f ? 1.f : 0.f;
+          acc_g += W * df;
+        } else if (lj > lk) {  // pair (j, k): k is the non-preferred item
+          const float W = pair_lambda<LAM>(lam, v, N, topn, j, k) * v.w[j];
+          float f, df;
+          phi_eval<PHI>(zj - zk, f, df);
+          acc_g -= W * df;
+        }
+      }
+    }
+    acc_g = warp_sum(acc_g);
+    acc_l = warp_sum(acc_l);
+    acc_w = warp_sum(acc_w);
+    acc_n = warp_sum(acc_n);
+    if (lane == 0) {
+      if (grad) grad[(size_t)b * N + k] = acc_g * inv_t;
+      if (row_loss) row_loss[(size_t)b * N + k] = acc_l;
+      part_l += acc_l;
+      part_w += acc_w;
+      part_n += acc_n;
+    }
+  }
+  part_l = block_sum(part_l, v.red);
+  part_w = block_sum(part_w, v.red);
+  part_n = block_sum(part_n, v.red);
+  if (tid == 0) {
+    loss_sum[b] = part_l;
+    if (w_sum) w_sum[b] = part_w;
+    if (nnz) nnz[b] = part_n;
+  }
+}
+
+template <int LAM>
+__global__ void __launch_bounds__(kLossThreads)
+pair_weights_kernel(const float* __restrict__ labels, const int32_t* __restrict__ ranks,
+                    int N, LamDev lam, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ListView v = carve(smem_raw, N);
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < N; i += blockDim.x) {
+    const float lab = labels[(size_t)b * N + i];
+    v.l[i] = lab;
+    v.lv[i] = lab >= 0.f;
+    v.mv[i] = lab >= 0.f;
+    v.rank[i] = ranks[(size_t)b * N + i];
+  }
+  __syncthreads();
+  setup_lambda(lam, v, b, N, tid);
+  __syncthreads();
+  const int topn = lam.topn > 0 ? lam.topn : N;
+  for (int p = tid; p < N * N; p += blockDim.x) {
+    const int i = p / N, j = p % N;
+    out[(size_t)b * N * N + p] = pair_lambda<LAM>(lam, v, N, topn, i, j);
+  }
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+sorted_ranks_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                    const uint8_t* __restrict__ mask, int N, int32_t* __restrict__ ranks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ListView v = carve(smem_raw, N);
+  const int b = blockIdx.x;
+  const float zmin = load_list(v, scores, labels, nullptr, 0, mask, b, N, 1.f);
+  compute_ranks(v, N, zmin);
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) ranks[(size_t)b * N + i] = v.rank[i];
+}
+
+// ---------------------------------------------------------------------------
+// K2  ApproxNDCG / ApproxMRR
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kLossThreads)
+approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                   const float* __restrict__ item_w, int w_per_item,
+                   const uint8_t* __restrict__ mask, int N, float temperature,
+                   float grad_scale, int scale_by_weight, float* __restrict__ grad,
+                   float* __restrict__ loss, float* __restrict__ weight) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ListView v = carve(smem_raw, N);
+  float* cl = v.g;               // cleaned labels
+  float* c = v.disc;             // d loss / d r_i          (N <= N + 2)
+  float* r = reinterpret_cast<float*>(v.rank);  // approx ranks
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+  const float zmin = load_list(v, scores, labels, item_w, w_per_item, mask, b, N,
+                               temperature);
+  // invalid logits -> min - 1e3, invalid labels -> 0   (losses_impl.py:1591-1594)
+  float lsum = 0.f, wl = 0.f, lvsum = 0.f;
+  const float zinv = -1e3f + zmin;
+  for (int i = tid; i < N; i += blockDim.x) {
+    const bool mvalid = v.mv[i];
+    if (!mvalid) v.z[i] = zinv;
+    const float x = mvalid ? v.l[i] : 0.f;
+    cl[i] = x;
+    lsum += x;
+    // list weight = sum(w * l) / sum(l) over label-valid items (:1004-1015)
+    const float lv = v.lv[i] ? v.l[i] : 0.f;
+    float wraw = 1.f;
+    if (item_w) wraw = w_per_item ? item_w[(size_t)b * N + i] : item_w[b];
+    wl += wraw * lv;
+    lvsum += lv;
+  }
+  lsum = block_sum(lsum, v.red);
+  wl = block_sum(wl, v.red);
+  lvsum = block_sum(lvsum, v.red);
+  const bool nonzero = lsum > 0.f;
+  if (!nonzero) {  // labels := 1e-10 on the whole row (:1598-1599)
+    for (int i = tid; i < N; i += blockDim.x) cl[i] = 1e-10f;
+  }
+  float list_w = item_w ? (lvsum != 0.f ? wl / lvsum : 0.f) : 1.f;
+  if (!nonzero) list_w = 0.f;
+  __syncthreads();
+
+  // pass 1: approx ranks r_i = 0.5 + sum_j sigmoid(z_j - z_i)   (:102-106)
+  for (int i = warp; i < N; i += nwarps) {
+    const float zi = v.z[i];
+    float acc = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      const float d = v.z[j] - zi;
+      const float e = expf(-fabsf(d));
+      acc += d >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) r[i] = acc + 0.5f;
+  }
+  __syncthreads();
+
+  float list_loss;
+  if (MODE == 0) {
+    // safe gains (:33-49), inverse max DCG with 1/ln(1+k) (:109-134), ndcg (:159-165)
+    float lmax = -CUDART_INF_F;
+    for (int i = tid; i < N; i += blockDim.x) lmax = fmaxf(lmax, cl[i]);
+    lmax = block_max(lmax, v.red);
+    const float shift = exp2f(-lmax);
+    for (int i = tid; i < N; i += blockDim.x) v.w[i] = exp2f(cl[i] - lmax) - shift;  // G_i
+    __syncthreads();
+    const float ideal = ideal_dcg(cl, v.w, N, N, v.red,
+                                  [](int k) { return 1.f / log1pf((float)k); });
+    const float D = ideal > 0.f ? 1.f / ideal : 0.f;
+    float dcg = 0.f;
+    for (int i = tid; i < N; i += blockDim.x) {
+      const float lg = log1pf(r[i]);
+      dcg += v.w[i] / lg;
+      c[i] = D * v.w[i] / ((1.f + r[i]) * lg * lg);
+    }
+    dcg = block_sum(dcg, v.red);
+    list_loss = -(dcg * D);
+  } else {
+    // mrr = sum(l_i / r_i) / sum(l_i)   (:1629-1632)
+    float s = 0.f, rr = 0.f;
+    for (int i = tid; i < N; i += blockDim.x) {
+      s += cl[i];
+      rr += cl[i] / r[i];
+    }
+    s = block_sum(s, v.red);
+    rr = block_sum(rr, v.red);
+    for (int i = tid; i < N; i += blockDim.x) c[i] = cl[i] / (r[i] * r[i] * s);
+    list_loss = -(rr / s);
+  }
+  __syncthreads();
+
+  // pass 2: grad_k = (1/T) sum_i (c_i - c_k) sigmoid'(z_k - z_i)
+  if (grad) {
+    const float gs = grad_scale / temperature * (scale_by_weight ? list_w : 1.f);
+    for (int k = warp; k < N; k += nwarps) {
+      float acc = 0.f;
+      if (v.mv[k]) {
+        const float zk = v.z[k], ck = c[k];
+        for (int i = lane; i < N; i += 32) {
+          const float e = expf(-fabsf(zk - v.z[i]));
+          const float inv = 1.f / (1.f + e);
+          acc += (c[i] - ck) * (e * inv * inv);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) grad[(size_t)b * N + k] = acc * gs;
+    }
+  }
+  if (tid == 0) {
+    loss[b] = list_loss;
+    if (weight) weight[b] = list_w;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3  Softmax
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossThreads)
+softmax_loss_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                    const float* __restrict__ item_w, int w_per_item,
+                    const uint8_t* __restrict__ mask, int N, float temperature,
+                    LamDev lam, float grad_scale, int scale_by_weight,
+                    float* __restrict__ grad, float* __restrict__ loss,
+                    float* __restrict__ weight) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ListView v = carve(smem_raw, N);
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float zmin = load_list(v, scores, labels, item_w, w_per_item, mask, b, N,
+                               temperature);
+  const bool use_lambda = lam.kind == TFR_LAMBDA_DCG;  // isinstance(DCGLambdaWeight) :1132-1134
+  if (use_lambda) {
+    compute_ranks(v, N, zmin);
+    __syncthreads();
+    // individual_weights cleans by the mask-cleaned labels (:1129, :285-287)
+    for (int i = tid; i < N; i += blockDim.x) v.lv[i] = v.mv[i] && v.lv[i];
+    __syncthreads();
+    setup_lambda(lam, v, b, N, tid);
+  }
+  float* lp = v.w;  // l' : effective labels (w no longer needed as-is)
+  float lsum = 0.f;
+  for (int i = tid; i < N; i += blockDim.x) {
+    const bool mvalid = v.mv[i];
+    float x = mvalid ? v.l[i] : 0.f;
+    if (use_lambda) x = v.g[i] * v.disc[v.rank[i]];
+    float wraw = 1.f;
+    if (item_w) wraw = w_per_item ? item_w[(size_t)b * N + i] : item_w[b];
+    x *= wraw;
+    if (!mvalid) v.z[i] = kLogEpsilon;
+    lp[i] = x;
+    lsum += x;
+  }
+  lsum = block_sum(lsum, v.red);
+  const bool nonzero = lsum > 0.f;
+  float psum = 0.f, zmax = -CUDART_INF_F;
+  for (int i = tid; i < N; i += blockDim.x) {
+    float p = nonzero ? lp[i] : 1e-10f;
+    if (!v.mv[i]) p = 0.f;
+    lp[i] = p;
+    psum += p;
+    zmax = fmaxf(zmax, v.z[i]);
+  }
+  psum = block_sum(psum, v.red);
+  zmax = block_max(zmax, v.red);
+  float se = 0.f, dot = 0.f;
+  const float pinv = psum != 0.f ? 1.f / psum : 0.f;
+  for (int i = tid; i < N; i += blockDim.x) {
+    se += expf(v.z[i] - zmax);
+    dot += lp[i] * pinv * v.z[i];
+  }
+  se = block_sum(se, v.red);
+  dot = block_sum(dot, v.red);
+  const float lse = zmax + logf(se);
+  const float ptot = psum != 0.f ? 1.f : 0.f;
+  if (grad) {
+    const float gs = grad_scale / temperature * (scale_by_weight ? lsum : 1.f);
+    for (int i = tid; i < N; i += blockDim.x) {
+      const float sm = expf(v.z[i] - lse);
+      grad[(size_t)b * N + i] = v.mv[i] ? (sm * ptot - lp[i] * pinv) * gs : 0.f;
+    }
+  }
+  if (tid == 0) {
+    loss[b] = lse * ptot - dot;
+    if (weight) weight[b] = lsum;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+weighted_sum_kernel(const float* __restrict__ v, const float* __restrict__ w, int n,
+                    float scale, float* __restrict__ out2) {
+  __shared__ float red[32];
+  float a = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float wi = w ? w[i] : 1.f;
+    a += v[i] * wi;
+    c += wi;
+  }
+  a = block_sum(a, red);
+  c = block_sum(c, red);
+  if (threadIdx.x == 0) {
+    out2[0] = a * scale;
+    out2[1] = c;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------
+template <typename K>
+static int prep_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    TFR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)bytes));
+  }
+  return TFR_OK;
+}
+
+static int check_list_args(const void* scores, const void* labels, int B, int N,
+                           float temperature) {
+  TFR_REQUIRE(scores != nullptr && labels != nullptr, "scores/labels must not be NULL");
+  TFR_REQUIRE(B >= 0 && N >= 1, "need batch_size >= 0 and list_size >= 1 (got B=%d N=%d)", B, N);
+  TFR_REQUIRE(N <= kMaxListSize, "list_size %d exceeds the supported maximum %d", N, kMaxListSize);
+  TFR_REQUIRE(temperature != 0.f, "temperature must be non-zero");
+  return TFR_OK;
+}
+
+template <int PHI>
+static int launch_pairwise(int lamkind, dim3 grid, size_t smem, cudaStream_t st,
+                           const float* scores, const float* labels, const float* item_w,
+                           int w_per_item, const uint8_t* mask, int N, float temperature,
+                           LamDev lam, float grad_scale, float* grad, float* row_loss,
+                           float* loss_sum, float* w_sum, float* nnz, int32_t* ranks_out) {
+#define TFR_CASE(L)                                                                      \
+  case L: {                                                                              \
+    int rc = prep_smem(pairwise_loss_kernel<PHI, L>, smem);                              \
+    if (rc) return rc;                                                                   \
+    pairwise_loss_kernel<PHI, L><<<grid, kLossThreads, smem, st>>>(                      \
+        scores, labels, item_w, w_per_item, mask, N, temperature, lam, grad_scale, grad, \
+        row_loss, loss_sum, w_sum, nnz, ranks_out);                                      \
+    break;                                                                               \
+  }
+  switch (lamkind) {
+    TFR_CASE(TFR_LAMBDA_NONE)
+    TFR_CASE(TFR_LAMBDA_LABEL_DIFF)
+    TFR_CASE(TFR_LAMBDA_DCG)
+    TFR_CASE(TFR_LAMBDA_DCG_V2)
+    TFR_CASE(TFR_LAMBDA_YETI)
+    TFR_CASE(TFR_LAMBDA_PRECISION)
+    default:
+      set_error("bad lambda kind %d", lamkind);
+      return TFR_INVALID_ARGUMENT;
+  }
+#undef TFR_CASE
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+}  // namespace tfr
+
+using namespace tfr;
+
+extern "C" int tfr_pairwise_loss_fwd_bwd(const float* scores, const float* labels,
+                                         const float* item_w, int w_per_item,
+                                         const uint8_t* mask, int B, int N,
+                                         float temperature, int phi,
+                                         const tfr_lambda_cfg* lam_host, float grad_scale,
+                                         float* grad, float* row_loss, float* loss_sum,
+                                         float* w_sum, float* nnz, int32_t* ranks_out,
+                                         void* stream) {
+  int rc = check_list_args(scores, labels, B, N, temperature);
+  if (rc) return rc;
+  TFR_REQUIRE(loss_sum != nullptr, "loss_sum must not be NULL");
+  TFR_REQUIRE(phi >= TFR_PHI_LOGISTIC && phi <= TFR_PHI_MSE, "phi %d is not a tfr_phi", phi);
+  rc = check_lam(lam_host);
+  if (rc) return rc;
+  if (B == 0) return TFR_OK;
+  const LamDev lam = make_lam(lam_host);
+  const size_t smem = list_smem_bytes(N);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(B);
+#define TFR_PHI_CASE(P)                                                                   \
+  case P:                                                                                 \
+    return launch_pairwise<P>(lam.kind, grid, smem, st, scores, labels, item_w, w_per_item, \
+                              mask, N, temperature, lam, grad_scale, grad, row_loss,      \
+                              loss_sum, w_sum, nnz, ranks_out);
+  switch (phi) {
+    TFR_PHI_CASE(TFR_PHI_LOGISTIC)
+    TFR_PHI_CASE(TFR_PHI_HINGE)
+    TFR_PHI_CASE(TFR_PHI_SOFT_ZERO_ONE)
+    TFR_PHI_CASE(TFR_PHI_MSE)
+  }
+#undef TFR_PHI_CASE
+  return TFR_INVALID_ARGUMENT;
+}
+
+extern "C" int tfr_lambda_pair_weights(const float* labels, const int32_t* ranks, int B,
+                                       int N, const tfr_lambda_cfg* lam_host, float* out,
+                                       void* stream) {
+  TFR_REQUIRE(labels && ranks && out && lam_host, "NULL argument");
+  TFR_REQUIRE(B >= 0 && N >= 1 && N <= 1024, "pair weights helper needs 1 <= N <= 1024");
+  int rc = check_lam(lam_host);
+  if (rc) return rc;
+  if (B == 0) return TFR_OK;
+  const LamDev lam = make_lam(lam_host);
+  const size_t smem = list_smem_bytes(N);
+  cudaStream_t st = (cudaStream_t)stream;
+#define TFR_CASE(L)                                                                   \
+  case L: {                                                                           \
+    rc = prep_smem(pair_weights_kernel<L>, smem);                                     \
+    if (rc) return rc;                                                                \
+    pair_weights_kernel<L><<<B, kLossThreads, smem, st>>>(labels, ranks, N, lam, out); \
+    break;                                                                            \
+  }
+  switch (lam.kind) {
+    TFR_CASE(TFR_LAMBDA_NONE)
+    TFR_CASE(TFR_LAMBDA_LABEL_DIFF)
+    TFR_CASE(TFR_LAMBDA_DCG)
+    TFR_CASE(TFR_LAMBDA_DCG_V2)
+    TFR_CASE(TFR_LAMBDA_YETI)
+    TFR_CASE(TFR_LAMBDA_PRECISION)
+  }
+#undef TFR_CASE
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+extern "C" int tfr_sorted_ranks(const float* scores, const float* labels,
+                                const uint8_t* mask, int B, int N, int32_t* ranks,
+                                void* stream) {
+  int rc = check_list_args(scores, labels, B, N, 1.f);
+  if (rc) return rc;
+  TFR_REQUIRE(ranks != nullptr, "ranks must not be NULL");
+  if (B == 0) return TFR_OK;
+  const size_t smem = list_smem_bytes(N);
+  rc = prep_smem(sorted_ranks_kernel, smem);
+  if (rc) return rc;
+  sorted_ranks_kernel<<<B, kLossThreads, smem, (cudaStream_t)stream>>>(scores, labels, mask,
+                                                                      N, ranks);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+extern "C" int tfr_approx_loss_fwd_bwd(const float* scores, const float* labels,
+                                       const float* item_w, int w_per_item,
+                                       const uint8_t* mask, int B, int N, float temperature,
+                                       int mode, float grad_scale, int scale_by_weight,
+                                       float* grad, float* loss, float* weight,
+                                       void* stream) {
+  int rc = check_list_args(scores, labels, B, N, temperature);
+  if (rc) return rc;
+  TFR_REQUIRE(loss != nullptr, "loss must not be NULL");
+  TFR_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (NDCG) or 1 (MRR)");
+  if (B == 0) return TFR_OK;
+  const size_t smem = list_smem_bytes(N);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0) {
+    rc = prep_smem(approx_loss_kernel<0>, smem);
+    if (rc) return rc;
+    approx_loss_kernel<0><<<B, kLossThreads, smem, st>>>(scores, labels, item_w, w_per_item,
+                                                        mask, N, temperature, grad_scale,
+                                                        scale_by_weight, grad, loss, weight);
+  } else {
+    rc = prep_smem(approx_loss_kernel<1>, smem);
+    if (rc) return rc;
+    approx_loss_kernel<1><<<B, kLossThreads, smem, st>>>(scores, labels, item_w, w_per_item,
+                                                        mask, N, temperature, grad_scale,
+                                                        scale_by_weight, grad, loss, weight);
+  }
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+extern "C" int tfr_softmax_loss_fwd_bwd(const float* scores, const float* labels,
+                                        const float* item_w, int w_per_item,
+                                        const uint8_t* mask, int B, int N, float temperature,
+                                        const tfr_lambda_cfg* lam_host, float grad_scale,
+                                        int scale_by_weight, float* grad, float* loss,
+                                        float* weight, void* stream) {
+  int rc = check_list_args(scores, labels, B, N, temperature);
+  if (rc) return rc;
+  TFR_REQUIRE(loss != nullptr, "loss must not be NULL");
+  rc = check_lam(lam_host);
+  if (rc) return rc;
+  if (B == 0) return TFR_OK;
+  const LamDev lam = make_lam(lam_host);
+  const size_t smem = list_smem_bytes(N);
+  rc = prep_smem(softmax_loss_kernel, smem);
+  if (rc) return rc;
+  softmax_loss_kernel<<<B, kLossThreads, smem, (cudaStream_t)stream>>>(
+      scores, labels, item_w, w_per_item, mask, N, temperature, lam, grad_scale,
+      scale_by_weight, grad, loss, weight);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+extern "C" int tfr_weighted_sum(const float* v, const float* w, int n, float scale,
+                                float* out2, void* stream) {
+  TFR_REQUIRE(v != nullptr && out2 != nullptr && n >= 0, "bad arguments");
+  weighted_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(v, w, n, scale, out2);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}

@@ -1,0 +1,225 @@
+// K4: NDCG@k / MRR@k for several cut-offs in one launch.
+//
+// One CTA per list.  The list is ordered with an in-shared-memory bitonic sort of
+// 64-bit keys (valid-first | score descending | original index), which makes the
+// order exactly "valid items by score, ties by index, invalid last" — the
+// reference's sort_by_scores(..., mask) with shuffle_ties=False (utils.py:115-164).
+// A second sort by weight*gain gives the ideal ordering (metrics_impl.py:660-665).
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace tfr {
+
+constexpr int kMetricThreads = 256;
+constexpr int kMaxMetricListSize = 8192;
+constexpr int kMaxTopn = 16;
+
+struct TopnList {
+  int n;
+  int v[kMaxTopn];
+};
+
+__device__ __forceinline__ uint32_t desc_bits(float x) {
+  if (x == 0.f) x = 0.f;  // -0 == +0
+  uint32_t u = __float_as_uint(x);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-order preserving
+  return ~u;                                        // descending
+}
+
+__device__ inline void bitonic_sort(unsigned long long* keys, int P) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int idx = threadIdx.x; idx < P; idx += blockDim.x) {
+        const int ixj = idx ^ j;
+        if (ixj > idx) {
+          const bool asc = (idx & k) == 0;
+          const unsigned long long a = keys[idx], c = keys[ixj];
+          if ((a > c) == asc) {
+            keys[idx] = c;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// raw[b, 0..4] = {sum w, sum w*gain, sum gain, sum w*rel, sum rel}, rel = [label >= 1]
+__global__ void __launch_bounds__(kMetricThreads)
+rank_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                    const float* __restrict__ item_w, int w_per_item,
+                    const uint8_t* __restrict__ mask, int N, int P, TopnList topns,
+                    int gain_fn, int disc_fn, const float* __restrict__ gain_table,
+                    const float* __restrict__ disc_table, float* __restrict__ ndcg,
+                    float* __restrict__ mrr, float* __restrict__ raw) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  float* cl = reinterpret_cast<float*>(keys + P);  // cleaned labels
+  float* w = cl + N;                                // example weights
+  float* wg = w + N;                                // weight * gain
+  float* term = wg + N;                             // per-position DCG terms
+  float* red = term + N;                            // [32]
+  unsigned char* valid = reinterpret_cast<unsigned char*>(red + 32);
+
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const size_t off = (size_t)b * N;
+
+  // metrics_impl.py:228-266: mask &= w > 0; labels := 0, preds := min - 1e-6 where masked out
+  float pmin = CUDART_INF_F;
+  for (int i = tid; i < N; i += blockDim.x) pmin = fminf(pmin, scores[off + i]);
+  pmin = block_min(pmin, red);
+  float s_w = 0.f, s_wg = 0.f, s_g = 0.f, s_wr = 0.f, s_r = 0.f;
+  for (int i = tid; i < N; i += blockDim.x) {
+    const float lab = labels[off + i];
+    float wv = 1.f;
+    if (item_w) wv = w_per_item ? item_w[off + i] : item_w[b];
+    bool ok = mask ? (mask[off + i] != 0) : (lab >= 0.f);
+    ok = ok && (wv > 0.f);
+    const float c = ok ? lab : 0.f;
+    const float g = gain_fn == TFR_GAIN_TABLE ? gain_table[off + i] : gain_of(gain_fn, c);
+    const float sc = ok ? scores[off + i] : (-1e-6f + pmin);
+    cl[i] = c;
+    w[i] = wv;
+    wg[i] = wv * g;
+    valid[i] = ok;
+    keys[i] = ((unsigned long long)(ok ? 0 : 1) << 45) |
+              ((unsigned long long)desc_bits(sc) << 13) | (unsigned long long)i;
+    const float rel = c >= 1.f ? 1.f : 0.f;
+    s_w += wv;
+    s_wg += wv * g;
+    s_g += g;
+    s_wr += wv * rel;
+    s_r += rel;
+  }
+  for (int i = N + tid; i < P; i += blockDim.x) keys[i] = ~0ull;
+  s_w = block_sum(s_w, red);
+  s_wg = block_sum(s_wg, red);
+  s_g = block_sum(s_g, red);
+  s_wr = block_sum(s_wr, red);
+  s_r = block_sum(s_r, red);
+  if (tid == 0 && raw) {
+    raw[b * 5 + 0] = s_w;
+    raw[b * 5 + 1] = s_wg;
+    raw[b * 5 + 2] = s_g;
+    raw[b * 5 + 3] = s_wr;
+    raw[b * 5 + 4] = s_r;
+  }
+  __syncthreads();
+  bitonic_sort(keys, P);
+
+  // DCG terms by position and first relevant position (MRR).
+  int first_rel = 0x7fffffff;
+  for (int k = tid; k < N; k += blockDim.x) {
+    const int idx = (int)(keys[k] & 0x1fffull);
+    const float d = disc_fn == TFR_DISC_TABLE ? disc_table[k + 1] : disc_of(disc_fn, (float)(k + 1));
+    term[k] = wg[idx] * d;
+    if (cl[idx] >= 1.f) first_rel = min(first_rel, k);
+  }
+  {
+    float fr = block_min((float)min(first_rel, 1 << 24), red);
+    first_rel = (int)fr;
+  }
+  float dcg[kMaxTopn];
+  for (int t = 0; t < topns.n; ++t) {
+    const int cut = topns.v[t] > 0 ? min(topns.v[t], N) : N;
+    float acc = 0.f;
+    for (int k = tid; k < cut; k += blockDim.x) acc += term[k];
+    dcg[t] = block_sum(acc, red);
+    if (tid == 0 && mrr)
+      mrr[(size_t)b * topns.n + t] = first_rel < cut ? 1.f / (float)(first_rel + 1) : 0.f;
+  }
+  if (ndcg == nullptr) return;
+  __syncthreads();
+
+  // ideal ordering: sort by weight * gain (metrics_impl.py:660-662), same mask.
+  for (int i = tid; i < N; i += blockDim.x) {
+    keys[i] = ((unsigned long long)(valid[i] ? 0 : 1) << 45) |
+              ((unsigned long long)desc_bits(valid[i] ? wg[i] : 0.f) << 13) |
+              (unsigned long long)i;
+  }
+  for (int i = N + tid; i < P; i += blockDim.x) keys[i] = ~0ull;
+  __syncthreads();
+  bitonic_sort(keys, P);
+  for (int k = tid; k < N; k += blockDim.x) {
+    const int idx = (int)(keys[k] & 0x1fffull);
+    const float d = disc_fn == TFR_DISC_TABLE ? disc_table[k + 1] : disc_of(disc_fn, (float)(k + 1));
+    term[k] = wg[idx] * d;
+  }
+  __syncthreads();
+  for (int t = 0; t < topns.n; ++t) {
+    const int cut = topns.v[t] > 0 ? min(topns.v[t], N) : N;
+    float acc = 0.f;
+    for (int k = tid; k < cut; k += blockDim.x) acc += term[k];
+    const float ideal = block_sum(acc, red);
+    if (tid == 0) ndcg[(size_t)b * topns.n + t] = ideal != 0.f ? dcg[t] / ideal : 0.f;
+  }
+}
+
+// metrics_impl.py:63-119 over one (single-process) batch.
+__global__ void __launch_bounds__(1024)
+metric_list_weights_kernel(const float* __restrict__ raw, int B, float* __restrict__ ndcg_w,
+                           float* __restrict__ mrr_w) {
+  __shared__ float red[32];
+  for (int m = 0; m < 2; ++m) {
+    float* out = m == 0 ? ndcg_w : mrr_w;
+    if (out == nullptr) continue;
+    float cnt = 0.f, sw = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+      const float sum_w = raw[b * 5 + 0];
+      const float wr = raw[b * 5 + 1 + 2 * m], r = raw[b * 5 + 2 + 2 * m];
+      cnt += (sum_w > 0.f && r > 0.f) ? 1.f : 0.f;
+      sw += r != 0.f ? wr / r : 0.f;
+    }
+    cnt = block_sum(cnt, red);
+    sw = block_sum(sw, red);
+    const float avg = cnt > 0.f ? sw / cnt : 1.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+      const float sum_w = raw[b * 5 + 0];
+      const float wr = raw[b * 5 + 1 + 2 * m], r = raw[b * 5 + 2 + 2 * m];
+      out[b] = sum_w > 0.f ? (r > 0.f ? wr / r : avg) : 0.f;
+    }
+  }
+}
+
+}  // namespace tfr
+
+using namespace tfr;
+
+extern "C" int tfr_rank_metrics(const float* scores, const float* labels,
+                                const float* item_w, int w_per_item, const uint8_t* mask,
+                                int B, int N, const int32_t* topns_host, int n_topn,
+                                int gain_fn, int disc_fn, const float* gain_table,
+                                const float* disc_table, float* ndcg, float* ndcg_w,
+                                float* mrr, float* mrr_w, float* raw, void* stream) {
+  TFR_REQUIRE(scores && labels, "scores/labels must not be NULL");
+  TFR_REQUIRE(B >= 0 && N >= 1 && N <= kMaxMetricListSize,
+              "need 1 <= list_size <= %d (got %d)", kMaxMetricListSize, N);
+  TFR_REQUIRE(n_topn >= 1 && n_topn <= kMaxTopn && topns_host, "need 1..%d cut-offs", kMaxTopn);
+  TFR_REQUIRE(gain_fn >= 0 && gain_fn <= TFR_GAIN_TABLE && disc_fn >= 0 && disc_fn <= TFR_DISC_TABLE,
+              "bad gain_fn/disc_fn");
+  TFR_REQUIRE(gain_fn != TFR_GAIN_TABLE || gain_table, "gain_fn TABLE needs gain_table");
+  TFR_REQUIRE(disc_fn != TFR_DISC_TABLE || disc_table, "disc_fn TABLE needs disc_table");
+  TFR_REQUIRE(raw != nullptr, "raw [B,5] workspace must not be NULL");
+  if (B == 0) return TFR_OK;
+  TopnList t;
+  t.n = n_topn;
+  for (int i = 0; i < n_topn; ++i) t.v[i] = topns_host[i];
+  int P = 1;
+  while (P < N) P <<= 1;
+  const size_t smem = (size_t)P * 8 + (size_t)(4 * N + 32) * 4 + N + 16;
+  if (smem > 48 * 1024)
+    TFR_CUDA_OK(cudaFuncSetAttribute(rank_metrics_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaStream_t st = (cudaStream_t)stream;
+  rank_metrics_kernel<<<B, kMetricThreads, smem, st>>>(scores, labels, item_w, w_per_item, mask,
+                                                      N, P, t, gain_fn, disc_fn, gain_table,
+                                                      disc_table, ndcg, mrr, raw);
+  TFR_LAUNCH_OK();
+  if (ndcg_w || mrr_w) {
+    metric_list_weights_kernel<<<1, 1024, 0, st>>>(raw, B, ndcg_w, mrr_w);
+    TFR_LAUNCH_OK();
+  }
+  return TFR_OK;
+}

@@ -1,0 +1,301 @@
+// K5/K6 (fp32 CUDA-core path): create_tower forward/backward over the flattened
+// [M, D] matrix with register-tiled SGEMMs.  This is the exact-fp32 path
+// (TFR_PREC_FP32); the tensor-core paths live in mlp_tc.cu.
+//
+// Layout: activations row-major [M, units]; Dense kernels [in, out] row-major
+// (Keras layout, keras/layers.py:70); all parameters / gradients in one flat
+// buffer: W_0, b_0, W_1, b_1, ...
+#include "common.cuh"
+#include "mlp.h"
+
+namespace tfr {
+
+// ------------------------------------------------------------------ SGEMM ---
+// C[M, N] = epi(opA(A) * opB(B)); 128x128x8 tile, 256 threads, 8x8 per thread.
+constexpr int BM = 128, BN = 128, BK = 8, GEMM_THREADS = 256;
+
+enum Epilogue { EPI_NONE = 0, EPI_BIAS_ACT = 1, EPI_MASK_POS = 2 };
+
+struct GemmArgs {
+  const float* A; int lda;
+  const float* B; int ldb;
+  float* C; int ldc;
+  int M, N, K;
+  const float* bias;   // EPI_BIAS_ACT: [N]
+  const float* aux;    // EPI_MASK_POS: [M, N] (ld = ldc); C *= (aux > 0)
+  int act;
+  // split-K (over the K dimension): each blockIdx.z handles k_per_split of K and
+  // writes to C + z * split_stride.
+  int k_per_split;
+  size_t split_stride;
+};
+
+template <bool TA, bool TB, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS)
+sgemm_kernel(GemmArgs g) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * g.k_per_split;
+  const int kend = min(g.K, kbeg + g.k_per_split);
+  float* C = g.C + (size_t)blockIdx.z * g.split_stride;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * GEMM_THREADS;  // 0 .. 1023
+      int m, k;
+      if (TA) { m = e & (BM - 1); k = e >> 7; } else { k = e & (BK - 1); m = e >> 3; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < g.M && gk < kend)
+        v = TA ? g.A[(size_t)gk * g.lda + gm] : g.A[(size_t)gm * g.lda + gk];
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * GEMM_THREADS;
+      int n, k;
+      if (TB) { k = e & (BK - 1); n = e >> 3; } else { n = e & (BN - 1); k = e >> 7; }
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < g.N && gk < kend)
+        v = TB ? g.B[(size_t)gn * g.ldb + gk] : g.B[(size_t)gk * g.ldb + gn];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[8], b[8];
+      *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+      *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (gn >= g.N) continue;
+      float v = acc[i][j];
+      if (EPI == EPI_BIAS_ACT) {
+        v += g.bias[gn];
+        if (g.act == TFR_ACT_RELU) v = fmaxf(v, 0.f);
+      } else if (EPI == EPI_MASK_POS) {
+        if (g.act == TFR_ACT_RELU && !(g.aux[(size_t)gm * g.ldc + gn] > 0.f)) v = 0.f;
+      }
+      C[(size_t)gm * g.ldc + gn] = v;
+    }
+  }
+}
+
+template <bool TA, bool TB, int EPI>
+static int launch_gemm(GemmArgs g, int splits, cudaStream_t st) {
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, splits);
+  sgemm_kernel<TA, TB, EPI><<<grid, GEMM_THREADS, 0, st>>>(g);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+// ------------------------------------------------------- output layer fwd ---
+// scores[m, o] = H[m, :] . W[:, o] + b[o]; RestoreList fill for masked rows
+// (keras/layers.py:265).  One warp per row.
+__global__ void __launch_bounds__(256)
+out_layer_fwd_kernel(const float* __restrict__ H, int M, int K, int O,
+                     const float* __restrict__ W, const float* __restrict__ bias,
+                     const uint8_t* __restrict__ mask, float* __restrict__ scores) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* h = H + (size_t)row * K;
+  for (int o = 0; o < O; ++o) {
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(h[k], W[(size_t)k * O + o], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float v = acc + bias[o];
+      if (mask && O == 1 && !mask[row]) v = kLogEpsilon;
+      scores[(size_t)row * O + o] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------- output layer bwd ---
+// Rows [z*rows_per, ...): dH[m, k] = (sum_o dS[m, o] W[k, o]) * act'(H[m, k]);
+// partial[z][k*O + o] = sum_m H[m, k] dS[m, o]; partial[z][K*O + o] = sum_m dS[m, o].
+constexpr int kMaxOut = 8;
+__global__ void __launch_bounds__(1024)
+out_layer_bwd_kernel(const float* __restrict__ H, int M, int K, int O,
+                     const float* __restrict__ W, const float* __restrict__ dS,
+                     const uint8_t* __restrict__ mask, int act, int rows_per,
+                     float* __restrict__ dH, float* __restrict__ partial,
+                     size_t partial_stride) {
+  const int k = threadIdx.x;
+  const int z = blockIdx.x;
+  const int mbeg = z * rows_per, mend = min(M, mbeg + rows_per);
+  float w[kMaxOut], dw[kMaxOut], db[kMaxOut];
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) {
+    w[o] = (k < K && o < O) ? W[(size_t)k * O + o] : 0.f;
+    dw[o] = 0.f;
+    db[o] = 0.f;
+  }
+  for (int m = mbeg; m < mend; ++m) {
+    const bool live = !(mask && O == 1 && !mask[m]);
+    float ds[kMaxOut];
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) ds[o] = (o < O && live) ? dS[(size_t)m * O + o] : 0.f;
+    if (k < K) {
+      const float h = H[(size_t)m * K + k];
+      float dh = 0.f;
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) {
+        dh = fmaf(ds[o], w[o], dh);
+        dw[o] = fmaf(h, ds[o], dw[o]);
+      }
+      if (dH) {
+        if (act == TFR_ACT_RELU && !(h > 0.f)) dh = 0.f;
+        dH[(size_t)m * K + k] = dh;
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) db[o] += ds[o];
+  }
+  float* p = partial + (size_t)z * partial_stride;
+  if (k < K)
+    for (int o = 0; o < O; ++o) p[(size_t)k * O + o] = dw[o];
+  if (k == 0)
+    for (int o = 0; o < O; ++o) p[(size_t)K * O + o] = db[o];
+}
+
+// partial[z][N cols] column sums of dZ rows handled by split z.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ dZ, int M, int N, int rows_per,
+              float* __restrict__ partial, size_t partial_stride, size_t col_offset) {
+  const int z = blockIdx.x;
+  const int mbeg = z * rows_per, mend = min(M, mbeg + rows_per);
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float acc = 0.f;
+    for (int m = mbeg; m < mend; ++m) acc += dZ[(size_t)m * N + n];
+    partial[(size_t)z * partial_stride + col_offset + n] = acc;
+  }
+}
+
+// out[i] = sum_z partial[z][i]  (deterministic order)
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partial, int splits, size_t stride,
+                       size_t n, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int z = 0; z < splits; ++z) acc += partial[(size_t)z * stride + i];
+  out[i] = acc;
+}
+
+// ------------------------------------------------------------- host side ---
+int mlp_simt_fwd(const float* X, int M, const MlpPlan& p, const float* params,
+                 const uint8_t* mask, float* ws, float* scores, cudaStream_t st) {
+  const int L = p.n_dense - 1;  // hidden layers
+  const float* in = X;
+  for (int d = 0; d < L; ++d) {
+    GemmArgs g{};
+    g.A = in; g.lda = p.dims[d];
+    g.B = params + p.w_off[d]; g.ldb = p.dims[d + 1];
+    g.C = ws + p.act_off[d]; g.ldc = p.dims[d + 1];
+    g.M = M; g.N = p.dims[d + 1]; g.K = p.dims[d];
+    g.bias = params + p.b_off[d];
+    g.act = p.activation;
+    g.k_per_split = g.K; g.split_stride = 0;
+    int rc = launch_gemm<false, false, EPI_BIAS_ACT>(g, 1, st);
+    if (rc) return rc;
+    in = g.C;
+  }
+  const int K = p.dims[L], O = p.dims[L + 1];
+  const int rows_per_block = 8;
+  out_layer_fwd_kernel<<<(M + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(
+      in, M, K, O, params + p.w_off[L], params + p.b_off[L], mask, scores);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+int mlp_simt_bwd(const float* X, int M, const MlpPlan& p, const float* params,
+                 const float* dscores, const uint8_t* mask, float* ws, float* grads,
+                 cudaStream_t st) {
+  const int L = p.n_dense - 1;
+  float* partial = ws + p.partial_off;
+  const size_t pstride = p.partial_stride;
+  const int rows_per = p.rows_per_split, splits = p.splits;
+  float* dz_cur = ws + p.dz_off[0];
+  float* dz_nxt = ws + p.dz_off[1];
+
+  // output layer
+  {
+    const int K = p.dims[L], O = p.dims[L + 1];
+    const float* H = L > 0 ? ws + p.act_off[L - 1] : X;
+    const int threads = ((K + 31) / 32) * 32;
+    out_layer_bwd_kernel<<<splits, threads, 0, st>>>(
+        H, M, K, O, params + p.w_off[L], dscores, mask, L > 0 ? p.activation : TFR_ACT_NONE,
+        rows_per, L > 0 ? dz_cur : nullptr, partial, pstride);
+    TFR_LAUNCH_OK();
+    const size_t n = (size_t)K * O + O;
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, splits, pstride, n,
+                                                                       grads + p.w_off[L]);
+    TFR_LAUNCH_OK();
+  }
+  // hidden layers, last to first: dz_cur = dZ_d  [M, dims[d+1]]
+  for (int d = L - 1; d >= 0; --d) {
+    const int Kin = p.dims[d], Nout = p.dims[d + 1];
+    const float* A = d > 0 ? ws + p.act_off[d - 1] : X;
+    colsum_kernel<<<splits, 256, 0, st>>>(dz_cur, M, Nout, rows_per, partial, pstride,
+                                          (size_t)Kin * Nout);
+    TFR_LAUNCH_OK();
+    {  // dW = A^T dZ, split over rows
+      GemmArgs g{};
+      g.A = A; g.lda = Kin;           // opA(A)[kin, m] = A[m, kin]
+      g.B = dz_cur; g.ldb = Nout;     // [m, nout]
+      g.C = partial; g.ldc = Nout;
+      g.M = Kin; g.N = Nout; g.K = M;
+      g.k_per_split = rows_per; g.split_stride = pstride;
+      int rc = launch_gemm<true, false, EPI_NONE>(g, splits, st);
+      if (rc) return rc;
+    }
+    const size_t n = (size_t)Kin * Nout + Nout;
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, splits, pstride, n,
+                                                                       grads + p.w_off[d]);
+    TFR_LAUNCH_OK();
+    if (d > 0) {  // dZ_{d-1} = (dZ_d W_d^T) * act'(H_{d-1})
+      GemmArgs g{};
+      g.A = dz_cur; g.lda = Nout;
+      g.B = params + p.w_off[d]; g.ldb = Nout;   // opB(B)[nout, kin] = W[kin, nout]
+      g.C = dz_nxt; g.ldc = Kin;
+      g.M = M; g.N = Kin; g.K = Nout;
+      g.aux = ws + p.act_off[d - 1];
+      g.act = p.activation;
+      g.k_per_split = g.K; g.split_stride = 0;
+      int rc = launch_gemm<false, true, EPI_MASK_POS>(g, 1, st);
+      if (rc) return rc;
+      float* t = dz_cur; dz_cur = dz_nxt; dz_nxt = t;
+    }
+  }
+  return TFR_OK;
+}
+
+}  // namespace tfr

@@ -1,0 +1,232 @@
+"""`tfr.keras.layers` pieces on the hot path: create_tower, FlattenList, RestoreList
+(keras/layers.py:26-77, 80-182, 185-272).
+
+`create_tower` returns a `Tower`: a torch.nn.Module whose forward/backward run in
+the CUDA scorer kernels (tfr_mlp_fwd / tfr_mlp_bwd).  All Dense kernels and
+biases live in ONE flat fp32 parameter (`Tower.flat`), Keras layout
+(kernel [in, out]), so data-parallel training needs a single all-reduce.
+"""
+import ctypes
+import math
+
+import torch
+
+from ranking_b200 import _C
+from ranking_b200 import utils as tfr_utils
+
+_LOG_EPSILON = math.log(1e-10)
+
+_PRECISIONS = {'fp32': _C.PREC_FP32, 'tf32x3': _C.PREC_TF32X3,
+               'tf32': _C.PREC_TF32, 'bf16': _C.PREC_BF16}
+
+
+def _activation_enum(activation):
+  if activation is None or activation == 'linear':
+    return _C.ACT_NONE
+  if activation == 'relu' or activation is torch.relu or \
+      activation is torch.nn.functional.relu:
+    return _C.ACT_RELU
+  raise NotImplementedError(
+      'activation %r: the CUDA tower supports None and relu' % (activation,))
+
+
+class _TowerFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, flat, mask, tower):
+    m = x.shape[0]
+    out = torch.empty(m, tower.output_units, dtype=torch.float32,
+                      device=x.device)
+    # The workspace carries the activations to backward; one per forward call
+    # so that several forwards may be outstanding (caching allocator: cheap).
+    ws = tower._new_workspace(m)
+    _C.check(_C.lib.tfr_mlp_fwd(_C.ptr(x), m, ctypes.byref(tower._cfg),
+                                _C.ptr(flat), _C.ptr(mask), _C.ptr(ws),
+                                _C.ptr(out), tower._precision, _C.stream()))
+    ctx.tower = tower
+    ctx.ws = ws
+    ctx.save_for_backward(x, flat, mask)
+    return out
+
+  @staticmethod
+  def backward(ctx, g_out):
+    x, flat, mask = ctx.saved_tensors
+    tower = ctx.tower
+    m = x.shape[0]
+    grads = torch.empty_like(flat)
+    ws = ctx.ws
+    _C.check(_C.lib.tfr_mlp_bwd(_C.ptr(x), m, ctypes.byref(tower._cfg),
+                                _C.ptr(flat), _C.ptr(g_out.contiguous()),
+                                _C.ptr(mask), _C.ptr(ws), _C.ptr(grads),
+                                tower._precision, _C.stream()))
+    return None, grads, None, None
+
+
+class Tower(torch.nn.Module):
+  """Feed-forward tower: (Dense -> activation) x L -> Dense(output_units)."""
+
+  def __init__(self, input_dim, hidden_layer_dims, output_units, activation=None,
+               precision='fp32', seed=None, device='cuda'):
+    super().__init__()
+    self.input_dim = int(input_dim)
+    self.hidden_layer_dims = [int(h) for h in hidden_layer_dims]
+    self.output_units = int(output_units)
+    self.activation = activation
+    dims = [self.input_dim] + self.hidden_layer_dims + [self.output_units]
+    if len(dims) - 1 > _C.MLP_MAX_LAYERS:
+      raise ValueError('at most %d Dense layers are supported' % _C.MLP_MAX_LAYERS)
+    cfg = _C.MlpCfg()
+    cfg.n_dense = len(dims) - 1
+    for i, d in enumerate(dims):
+      cfg.dims[i] = d
+    cfg.activation = _activation_enum(activation)
+    self._cfg = cfg
+    self.dims = dims
+    self.set_precision(precision)
+    n = _C.lib.tfr_mlp_param_count(ctypes.byref(cfg))
+    if n == 0:
+      raise ValueError(_C.last_error())
+    # Keras defaults: glorot_uniform kernels, zero biases.
+    gen = torch.Generator()
+    if seed is not None:
+      gen.manual_seed(seed)
+    flat = torch.zeros(n, dtype=torch.float32)
+    self.offsets = []
+    off = 0
+    for i in range(cfg.n_dense):
+      fi, fo = dims[i], dims[i + 1]
+      limit = math.sqrt(6.0 / (fi + fo))
+      w = (torch.rand(fi, fo, generator=gen, dtype=torch.float64) * 2 * limit -
+           limit).float()
+      flat[off:off + fi * fo] = w.reshape(-1)
+      self.offsets.append((off, off + fi * fo, off + fi * fo + fo))
+      off += fi * fo + fo
+    self.flat = torch.nn.Parameter(flat.to(device))
+
+  def set_precision(self, precision):
+    if precision not in _PRECISIONS:
+      raise ValueError('precision must be one of %s' % sorted(_PRECISIONS))
+    self.precision = precision
+    self._precision = _PRECISIONS[precision]
+
+  def kernel(self, i):
+    a, b, _ = self.offsets[i]
+    return self.flat[a:b].view(self.dims[i], self.dims[i + 1])
+
+  def bias(self, i):
+    _, b, c = self.offsets[i]
+    return self.flat[b:c]
+
+  def load_keras_weights(self, kernels, biases):
+    """Loads per-layer Dense kernels [in, out] / biases (Keras `get_weights()`)."""
+    with torch.no_grad():
+      for i, (k, b) in enumerate(zip(kernels, biases)):
+        self.kernel(i).copy_(torch.as_tensor(k, dtype=torch.float32))
+        self.bias(i).copy_(torch.as_tensor(b, dtype=torch.float32))
+
+  def _new_workspace(self, m):
+    nbytes = _C.lib.tfr_mlp_workspace_bytes(ctypes.byref(self._cfg), m)
+    return torch.empty(nbytes, dtype=torch.uint8, device=self.flat.device)
+
+  def forward(self, inputs, mask=None):
+    """inputs [..., input_dim] -> [..., output_units] (flattened internally).
+    `mask` (flat bool [M]) applies RestoreList's ln(1e-10) fill in-kernel."""
+    x = inputs
+    _C.require_cuda(x, 'tower inputs')
+    lead = x.shape[:-1]
+    if x.shape[-1] != self.input_dim:
+      raise ValueError('expected last dim %d, got %d' % (self.input_dim,
+                                                        x.shape[-1]))
+    if x.requires_grad:
+      raise NotImplementedError('gradients w.r.t. tower inputs are not computed')
+    x = x.reshape(-1, self.input_dim).float().contiguous()
+    m8 = None if mask is None else mask.reshape(-1).to(torch.uint8).contiguous()
+    out = _TowerFn.apply(x, self.flat, m8, self)
+    return out.reshape(*lead, self.output_units)
+
+
+def create_tower(hidden_layer_dims, output_units, activation=None,
+                 input_batch_norm=False, use_batch_norm=True,
+                 batch_norm_moment=0.999, dropout=0.5, name=None,
+                 input_dim=None, precision='fp32', seed=None, **kwargs):
+  """keras/layers.py:26-77.  Same arguments and defaults as the reference.
+
+  The CUDA tower covers the Dense/activation chain.  BatchNormalization and
+  Dropout (both ON by default in the reference) are not in the fused kernels yet:
+  pass `use_batch_norm=False, dropout=0` (DESIGN.md "out of scope / next").
+  `input_dim` is required here because torch modules are built eagerly (Keras
+  infers it at first call); `DNNScorer` supplies it automatically.
+  """
+  if input_batch_norm or use_batch_norm:
+    raise NotImplementedError(
+        'BatchNormalization inside create_tower is not implemented in the CUDA '
+        'tower yet; pass use_batch_norm=False, input_batch_norm=False.')
+  if dropout:
+    raise NotImplementedError(
+        'Dropout inside create_tower is not implemented in the CUDA tower yet; '
+        'pass dropout=0.')
+  if input_dim is None:
+    raise ValueError('create_tower needs input_dim')
+  return Tower(input_dim, hidden_layer_dims, output_units, activation,
+               precision=precision, seed=seed)
+
+
+class FlattenList(torch.nn.Module):
+  """keras/layers.py:80-182."""
+
+  def __init__(self, circular_padding=True, name=None, **kwargs):
+    super().__init__()
+    self._circular_padding = circular_padding
+
+  def forward(self, inputs):
+    context_features, example_features, list_mask = inputs
+    if not example_features:
+      raise ValueError('Need a valid example feature.')
+    list_mask = torch.as_tensor(list_mask)
+    b, n = list_mask.shape
+    flat_ctx = {}
+    for name, t in context_features.items():
+      flat_ctx[name] = t.unsqueeze(1).expand(b, n, *t.shape[1:]).reshape(
+          b * n, *t.shape[1:])
+    idx = None
+    if self._circular_padding and not bool(list_mask.all()):
+      idx, _ = tfr_utils.padded_nd_indices(list_mask)
+    flat_ex = {}
+    for name, t in example_features.items():
+      if idx is not None:
+        gi = idx.reshape(b, n, *([1] * (t.dim() - 2))).expand(-1, -1,
+                                                              *t.shape[2:])
+        t = torch.gather(t, 1, gi)
+      flat_ex[name] = t.reshape(b * n, *t.shape[2:])
+    return flat_ctx, flat_ex
+
+  def get_config(self):
+    return {'circular_padding': self._circular_padding}
+
+
+class RestoreList(torch.nn.Module):
+  """keras/layers.py:185-272."""
+
+  def __init__(self, name=None, by_scatter=False, **kwargs):
+    super().__init__()
+    self._by_scatter = by_scatter
+
+  def forward(self, inputs):
+    flattened_logits, list_mask = inputs
+    list_mask = torch.as_tensor(list_mask)
+    try:
+      logits = flattened_logits.reshape(list_mask.shape)
+    except RuntimeError:
+      raise ValueError('`flattened_logits` needs to be either 1D of [batch_size '
+                       '* list_size] or 2D of [batch_size * list_size, 1].')
+    fill = torch.full_like(logits, _LOG_EPSILON)
+    if self._by_scatter:
+      idx, _ = tfr_utils.padded_nd_indices(list_mask)
+      counts = torch.zeros_like(logits).scatter_add_(1, idx,
+                                                     torch.ones_like(logits))
+      summed = torch.zeros_like(logits).scatter_add_(1, idx, logits)
+      return torch.where(counts > 0., summed / counts.clamp(min=1.), fill)
+    return torch.where(list_mask, logits, fill)
+
+  def get_config(self):
+    return {'by_scatter': self._by_scatter}

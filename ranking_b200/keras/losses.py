@@ -1,0 +1,347 @@
+"""The `tfr.keras.losses` surface on torch tensors + fused CUDA kernels.
+
+Mirrors tensorflow_ranking/python/keras/losses.py: `RankingLossKey`, `get`,
+the serialisable LambdaWeight classes with their Keras defaults, and the loss
+classes `__call__(y_true, y_pred, sample_weight=None) -> scalar` with the Keras
+reduction semantics (AUTO / SUM_OVER_BATCH_SIZE -> sum / numel of the per-item
+or per-list loss tensor; pairwise losses therefore divide by B*N,
+keras/losses.py:324-335; listwise by B).  Losses are differentiable w.r.t.
+`y_pred` through torch autograd.
+"""
+import torch
+
+from ranking_b200 import _C
+from ranking_b200 import losses_impl
+from ranking_b200.keras import utils
+
+
+class Reduction(object):
+  """tf.keras.losses.Reduction."""
+  AUTO = 'auto'
+  NONE = 'none'
+  SUM = 'sum'
+  SUM_OVER_BATCH_SIZE = 'sum_over_batch_size'
+
+  @classmethod
+  def validate(cls, key):
+    if key not in (cls.AUTO, cls.NONE, cls.SUM, cls.SUM_OVER_BATCH_SIZE):
+      raise ValueError('Invalid Reduction Key: {}.'.format(key))
+
+
+class RankingLossKey(object):
+  """keras/losses.py:25-48 (keys of losses not on the hot path are listed so
+  that `get` can say precisely what is unsupported)."""
+  PAIRWISE_HINGE_LOSS = 'pairwise_hinge_loss'
+  PAIRWISE_LOGISTIC_LOSS = 'pairwise_logistic_loss'
+  PAIRWISE_SOFT_ZERO_ONE_LOSS = 'pairwise_soft_zero_one_loss'
+  PAIRWISE_MSE_LOSS = 'pairwise_mse_loss'
+  YETI_LOGISTIC_LOSS = 'yeti_logistic_loss'
+  SOFTMAX_LOSS = 'softmax_loss'
+  CALIBRATED_SOFTMAX_LOSS = 'calibrated_softmax_loss'
+  UNIQUE_SOFTMAX_LOSS = 'unique_softmax_loss'
+  SIGMOID_CROSS_ENTROPY_LOSS = 'sigmoid_cross_entropy_loss'
+  MEAN_SQUARED_LOSS = 'mean_squared_loss'
+  ORDINAL_LOSS = 'ordinal_loss'
+  LIST_MLE_LOSS = 'list_mle_loss'
+  APPROX_NDCG_LOSS = 'approx_ndcg_loss'
+  APPROX_MRR_LOSS = 'approx_mrr_loss'
+  GUMBEL_APPROX_NDCG_LOSS = 'gumbel_approx_ndcg_loss'
+  COUPLED_RANKDISTIL_LOSS = 'coupled_rankdistil_loss'
+
+  @classmethod
+  def all_keys(cls):
+    return [v for k, v in vars(cls).items() if k.isupper()]
+
+
+# ---------------------------------------------------------------------------
+# LambdaWeights with Keras defaults (keras/losses.py:114-244)
+# ---------------------------------------------------------------------------
+class LabelDiffLambdaWeight(losses_impl.LabelDiffLambdaWeight):
+
+  def __init__(self, **kwargs):
+    super().__init__()
+
+  def get_config(self):
+    return {}
+
+
+class DCGLambdaWeight(losses_impl.DCGLambdaWeight):
+
+  def __init__(self, topn=None, gain_fn=None, rank_discount_fn=None,
+               normalized=False, smooth_fraction=0., **kwargs):
+    super().__init__(topn, gain_fn or utils.identity,
+                     rank_discount_fn or utils.inverse, normalized,
+                     smooth_fraction)
+
+  def get_config(self):
+    return {
+        'topn': self._topn,
+        'gain_fn': self._gain_fn,
+        'rank_discount_fn': self._rank_discount_fn,
+        'normalized': self._normalized,
+        'smooth_fraction': self._smooth_fraction,
+    }
+
+
+class NDCGLambdaWeight(DCGLambdaWeight):
+
+  def __init__(self, topn=None, gain_fn=None, rank_discount_fn=None,
+               smooth_fraction=0., **kwargs):
+    super().__init__(topn, gain_fn or utils.pow_minus_1,
+                     rank_discount_fn or utils.log2_inverse, normalized=True,
+                     smooth_fraction=smooth_fraction)
+
+
+class NDCGLambdaWeightV2(losses_impl.DCGLambdaWeightV2):
+
+  def __init__(self, topn=None, gain_fn=None, rank_discount_fn=None, **kwargs):
+    super().__init__(topn, gain_fn or utils.pow_minus_1,
+                     rank_discount_fn or utils.log2_inverse, normalized=True)
+
+  def get_config(self):
+    return {
+        'topn': self._topn,
+        'gain_fn': self._gain_fn,
+        'rank_discount_fn': self._rank_discount_fn,
+    }
+
+
+class YetiDCGLambdaWeight(losses_impl.YetiDCGLambdaWeight):
+
+  def __init__(self, topn=None, gain_fn=None, rank_discount_fn=None,
+               normalized=False, **kwargs):
+    super().__init__(topn, gain_fn or utils.pow_minus_1,
+                     rank_discount_fn or utils.log2_inverse,
+                     normalized=normalized)
+
+  def get_config(self):
+    return {
+        'topn': self._topn,
+        'gain_fn': self._gain_fn,
+        'rank_discount_fn': self._rank_discount_fn,
+        'normalized': self._normalized,
+    }
+
+
+class PrecisionLambdaWeight(losses_impl.PrecisionLambdaWeight):
+
+  def __init__(self, topn=None, positive_fn=None, **kwargs):
+    super().__init__(topn, positive_fn or utils.is_greater_equal_1)
+
+  def get_config(self):
+    return {'topn': self._topn, 'positive_fn': self._positive_fn}
+
+
+# ---------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------
+def _keras_reduce(losses, sample_weight, reduction):
+  """tf.keras compute_weighted_loss: rank-align the weights, multiply, reduce."""
+  if sample_weight is not None and not isinstance(sample_weight, float):
+    sw = sample_weight
+    if sw.dim() == losses.dim() + 1 and sw.shape[-1] == 1:
+      sw = sw.squeeze(-1)
+    elif sw.dim() == losses.dim() - 1:
+      sw = sw.unsqueeze(-1)
+    losses = losses * sw
+  elif isinstance(sample_weight, float) and sample_weight != 1.0:
+    losses = losses * sample_weight
+  if reduction == Reduction.NONE:
+    return losses
+  total = losses.sum()
+  if reduction == Reduction.SUM:
+    return total
+  return total / float(losses.numel())
+
+
+class _RankingLoss(object):
+  """keras/losses.py:247-285."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, ragged=False):
+    Reduction.validate(reduction)
+    self.reduction = reduction
+    self.name = name
+    self._loss = None
+    self._ragged = ragged
+
+  def __call__(self, y_true, y_pred, sample_weight=None):
+    raise NotImplementedError
+
+  def get_config(self):
+    return {'reduction': self.reduction, 'name': self.name,
+            'ragged': self._ragged}
+
+  @classmethod
+  def from_config(cls, config):
+    return cls(**config)
+
+
+class _PairwiseLoss(_RankingLoss):
+  """keras/losses.py:288-335."""
+  _impl = None
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, lambda_weight=None,
+               temperature=1.0, ragged=False, **kwargs):
+    super().__init__(reduction, name, ragged)
+    self._lambda_weight = lambda_weight
+    self._temperature = temperature
+    self._loss = self._impl(name='{}_impl'.format(name) if name else None,
+                            lambda_weight=lambda_weight,
+                            temperature=temperature, ragged=ragged)
+
+  def __call__(self, y_true, y_pred, sample_weight=None):
+    # `normalize_weights` + `call` + the Keras reduction of the reference are
+    # one kernel here: row sums already carry the item weights w_i.
+    row = self._loss.compute_row_sums(y_true, y_pred, sample_weight)
+    return _keras_reduce(row, None, self.reduction)
+
+  def fused_fwd_bwd(self, y_true, y_pred, sample_weight, grad_out, per_list,
+                    total2):
+    """Training fast path: ONE launch writes d loss / d y_pred (already divided
+    by the Keras normaliser) into `grad_out` and the per-list loss sums into
+    `per_list[0]`; a second tiny launch reduces the scalar loss into `total2[0]`.
+    No autograd graph, no intermediate tensors."""
+    labels, logits = losses_impl._prep_2d(y_true, y_pred)
+    w, wpi = losses_impl._prep_weights(sample_weight, logits)
+    b, n = logits.shape
+    scale = 1.0 if self.reduction == Reduction.SUM else 1.0 / float(b * n)
+    cfg, keep = losses_impl._lambda_cfg(self._lambda_weight, labels)
+    _C.check(_C.lib.tfr_pairwise_loss_fwd_bwd(
+        _C.ptr(logits), _C.ptr(labels), _C.ptr(w), wpi, None, b, n,
+        float(self._temperature), self._loss._phi, losses_impl._byref(cfg),
+        scale, _C.ptr(grad_out), None, _C.ptr(per_list[0]), None, None, None,
+        _C.stream()))
+    del keep
+    _C.check(_C.lib.tfr_weighted_sum(_C.ptr(per_list[0]), None, b, scale,
+                                     _C.ptr(total2), _C.stream()))
+
+  def get_config(self):
+    config = super().get_config()
+    config.update({'lambda_weight': self._lambda_weight,
+                   'temperature': self._temperature})
+    return config
+
+
+class PairwiseHingeLoss(_PairwiseLoss):
+  """keras/losses.py:338-402."""
+  _impl = losses_impl.PairwiseHingeLoss
+
+
+class PairwiseLogisticLoss(_PairwiseLoss):
+  """keras/losses.py:405-469."""
+  _impl = losses_impl.PairwiseLogisticLoss
+
+
+class PairwiseSoftZeroOneLoss(_PairwiseLoss):
+  """keras/losses.py:472-537."""
+  _impl = losses_impl.PairwiseSoftZeroOneLoss
+
+
+class PairwiseMSELoss(_PairwiseLoss):
+  """keras/losses.py:540-606."""
+  _impl = losses_impl.PairwiseMSELoss
+
+
+class _ListwiseLoss(_RankingLoss):
+  """keras/losses.py:721-755."""
+  _impl = None
+  _default_temperature = 1.0
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, lambda_weight=None,
+               temperature=None, ragged=False, **kwargs):
+    super().__init__(reduction, name, ragged)
+    if temperature is None:
+      temperature = self._default_temperature
+    self._lambda_weight = lambda_weight
+    self._temperature = temperature
+    self._loss = self._impl(name='{}_impl'.format(name) if name else None,
+                            lambda_weight=lambda_weight,
+                            temperature=temperature, ragged=ragged)
+
+  def __call__(self, y_true, y_pred, sample_weight=None):
+    # losses [B] * loss weights [B] (already times the normalised sample
+    # weight, losses_impl.py:1004-1015), then the Keras reduction over [B, 1].
+    losses, weights = self._loss._run(y_true, y_pred, sample_weight, None,
+                                      self._temperature)
+    return _keras_reduce((losses * weights).unsqueeze(1), None, self.reduction)
+
+  def fused_fwd_bwd(self, y_true, y_pred, sample_weight, grad_out, per_list,
+                    total2):
+    """Training fast path (see _PairwiseLoss.fused_fwd_bwd): per_list[0] = loss,
+    per_list[1] = weight, total2[0] = reduced scalar loss."""
+    labels, logits = losses_impl._prep_2d(y_true, y_pred)
+    w, wpi = losses_impl._prep_weights(sample_weight, logits)
+    b, n = logits.shape
+    scale = 1.0 if self.reduction == Reduction.SUM else 1.0 / float(b)
+    kind = self._loss._kind
+    if kind == 'softmax':
+      cfg, keep = losses_impl._lambda_cfg(self._lambda_weight, labels)
+      _C.check(_C.lib.tfr_softmax_loss_fwd_bwd(
+          _C.ptr(logits), _C.ptr(labels), _C.ptr(w), wpi, None, b, n,
+          float(self._temperature), losses_impl._byref(cfg), scale, 1,
+          _C.ptr(grad_out), _C.ptr(per_list[0]), _C.ptr(per_list[1]),
+          _C.stream()))
+      del keep
+    else:
+      _C.check(_C.lib.tfr_approx_loss_fwd_bwd(
+          _C.ptr(logits), _C.ptr(labels), _C.ptr(w), wpi, None, b, n,
+          float(self._temperature), 0 if kind == 'ndcg' else 1, scale, 1,
+          _C.ptr(grad_out), _C.ptr(per_list[0]), _C.ptr(per_list[1]),
+          _C.stream()))
+    _C.check(_C.lib.tfr_weighted_sum(_C.ptr(per_list[0]), _C.ptr(per_list[1]), b,
+                                     scale, _C.ptr(total2), _C.stream()))
+
+  def get_config(self):
+    config = super().get_config()
+    config.update({'lambda_weight': self._lambda_weight,
+                   'temperature': self._temperature})
+    return config
+
+
+class SoftmaxLoss(_ListwiseLoss):
+  """keras/losses.py:758-832."""
+  _impl = losses_impl.SoftmaxLoss
+
+  def __call__(self, y_true, y_pred, sample_weight=None):
+    losses, weights = self._loss.compute_per_list(y_true, y_pred, sample_weight)
+    return _keras_reduce(losses * weights, None, self.reduction)
+
+
+class ApproxNDCGLoss(_ListwiseLoss):
+  """keras/losses.py:1164-1237."""
+  _impl = losses_impl.ApproxNDCGLoss
+  _default_temperature = 0.1
+
+
+class ApproxMRRLoss(_ListwiseLoss):
+  """keras/losses.py:1093-1161."""
+  _impl = losses_impl.ApproxMRRLoss
+  _default_temperature = 0.1
+
+
+_KEY_TO_CLS = {
+    RankingLossKey.APPROX_NDCG_LOSS: ApproxNDCGLoss,
+    RankingLossKey.APPROX_MRR_LOSS: ApproxMRRLoss,
+}
+_KEY_TO_CLS_WITH_LAMBDA = {
+    RankingLossKey.PAIRWISE_HINGE_LOSS: PairwiseHingeLoss,
+    RankingLossKey.PAIRWISE_LOGISTIC_LOSS: PairwiseLogisticLoss,
+    RankingLossKey.PAIRWISE_SOFT_ZERO_ONE_LOSS: PairwiseSoftZeroOneLoss,
+    RankingLossKey.PAIRWISE_MSE_LOSS: PairwiseMSELoss,
+    RankingLossKey.SOFTMAX_LOSS: SoftmaxLoss,
+}
+
+
+def get(loss, reduction=Reduction.AUTO, lambda_weight=None, name=None, **kwargs):
+  """keras/losses.py:51-111."""
+  loss_kwargs = {'reduction': reduction, 'name': name}
+  loss_kwargs.update(kwargs)
+  if loss in _KEY_TO_CLS:
+    return _KEY_TO_CLS[loss](**loss_kwargs)
+  if loss in _KEY_TO_CLS_WITH_LAMBDA:
+    return _KEY_TO_CLS_WITH_LAMBDA[loss](lambda_weight=lambda_weight,
+                                         **loss_kwargs)
+  if loss in RankingLossKey.all_keys():
+    raise ValueError('unsupported loss: {} (not on the B200 hot path yet; see '
+                     'DESIGN.md scope)'.format(loss))
+  raise ValueError('unsupported loss: {}'.format(loss))

@@ -1,0 +1,178 @@
+"""The `tfr.keras.metrics` surface (keras/metrics.py) for NDCG and MRR.
+
+Each metric is a running weighted mean (tf.keras.metrics.Mean semantics,
+keras/metrics.py:156-193): state = (sum v*w, sum w) kept on the device;
+`update_state(y_true, y_pred, sample_weight=None)`, `result()`,
+`reset_state()`.  `default_keras_metrics()`-style groups of NDCG@k / MRR can be
+evaluated with ONE kernel launch through `MetricGroup`.
+"""
+import torch
+import torch.distributed as dist
+
+from ranking_b200 import metrics_impl
+from ranking_b200.keras import utils
+
+
+class RankingMetricKey(object):
+  """keras/metrics.py:34-66."""
+  MRR = 'mrr'
+  ARP = 'arp'
+  NDCG = 'ndcg'
+  DCG = 'dcg'
+  PRECISION = 'precision'
+  MAP = 'map'
+  PRECISION_IA = 'precision_ia'
+  ORDERED_PAIR_ACCURACY = 'ordered_pair_accuracy'
+  ALPHA_DCG = 'alpha_dcg'
+  HITS = 'hits'
+
+
+class _RankingMetric(object):
+  """keras/metrics.py:156-200."""
+
+  def __init__(self, name=None, dtype=None, ragged=False, **kwargs):
+    self.name = name
+    self._dtype = dtype or torch.float32
+    self._ragged = ragged
+    self._metric = None
+    self._state = None   # device tensor [2] = (sum v*w, sum w)
+
+  def reset_state(self):
+    self._state = None
+
+  reset_states = reset_state
+
+  def update_state(self, y_true, y_pred, sample_weight=None):
+    v, w = self._metric.compute(y_true, y_pred, sample_weight)
+    upd = torch.stack([(v * w).sum(), w.sum()])
+    self._state = upd if self._state is None else self._state + upd
+
+  def all_reduce(self, group=None):
+    """Data-parallel evaluation: SUM the (sum v*w, sum w) pair across ranks."""
+    if self._state is not None and dist.is_available() and dist.is_initialized():
+      dist.all_reduce(self._state, op=dist.ReduceOp.SUM, group=group)
+
+  def result(self):
+    if self._state is None:
+      return torch.zeros((), dtype=torch.float32)
+    s = self._state
+    return torch.where(s[1] != 0, s[0] / torch.where(s[1] != 0, s[1],
+                                                     torch.ones_like(s[1])),
+                       torch.zeros_like(s[0]))
+
+  def __call__(self, y_true, y_pred, sample_weight=None):
+    self.update_state(y_true, y_pred, sample_weight)
+    return self.result()
+
+  def get_config(self):
+    return {'name': self.name, 'dtype': self._dtype, 'ragged': self._ragged}
+
+
+class MRRMetric(_RankingMetric):
+  """keras/metrics.py:203-266."""
+
+  def __init__(self, name=None, topn=None, dtype=None, ragged=False, **kwargs):
+    super().__init__(name=name, dtype=dtype, ragged=ragged, **kwargs)
+    self._topn = topn
+    self._metric = metrics_impl.MRRMetric(name=name, topn=topn, ragged=ragged)
+
+  def get_config(self):
+    config = super().get_config()
+    config.update({'topn': self._topn})
+    return config
+
+
+class NDCGMetric(_RankingMetric):
+  """keras/metrics.py:709-796."""
+
+  def __init__(self, name=None, topn=None, gain_fn=None, rank_discount_fn=None,
+               dtype=None, ragged=False, **kwargs):
+    super().__init__(name=name, dtype=dtype, ragged=ragged, **kwargs)
+    self._topn = topn
+    self._gain_fn = gain_fn or utils.pow_minus_1
+    self._rank_discount_fn = rank_discount_fn or utils.log2_inverse
+    self._metric = metrics_impl.NDCGMetric(
+        name=name, topn=topn, gain_fn=self._gain_fn,
+        rank_discount_fn=self._rank_discount_fn, ragged=ragged)
+
+  def get_config(self):
+    config = super().get_config()
+    config.update({'topn': self._topn, 'gain_fn': self._gain_fn,
+                   'rank_discount_fn': self._rank_discount_fn})
+    return config
+
+
+_KEY_TO_CLS = {RankingMetricKey.MRR: MRRMetric, RankingMetricKey.NDCG: NDCGMetric}
+_ALL_KEYS = [v for k, v in vars(RankingMetricKey).items() if k.isupper()]
+
+
+def get(key, name=None, dtype=None, topn=None, **kwargs):
+  """keras/metrics.py:69-128."""
+  if not isinstance(key, str):
+    raise ValueError('Input `key` needs to be string.')
+  metric_kwargs = {'name': name, 'dtype': dtype}
+  if topn:
+    metric_kwargs.update({'topn': topn})
+  metric_kwargs.update(kwargs)
+  if key in _KEY_TO_CLS:
+    return _KEY_TO_CLS[key](**metric_kwargs)
+  if key in _ALL_KEYS:
+    raise ValueError('Unsupported metric: {} (not on the B200 hot path yet; see '
+                     'DESIGN.md scope)'.format(key))
+  raise ValueError('Unsupported metric: {}'.format(key))
+
+
+def default_keras_metrics(**kwargs):
+  """keras/metrics.py:131-153, restricted to the metrics on the hot path:
+  NDCG@{1,3,5,10}, MRR, NDCG."""
+  list_kwargs = [
+      dict(key='ndcg', topn=topn, name='metric/ndcg_{}'.format(topn), **kwargs)
+      for topn in [1, 3, 5, 10]
+  ] + [
+      dict(key='mrr', name='metric/mrr', **kwargs),
+      dict(key='ndcg', name='metric/ndcg', **kwargs),
+  ]
+  return [get(**kw) for kw in list_kwargs]
+
+
+class MetricGroup(object):
+  """NDCG@k for several k, plus MRR, from ONE K4 launch per update.
+
+  `default_keras_metrics()` in the reference builds one object per cut-off and
+  each re-sorts the batch; this evaluates them together.
+  """
+
+  def __init__(self, topns=(1, 3, 5, 10, None), gain_fn=None,
+               rank_discount_fn=None):
+    self.topns = tuple(topns)
+    self._gain_fn = gain_fn
+    self._rank_discount_fn = rank_discount_fn
+    self._state = None    # [2T + 2]: sum ndcg_t*w (T), sum mrr_t*w (T), sum w_ndcg, sum w_mrr
+
+  def reset_state(self):
+    self._state = None
+
+  def update_state(self, y_true, y_pred, sample_weight=None):
+    o = metrics_impl.rank_metrics(y_true, y_pred, sample_weight, None,
+                                  self.topns, self._gain_fn,
+                                  self._rank_discount_fn)
+    upd = torch.cat([
+        (o['ndcg'] * o['ndcg_w'].unsqueeze(1)).sum(0),
+        (o['mrr'] * o['mrr_w'].unsqueeze(1)).sum(0),
+        o['ndcg_w'].sum().reshape(1), o['mrr_w'].sum().reshape(1)])
+    self._state = upd if self._state is None else self._state + upd
+
+  def all_reduce(self, group=None):
+    if self._state is not None and dist.is_available() and dist.is_initialized():
+      dist.all_reduce(self._state, op=dist.ReduceOp.SUM, group=group)
+
+  def result(self):
+    t = len(self.topns)
+    s = self._state.double().cpu()
+    out = {}
+    for i, k in enumerate(self.topns):
+      suffix = '' if not k else '_{}'.format(k)
+      out['metric/ndcg' + suffix] = float(s[i] / s[2 * t]) if s[2 * t] else 0.0
+      out['metric/mrr' + suffix] = float(s[t + i] / s[2 * t + 1]) if s[
+          2 * t + 1] else 0.0
+    return out

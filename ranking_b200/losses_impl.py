@@ -1,0 +1,486 @@
+"""Host-side mirror of tensorflow_ranking/python/losses_impl.py for the hot path.
+
+Same class names, constructor arguments and method meaning as the reference
+(`compute`, `compute_per_list`, `normalize_weights`, `get_logits`), but every
+numeric step runs in the fused CUDA kernels behind the C ABI
+(include/tfr_b200.h): no [B, N, N] tensor is ever created.  Gradients are
+produced by the same kernel launch as the forward values (weights and ranks are
+`stop_gradient` constants in the reference, losses_impl.py:882-883), and are
+wired into torch autograd through `torch.autograd.Function`.
+"""
+import ctypes
+
+import torch
+
+from ranking_b200 import _C
+from ranking_b200.keras import utils as keras_utils
+
+_EPSILON = 1e-10
+
+
+class Reduction(object):
+  """tf.compat.v1.losses.Reduction values used by `compute` (losses.py:66-67)."""
+  NONE = 'none'
+  SUM = 'weighted_sum'
+  MEAN = 'weighted_mean'
+  SUM_OVER_BATCH_SIZE = 'weighted_sum_over_batch_size'
+  SUM_BY_NONZERO_WEIGHTS = 'weighted_sum_by_nonzero_weights'
+
+
+# ----------------------------------------------------------------------------
+# tensor plumbing
+# ----------------------------------------------------------------------------
+def _as_f32(x, device=None, what='tensor'):
+  if not torch.is_tensor(x):
+    x = torch.as_tensor(x, dtype=torch.float32,
+                        device=device if device is not None else 'cuda')
+  _C.require_cuda(x, what)
+  if x.dtype != torch.float32:
+    x = x.float()
+  return x.contiguous()
+
+
+def _prep_2d(labels, logits):
+  logits = _as_f32(logits, what='logits')
+  labels = _as_f32(labels, logits.device, 'labels')
+  if logits.dim() != 2 or labels.shape != logits.shape:
+    raise ValueError('labels and logits must both have shape [batch_size, '
+                     'list_size]; got %s and %s' % (tuple(labels.shape),
+                                                    tuple(logits.shape)))
+  return labels, logits
+
+
+def _prep_weights(weights, like):
+  """None | scalar | [B, 1] | [B] | [B, N] -> (tensor or None, w_per_item)."""
+  if weights is None:
+    return None, 0
+  b, n = like.shape
+  w = _as_f32(weights, like.device, 'weights')
+  if w.dim() == 0:
+    return w.expand(b).contiguous(), 0
+  if w.dim() == 1 and w.shape[0] == b:
+    return w, 0
+  if w.dim() == 2 and w.shape == (b, 1):
+    return w.reshape(b).contiguous(), 0
+  if w.dim() == 2 and w.shape == (b, n):
+    return w, 1
+  if w.dim() == 2 and w.shape == (1, n):
+    return w.expand(b, n).contiguous(), 1
+  raise ValueError('weights must be a scalar, [batch_size, 1] or [batch_size, '
+                   'list_size]; got %s' % (tuple(w.shape),))
+
+
+def _prep_mask(mask, like):
+  if mask is None:
+    return None
+  m = torch.as_tensor(mask, device=like.device)
+  if m.shape != like.shape:
+    raise ValueError('mask must have the shape of logits')
+  return m.to(torch.uint8).contiguous()
+
+
+def _safe_div(num, den):
+  den_t = torch.as_tensor(den, dtype=num.dtype, device=num.device)
+  return torch.where(den_t != 0, num / torch.where(den_t != 0, den_t,
+                                                   torch.ones_like(den_t)),
+                     torch.zeros_like(num))
+
+
+# ----------------------------------------------------------------------------
+# LambdaWeight family (losses_impl.py:170-454): configuration objects that
+# select the in-kernel lambda; `pair_weights` materialises [B, N, N] for parity
+# tests only (small N).
+# ----------------------------------------------------------------------------
+_GAIN_ENUM = {keras_utils.identity: _C.GAIN_IDENTITY,
+              keras_utils.pow_minus_1: _C.GAIN_POW2_MINUS_1}
+_DISC_ENUM = {keras_utils.inverse: _C.DISC_INVERSE,
+              keras_utils.log2_inverse: _C.DISC_LOG2_INVERSE,
+              keras_utils.log1p_inverse: _C.DISC_LOG1P_INVERSE}
+
+
+class _LambdaWeight(object):
+  _kind = _C.LAMBDA_NONE
+  _topn = None
+  _gain_fn = None
+  _rank_discount_fn = None
+  _normalized = False
+  _smooth_fraction = 0.
+
+  def _cfg(self, labels):
+    """Builds the C struct for a [B, N] label tensor; returns (cfg, keepalive)."""
+    keep = []
+    cfg = _C.LambdaCfg()
+    cfg.kind = self._kind
+    cfg.topn = int(self._topn) if self._topn else 0
+    cfg.normalized = 1 if self._normalized else 0
+    cfg.smooth_fraction = float(self._smooth_fraction)
+    cfg.gain_fn = _C.GAIN_IDENTITY
+    cfg.disc_fn = _C.DISC_INVERSE
+    cfg.gain_table = None
+    cfg.disc_table = None
+    n = labels.shape[1]
+    if self._gain_fn is not None:
+      if self._gain_fn in _GAIN_ENUM:
+        cfg.gain_fn = _GAIN_ENUM[self._gain_fn]
+      elif self._kind == _C.LAMBDA_PRECISION and \
+          self._gain_fn is keras_utils.is_greater_equal_1:
+        cfg.gain_fn = _C.GAIN_IDENTITY
+      else:
+        cleaned = torch.where(labels >= 0, labels, torch.zeros_like(labels))
+        table = torch.as_tensor(self._gain_fn(cleaned)).to(
+            torch.float32).contiguous()
+        keep.append(table)
+        cfg.gain_fn = _C.GAIN_TABLE
+        cfg.gain_table = table.data_ptr()
+    if self._rank_discount_fn is not None:
+      if self._rank_discount_fn in _DISC_ENUM:
+        cfg.disc_fn = _DISC_ENUM[self._rank_discount_fn]
+      else:
+        r = torch.arange(0, n + 2, dtype=torch.float32, device=labels.device)
+        r[0] = 1.0   # d(0) is never used; avoid evaluating user code at 0
+        table = torch.as_tensor(self._rank_discount_fn(r)).to(
+            torch.float32).contiguous()
+        keep.append(table)
+        cfg.disc_fn = _C.DISC_TABLE
+        cfg.disc_table = table.data_ptr()
+    return cfg, keep
+
+  def pair_weights(self, labels, ranks):
+    """[B, N, N] lambda pair weights for given 1-based ranks (parity helper)."""
+    labels = _as_f32(labels, what='labels')
+    ranks = torch.as_tensor(ranks, device=labels.device).to(
+        torch.int32).contiguous()
+    b, n = labels.shape
+    out = torch.empty(b, n, n, dtype=torch.float32, device=labels.device)
+    cfg, keep = self._cfg(labels)
+    _C.check(_C.lib.tfr_lambda_pair_weights(
+        _C.ptr(labels), _C.ptr(ranks), b, n, ctypes.byref(cfg), _C.ptr(out),
+        _C.stream()))
+    del keep
+    return out
+
+  def individual_weights(self, labels, ranks):
+    """losses_impl.py:195-207."""
+    return labels
+
+
+class LabelDiffLambdaWeight(_LambdaWeight):
+  """losses_impl.py:210-216."""
+  _kind = _C.LAMBDA_LABEL_DIFF
+
+
+class AbstractDCGLambdaWeight(_LambdaWeight):
+  """losses_impl.py:219-296."""
+
+  def __init__(self, topn=None, gain_fn=None, rank_discount_fn=None,
+               normalized=False):
+    self._topn = topn
+    self._gain_fn = gain_fn or keras_utils.identity
+    self._rank_discount_fn = rank_discount_fn or keras_utils.inverse
+    self._normalized = normalized
+
+
+class DCGLambdaWeight(AbstractDCGLambdaWeight):
+  """losses_impl.py:299-369."""
+  _kind = _C.LAMBDA_DCG
+
+  def __init__(self, topn=None, gain_fn=None, rank_discount_fn=None,
+               normalized=False, smooth_fraction=0.):
+    super().__init__(topn, gain_fn, rank_discount_fn, normalized)
+    if not 0. <= smooth_fraction <= 1.:
+      raise ValueError('smooth_fraction %s should be in range [0, 1].' %
+                       smooth_fraction)
+    self._smooth_fraction = smooth_fraction
+
+
+class DCGLambdaWeightV2(AbstractDCGLambdaWeight):
+  """losses_impl.py:372-394."""
+  _kind = _C.LAMBDA_DCG_V2
+
+
+class YetiDCGLambdaWeight(DCGLambdaWeightV2):
+  """losses_impl.py:397-407."""
+  _kind = _C.LAMBDA_YETI
+
+
+class PrecisionLambdaWeight(_LambdaWeight):
+  """losses_impl.py:410-454."""
+  _kind = _C.LAMBDA_PRECISION
+
+  def __init__(self, topn, positive_fn=None):
+    self._topn = topn
+    self._gain_fn = positive_fn or keras_utils.is_greater_equal_1
+    self._positive_fn = self._gain_fn
+
+
+def _lambda_cfg(lambda_weight, labels):
+  if lambda_weight is None:
+    return None, []
+  if not isinstance(lambda_weight, _LambdaWeight):
+    raise ValueError('lambda_weight must be a ranking_b200 LambdaWeight object')
+  cfg, keep = lambda_weight._cfg(labels)
+  return cfg, keep
+
+
+def _byref(cfg):
+  return ctypes.byref(cfg) if cfg is not None else None
+
+
+# ----------------------------------------------------------------------------
+# autograd bridges
+# ----------------------------------------------------------------------------
+class _PairwiseFn(torch.autograd.Function):
+  """loss_sum[B], row_loss[B, N], w_sum[B], nnz[B] = K1(logits, ...)."""
+
+  @staticmethod
+  def forward(ctx, logits, labels, w, w_per_item, mask, temperature, phi,
+              lambda_weight):
+    b, n = logits.shape
+    dev = logits.device
+    grad = torch.empty_like(logits)
+    row_loss = torch.empty_like(logits)
+    loss_sum = torch.empty(b, dtype=torch.float32, device=dev)
+    w_sum = torch.empty_like(loss_sum)
+    nnz = torch.empty_like(loss_sum)
+    cfg, keep = _lambda_cfg(lambda_weight, labels)
+    _C.check(_C.lib.tfr_pairwise_loss_fwd_bwd(
+        _C.ptr(logits), _C.ptr(labels), _C.ptr(w), w_per_item, _C.ptr(mask), b,
+        n, float(temperature), phi, _byref(cfg), 1.0, _C.ptr(grad),
+        _C.ptr(row_loss), _C.ptr(loss_sum), _C.ptr(w_sum), _C.ptr(nnz), None,
+        _C.stream()))
+    del keep
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(grad, logits, labels, w, mask)
+    ctx.args = (w_per_item, temperature, phi, lambda_weight)
+    ctx.mark_non_differentiable(w_sum, nnz)
+    return loss_sum, row_loss, w_sum, nnz
+
+  @staticmethod
+  def backward(ctx, g_sum, g_row, _gw, _gn):
+    grad, logits, labels, w, mask = ctx.saved_tensors
+    w_per_item, temperature, phi, lambda_weight = ctx.args
+    out = None
+    if g_row is None:
+      if g_sum is not None:
+        out = grad * g_sum.reshape(-1, 1)
+    else:
+      # Non-uniform upstream gradient per row (reduction NONE): rerun K1 with the
+      # row weights scaled by the upstream gradient; W_ij is linear in w_i.
+      b, n = logits.shape
+      scale = g_row if g_sum is None else g_row + g_sum.reshape(-1, 1)
+      if w is None:
+        w_eff = scale.contiguous()
+      else:
+        w_eff = (scale * (w if w_per_item else w.reshape(-1, 1))).contiguous()
+      out = torch.empty_like(logits)
+      dummy = torch.empty(b, dtype=torch.float32, device=logits.device)
+      cfg, keep = _lambda_cfg(lambda_weight, labels)
+      _C.check(_C.lib.tfr_pairwise_loss_fwd_bwd(
+          _C.ptr(logits), _C.ptr(labels), _C.ptr(w_eff), 1, _C.ptr(mask), b, n,
+          float(temperature), phi, _byref(cfg), 1.0, _C.ptr(out), None,
+          _C.ptr(dummy), None, None, None, _C.stream()))
+      del keep
+    return out, None, None, None, None, None, None, None
+
+
+class _ListwiseFn(torch.autograd.Function):
+  """loss[B], weight[B] = K2 / K3 (kind: 'ndcg' | 'mrr' | 'softmax')."""
+
+  @staticmethod
+  def forward(ctx, logits, labels, w, w_per_item, mask, temperature, kind,
+              lambda_weight):
+    b, n = logits.shape
+    dev = logits.device
+    grad = torch.empty_like(logits)
+    loss = torch.empty(b, dtype=torch.float32, device=dev)
+    weight = torch.empty_like(loss)
+    if kind == 'softmax':
+      cfg, keep = _lambda_cfg(lambda_weight, labels)
+      _C.check(_C.lib.tfr_softmax_loss_fwd_bwd(
+          _C.ptr(logits), _C.ptr(labels), _C.ptr(w), w_per_item, _C.ptr(mask),
+          b, n, float(temperature), _byref(cfg), 1.0, 0, _C.ptr(grad),
+          _C.ptr(loss), _C.ptr(weight), _C.stream()))
+      del keep
+    else:
+      _C.check(_C.lib.tfr_approx_loss_fwd_bwd(
+          _C.ptr(logits), _C.ptr(labels), _C.ptr(w), w_per_item, _C.ptr(mask),
+          b, n, float(temperature), 0 if kind == 'ndcg' else 1, 1.0, 0,
+          _C.ptr(grad), _C.ptr(loss), _C.ptr(weight), _C.stream()))
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(grad)
+    ctx.mark_non_differentiable(weight)
+    return loss, weight
+
+  @staticmethod
+  def backward(ctx, g_loss, _gw):
+    grad, = ctx.saved_tensors
+    out = None if g_loss is None else grad * g_loss.reshape(-1, 1)
+    return out, None, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------
+# _RankingLoss (losses_impl.py:652-860)
+# ----------------------------------------------------------------------------
+class _RankingLoss(object):
+
+  def __init__(self, name=None, lambda_weight=None, temperature=1.0,
+               ragged=False):
+    if ragged:
+      raise NotImplementedError(
+          'ragged=True needs tf.RaggedTensor inputs; pass dense [B, N] tensors '
+          'padded with label -1 (utils.py:21-23) instead.')
+    self._name = name
+    self._lambda_weight = lambda_weight
+    self._temperature = temperature
+    self._ragged = ragged
+
+  @property
+  def name(self):
+    return self._name
+
+  def get_logits(self, logits):
+    """losses_impl.py:773-785."""
+    return _as_f32(logits, what='logits') / self._temperature
+
+  def normalize_weights(self, labels, weights):
+    """losses_impl.py:745-766."""
+    return self._normalize_weights_impl(_as_f32(labels, what='labels'), weights)
+
+  def _normalize_weights_impl(self, labels, weights):
+    return 1.0 if weights is None else weights
+
+
+class _PairwiseLoss(_RankingLoss):
+  """losses_impl.py:863-930."""
+  _phi = None
+
+  def _run(self, labels, logits, weights, mask, temperature):
+    labels, logits = _prep_2d(labels, logits)
+    w, wpi = _prep_weights(weights, logits)
+    m = _prep_mask(mask, logits)
+    return _PairwiseFn.apply(logits, labels, w, wpi, m, temperature, self._phi,
+                             self._lambda_weight)
+
+  def compute(self, labels, logits, weights, reduction, mask=None):
+    """losses_impl.py:787-814 over [B, N, N] pair losses, reduced per
+    tf.compat.v1.losses.compute_weighted_loss."""
+    loss_sum, _, w_sum, nnz = self._run(labels, logits, weights, mask,
+                                        self._temperature)
+    total = loss_sum.sum()
+    if reduction == Reduction.SUM:
+      return total
+    if reduction == Reduction.MEAN:
+      return _safe_div(total, w_sum.sum())
+    if reduction == Reduction.SUM_BY_NONZERO_WEIGHTS:
+      return _safe_div(total, nnz.sum())
+    if reduction == Reduction.SUM_OVER_BATCH_SIZE:
+      b, n = loss_sum.shape[0], torch.as_tensor(logits).shape[1]
+      return total / float(b * n * n)
+    raise ValueError('reduction %r is not supported for pairwise losses (the '
+                     '[B, N, N] loss tensor is never materialised)' % (reduction,))
+
+  def compute_per_list(self, labels, logits, weights, mask=None):
+    """losses_impl.py:886-915 (no temperature, as in the reference)."""
+    loss_sum, _, w_sum, _ = self._run(labels, logits, weights, mask, 1.0)
+    return _safe_div(loss_sum, w_sum), w_sum
+
+  def compute_row_sums(self, labels, logits, weights):
+    """sum_j loss_ij * W_ij per item: what keras/losses.py:324-335 reduces."""
+    return self._run(labels, logits, weights, None, self._temperature)[1]
+
+  def _normalize_weights_impl(self, labels, weights):
+    """losses_impl.py:917-930: [B, N, 1] row-item weights."""
+    w = 1. if weights is None else _as_f32(weights, labels.device, 'weights')
+    w = torch.where(labels >= 0, torch.ones_like(labels) * w,
+                    torch.zeros_like(labels))
+    return w.unsqueeze(2)
+
+
+class PairwiseLogisticLoss(_PairwiseLoss):
+  """losses_impl.py:933-940."""
+  _phi = _C.PHI_LOGISTIC
+
+
+class PairwiseHingeLoss(_PairwiseLoss):
+  """losses_impl.py:943-948."""
+  _phi = _C.PHI_HINGE
+
+
+class PairwiseSoftZeroOneLoss(_PairwiseLoss):
+  """losses_impl.py:951-958."""
+  _phi = _C.PHI_SOFT_ZERO_ONE
+
+
+class PairwiseMSELoss(_PairwiseLoss):
+  """losses_impl.py:961-998."""
+  _phi = _C.PHI_MSE
+
+
+class _ListwiseLoss(_RankingLoss):
+  """losses_impl.py:1001-1033."""
+  _kind = None
+
+  def _run(self, labels, logits, weights, mask, temperature):
+    labels, logits = _prep_2d(labels, logits)
+    w, wpi = _prep_weights(weights, logits)
+    m = _prep_mask(mask, logits)
+    return _ListwiseFn.apply(logits, labels, w, wpi, m, temperature, self._kind,
+                             self._lambda_weight)
+
+  def compute(self, labels, logits, weights, reduction, mask=None):
+    losses, w = self._run(labels, logits, weights, mask, self._temperature)
+    return _reduce_lists(losses, w, reduction)
+
+  def compute_per_list(self, labels, logits, weights, mask=None):
+    """losses_impl.py:1017-1033 (no temperature, as in the reference)."""
+    return self._run(labels, logits, weights, mask, 1.0)
+
+  def _normalize_weights_impl(self, labels, weights):
+    """losses_impl.py:1004-1015: sum(w * l) / sum(l) per list, [B, 1]."""
+    if weights is None:
+      return 1.0
+    w = _as_f32(weights, labels.device, 'weights')
+    lab = torch.where(labels >= 0, labels, torch.zeros_like(labels))
+    return _safe_div((w * lab).sum(1, keepdim=True), lab.sum(1, keepdim=True))
+
+
+def _reduce_lists(losses, weights, reduction):
+  total = (losses * weights).sum()
+  if reduction == Reduction.NONE:
+    return losses * weights
+  if reduction == Reduction.SUM:
+    return total
+  if reduction == Reduction.MEAN:
+    return _safe_div(total, weights.sum())
+  if reduction == Reduction.SUM_BY_NONZERO_WEIGHTS:
+    return _safe_div(total, (weights != 0).to(losses.dtype).sum())
+  if reduction == Reduction.SUM_OVER_BATCH_SIZE:
+    return total / float(losses.numel())
+  raise ValueError('bad reduction %r' % (reduction,))
+
+
+class SoftmaxLoss(_ListwiseLoss):
+  """losses_impl.py:1119-1197."""
+  _kind = 'softmax'
+
+  def compute_per_list(self, labels, logits, weights, mask=None):
+    """losses_impl.py:1179-1189 (this one does apply the temperature)."""
+    return self._run(labels, logits, weights, mask, self._temperature)
+
+
+class ApproxNDCGLoss(_ListwiseLoss):
+  """losses_impl.py:1579-1603."""
+  _kind = 'ndcg'
+
+  def __init__(self, name=None, lambda_weight=None, temperature=0.1,
+               ragged=False):
+    super().__init__(name, lambda_weight, temperature, ragged)
+
+
+class ApproxMRRLoss(_ListwiseLoss):
+  """losses_impl.py:1606-1632."""
+  _kind = 'mrr'
+
+  def __init__(self, name=None, lambda_weight=None, temperature=0.1,
+               ragged=False):
+    super().__init__(name, lambda_weight, temperature, ragged)

@@ -1,0 +1,127 @@
+"""Host-side mirror of tensorflow_ranking/python/metrics_impl.py (NDCG, MRR).
+
+`compute(labels, predictions, weights=None, mask=None)` returns
+`(per_list_metric [B, 1], per_list_weight [B, 1])` like the reference
+(metrics_impl.py:268-291); the sort, DCG, ideal DCG, MRR and the per-list weight
+rule all run in one CUDA launch (+ a one-block finalise), for any number of
+cut-offs at once (`compute_topns`).
+"""
+import ctypes
+
+import torch
+
+from ranking_b200 import _C
+from ranking_b200.keras import utils as keras_utils
+from ranking_b200.losses_impl import (_as_f32, _prep_2d, _prep_mask,
+                                      _prep_weights, _GAIN_ENUM, _DISC_ENUM)
+
+_DEFAULT_GAIN_FN = keras_utils.pow_minus_1            # metrics_impl.py:31
+_DEFAULT_RANK_DISCOUNT_FN = keras_utils.log2_inverse  # metrics_impl.py:33
+
+
+def rank_metrics(labels, predictions, weights=None, mask=None, topns=(None,),
+                 gain_fn=None, rank_discount_fn=None, want_ndcg=True,
+                 want_mrr=True):
+  """One launch of K4.  Returns dict(ndcg [B, T], ndcg_w [B], mrr [B, T],
+  mrr_w [B], raw [B, 5])."""
+  labels, predictions = _prep_2d(labels, predictions)
+  w, wpi = _prep_weights(weights, predictions)
+  m = _prep_mask(mask, predictions)
+  b, n = predictions.shape
+  dev = predictions.device
+  gain_fn = gain_fn or _DEFAULT_GAIN_FN
+  rank_discount_fn = rank_discount_fn or _DEFAULT_RANK_DISCOUNT_FN
+  keep = []
+  gain_enum, gain_table = _C.GAIN_TABLE, None
+  if gain_fn in _GAIN_ENUM:
+    gain_enum = _GAIN_ENUM[gain_fn]
+  else:
+    # gain of the cleaned labels (metrics_impl.py:256-262: labels := 0 where the
+    # item is masked out or has weight <= 0)
+    ok = (m != 0) if m is not None else (labels >= 0)
+    if w is not None:
+      ok = ok & ((w if wpi else w.reshape(-1, 1)) > 0)
+    cleaned = torch.where(ok, labels, torch.zeros_like(labels))
+    gain_table = torch.as_tensor(gain_fn(cleaned)).to(torch.float32).contiguous()
+    keep.append(gain_table)
+  disc_enum, disc_table = _C.DISC_TABLE, None
+  if rank_discount_fn in _DISC_ENUM:
+    disc_enum = _DISC_ENUM[rank_discount_fn]
+  else:
+    r = torch.arange(0, n + 2, dtype=torch.float32, device=dev)
+    r[0] = 1.0
+    disc_table = torch.as_tensor(rank_discount_fn(r)).to(
+        torch.float32).contiguous()
+    keep.append(disc_table)
+  t = len(topns)
+  topn_arr = (ctypes.c_int32 * t)(*[int(x) if x else 0 for x in topns])
+  out = {
+      'ndcg': torch.empty(b, t, dtype=torch.float32, device=dev)
+              if want_ndcg else None,
+      'mrr': torch.empty(b, t, dtype=torch.float32, device=dev)
+             if want_mrr else None,
+      'ndcg_w': torch.empty(b, dtype=torch.float32, device=dev)
+                if want_ndcg else None,
+      'mrr_w': torch.empty(b, dtype=torch.float32, device=dev)
+               if want_mrr else None,
+      'raw': torch.empty(b, 5, dtype=torch.float32, device=dev),
+  }
+  _C.check(_C.lib.tfr_rank_metrics(
+      _C.ptr(predictions), _C.ptr(labels), _C.ptr(w), wpi, _C.ptr(m), b, n,
+      topn_arr, t, gain_enum, disc_enum, _C.ptr(gain_table),
+      _C.ptr(disc_table), _C.ptr(out['ndcg']), _C.ptr(out['ndcg_w']),
+      _C.ptr(out['mrr']), _C.ptr(out['mrr_w']), _C.ptr(out['raw']),
+      _C.stream()))
+  del keep
+  return out
+
+
+class _RankingMetric(object):
+  """metrics_impl.py:199-291."""
+
+  def __init__(self, ragged=False):
+    if ragged:
+      raise NotImplementedError('ragged=True: pass dense padded tensors.')
+    self._ragged = ragged
+
+  def compute(self, labels, predictions, weights=None, mask=None):
+    raise NotImplementedError
+
+
+class MRRMetric(_RankingMetric):
+  """metrics_impl.py:429-459."""
+
+  def __init__(self, name=None, topn=None, ragged=False):
+    super().__init__(ragged)
+    self._name = name
+    self._topn = topn
+
+  @property
+  def name(self):
+    return self._name
+
+  def compute(self, labels, predictions, weights=None, mask=None):
+    o = rank_metrics(labels, predictions, weights, mask, (self._topn,),
+                     want_ndcg=False)
+    return o['mrr'], o['mrr_w'].unsqueeze(1)
+
+
+class NDCGMetric(_RankingMetric):
+  """metrics_impl.py:631-670."""
+
+  def __init__(self, name=None, topn=None, gain_fn=_DEFAULT_GAIN_FN,
+               rank_discount_fn=_DEFAULT_RANK_DISCOUNT_FN, ragged=False):
+    super().__init__(ragged)
+    self._name = name
+    self._topn = topn
+    self._gain_fn = gain_fn
+    self._rank_discount_fn = rank_discount_fn
+
+  @property
+  def name(self):
+    return self._name
+
+  def compute(self, labels, predictions, weights=None, mask=None):
+    o = rank_metrics(labels, predictions, weights, mask, (self._topn,),
+                     self._gain_fn, self._rank_discount_fn, want_mrr=False)
+    return o['ndcg'], o['ndcg_w'].unsqueeze(1)

@@ -1,0 +1,394 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on the same
+seeded inputs.  Tolerance for floating point: 1e-5 relative (the north_star
+bar) on losses and on gradients relative to the largest gradient entry of the
+batch; ranks and NDCG permutations must agree exactly on tie-free scores.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _batch(b, n, seed, pad=True, zero_rows=True):
+  g = torch.Generator().manual_seed(seed)
+  scores = torch.randn(b, n, generator=g) * 2.0
+  probs = torch.tensor([.55, .25, .12, .06, .02])
+  labels = torch.multinomial(probs, b * n, replacement=True,
+                             generator=g).reshape(b, n).float()
+  if pad:
+    lens = torch.randint((n + 1) // 2, n + 1, (b,), generator=g)
+    labels = torch.where(torch.arange(n).unsqueeze(0) < lens.unsqueeze(1),
+                         labels, torch.full_like(labels, -1.))
+  if zero_rows and b >= 4:
+    labels[1] = torch.where(labels[1] >= 0, torch.zeros_like(labels[1]),
+                            labels[1])       # a list without relevant items
+    labels[2] = -1.                          # a fully padded list
+  item_w = torch.rand(b, n, generator=g) + 0.5
+  list_w = torch.rand(b, 1, generator=g) + 0.5
+  return scores, labels, item_w, list_w
+
+
+def _rel_err(got, ref):
+  got = got.detach().double().cpu()
+  ref = ref.detach().double().cpu()
+  return float((got - ref).abs().max() / (ref.abs().max() + 1e-30))
+
+
+def _check_loss_and_grad(cuda_loss, oracle_loss, scores, labels, weights):
+  s_gpu = scores.cuda().requires_grad_()
+  w_gpu = None if weights is None else weights.cuda()
+  got = cuda_loss(labels.cuda(), s_gpu, w_gpu)
+  got.backward()
+  s_ref = scores.double().requires_grad_()
+  w_ref = None if weights is None else weights.double()
+  ref = oracle_loss(labels.double(), s_ref, w_ref)
+  ref.backward()
+  assert abs(float(got) - float(ref)) <= RTOL * max(1.0, abs(float(ref))), (
+      float(got), float(ref))
+  if float(s_ref.grad.abs().max()) > 0:
+    err = _rel_err(s_gpu.grad, s_ref.grad)
+    assert err <= RTOL, err
+  else:
+    assert float(s_gpu.grad.abs().max()) == 0.0
+
+
+LAMBDAS = {
+    'none': lambda K: None,
+    'label_diff': lambda K: K.LabelDiffLambdaWeight(),
+    'dcg': lambda K: K.DCGLambdaWeight(),
+    'ndcg': lambda K: K.NDCGLambdaWeight(),
+    'ndcg_smooth_top5': lambda K: K.NDCGLambdaWeight(topn=5, smooth_fraction=0.25),
+    'ndcg_v2_top5': lambda K: K.NDCGLambdaWeightV2(topn=5),
+    'yeti': lambda K: K.YetiDCGLambdaWeight(topn=4, normalized=True),
+    'precision_top3': lambda K: K.PrecisionLambdaWeight(topn=3),
+}
+
+
+@pytest.mark.parametrize('cls', ['PairwiseLogisticLoss', 'PairwiseHingeLoss',
+                                 'PairwiseSoftZeroOneLoss', 'PairwiseMSELoss'])
+@pytest.mark.parametrize('lam', sorted(LAMBDAS))
+@pytest.mark.parametrize('wkind', ['none', 'list', 'item'])
+def test_pairwise_loss_and_grad(cuda_api, oracle_api, cls, lam, wkind):
+  scores, labels, item_w, list_w = _batch(6, 37, seed=11)
+  weights = {'none': None, 'list': list_w, 'item': item_w}[wkind]
+  KC, KO = cuda_api.keras_losses, oracle_api.keras_losses
+  loss_c = getattr(KC, cls)(lambda_weight=LAMBDAS[lam](KC), temperature=0.7)
+  loss_o = getattr(KO, cls)(lambda_weight=LAMBDAS[lam](KO), temperature=0.7)
+  _check_loss_and_grad(loss_c, loss_o, scores, labels, weights)
+
+
+@pytest.mark.parametrize('cls', ['ApproxNDCGLoss', 'ApproxMRRLoss', 'SoftmaxLoss'])
+@pytest.mark.parametrize('wkind', ['none', 'list', 'item'])
+@pytest.mark.parametrize('n', [1, 5, 64, 200])
+def test_listwise_loss_and_grad(cuda_api, oracle_api, cls, wkind, n):
+  scores, labels, item_w, list_w = _batch(8, n, seed=5 + n)
+  weights = {'none': None, 'list': list_w, 'item': item_w}[wkind]
+  loss_c = getattr(cuda_api.keras_losses, cls)()
+  loss_o = getattr(oracle_api.keras_losses, cls)()
+  _check_loss_and_grad(loss_c, loss_o, scores, labels, weights)
+
+
+def test_softmax_with_dcg_lambda(cuda_api, oracle_api):
+  scores, labels, item_w, _ = _batch(8, 50, seed=3)
+  KC, KO = cuda_api.keras_losses, oracle_api.keras_losses
+  _check_loss_and_grad(KC.SoftmaxLoss(lambda_weight=KC.NDCGLambdaWeight(topn=10)),
+                       KO.SoftmaxLoss(lambda_weight=KO.NDCGLambdaWeight(topn=10)),
+                       scores, labels, item_w)
+
+
+def test_custom_gain_and_discount_tables(cuda_api, oracle_api):
+  """User callables travel as tables (SURVEY.md §7 hard parts)."""
+  scores, labels, _, _ = _batch(4, 21, seed=9)
+  gain = lambda l: l * l + 0.5 * l
+  disc = lambda r: 1. / (r + 3.)
+  KC, KO = cuda_api.keras_losses, oracle_api.keras_losses
+  _check_loss_and_grad(
+      KC.PairwiseLogisticLoss(lambda_weight=KC.DCGLambdaWeight(
+          gain_fn=gain, rank_discount_fn=disc, normalized=True,
+          smooth_fraction=0.5)),
+      KO.PairwiseLogisticLoss(lambda_weight=KO.DCGLambdaWeight(
+          gain_fn=gain, rank_discount_fn=disc, normalized=True,
+          smooth_fraction=0.5)), scores, labels, None)
+
+
+@pytest.mark.parametrize('n', [32, 256, 1024])
+def test_pairwise_logistic_list_size_sweep(cuda_api, oracle_api, n):
+  """BASELINE config 5 sizes, checked on a few lists (the oracle materialises
+  [B, N, N])."""
+  scores, labels, _, _ = _batch(4, n, seed=n, zero_rows=False)
+  _check_loss_and_grad(cuda_api.keras_losses.PairwiseLogisticLoss(),
+                       oracle_api.keras_losses.PairwiseLogisticLoss(), scores,
+                       labels, None)
+
+
+def test_lambda_loss_config3_shape(cuda_api, oracle_api):
+  """BASELINE config 3 list size (N=512) with NDCGLambdaWeight, few lists."""
+  scores, labels, _, _ = _batch(3, 512, seed=21, zero_rows=False)
+  KC, KO = cuda_api.keras_losses, oracle_api.keras_losses
+  _check_loss_and_grad(KC.PairwiseLogisticLoss(lambda_weight=KC.NDCGLambdaWeight()),
+                       KO.PairwiseLogisticLoss(lambda_weight=KO.NDCGLambdaWeight()),
+                       scores, labels, None)
+
+
+def test_reduction_none_and_row_gradients(cuda_api, oracle_api):
+  scores, labels, item_w, _ = _batch(5, 19, seed=2)
+  KC, KO = cuda_api.keras_losses, oracle_api.keras_losses
+  up = torch.rand(5, 19)
+  s_gpu = scores.cuda().requires_grad_()
+  out = KC.PairwiseLogisticLoss(reduction=KC.Reduction.NONE)(
+      labels.cuda(), s_gpu, item_w.cuda())
+  (out * up.cuda()).sum().backward()
+  s_ref = scores.double().requires_grad_()
+  ref = KO.PairwiseLogisticLoss(reduction=KO.Reduction.NONE)(
+      labels.double(), s_ref, item_w.double())
+  (ref * up.double()).sum().backward()
+  assert _rel_err(out, ref) <= RTOL
+  assert _rel_err(s_gpu.grad, s_ref.grad) <= RTOL
+
+
+def test_estimator_reductions(cuda_api, oracle_api):
+  scores, labels, item_w, _ = _batch(6, 23, seed=4)
+  LC, LO = cuda_api.losses_impl, oracle_api.losses_impl
+  for red in ['SUM', 'MEAN', 'SUM_BY_NONZERO_WEIGHTS', 'SUM_OVER_BATCH_SIZE']:
+    for cls in ['PairwiseLogisticLoss', 'ApproxNDCGLoss', 'SoftmaxLoss']:
+      got = getattr(LC, cls)(name=None).compute(
+          labels.cuda(), scores.cuda(), item_w.cuda(),
+          getattr(LC.Reduction, red))
+      ref = getattr(LO, cls)(name=None).compute(
+          labels.double(), scores.double(), item_w.double(),
+          getattr(LO.Reduction, red))
+      assert abs(float(got) - float(ref)) <= RTOL * max(1., abs(float(ref))), (
+          red, cls, float(got), float(ref))
+
+
+def test_sorted_ranks_exact(cuda_api, oracle_api):
+  scores, labels, _, _ = _batch(16, 100, seed=8)
+  ranks = cuda_api.utils.sorted_ranks(scores.cuda(), labels.cuda())
+  ref = oracle_api.losses_impl._compute_ranks(scores.double(), labels >= 0)
+  assert torch.equal(ranks.cpu().long(), ref)
+  # ties are broken by index
+  tie = torch.tensor([[1., 2., 1., 2., 0.]])
+  assert cuda_api.utils.sorted_ranks(tie.cuda()).tolist() == [[3, 1, 4, 2, 5]]
+
+
+@pytest.mark.parametrize('n', [1, 7, 200, 777])
+def test_rank_metrics(cuda_api, oracle_api, n):
+  scores, labels, item_w, _ = _batch(16, n, seed=n)
+  topns = (1, 3, 5, 10, None)
+  for weights in (None, item_w):
+    out = cuda_api.metrics_impl.rank_metrics(
+        labels.cuda(), scores.cuda(), None if weights is None else weights.cuda(),
+        None, topns)
+    for t, topn in enumerate(topns):
+      w64 = None if weights is None else weights.double()
+      nd, ndw = oracle_api.metrics_impl.NDCGMetric(topn=topn).compute(
+          labels.double(), scores.double(), w64)
+      mr, mrw = oracle_api.metrics_impl.MRRMetric(topn=topn).compute(
+          labels.double(), scores.double(), w64)
+      torch.testing.assert_close(out['ndcg'][:, t].cpu().double(), nd[:, 0],
+                                 rtol=1e-5, atol=1e-6)
+      torch.testing.assert_close(out['mrr'][:, t].cpu().double(), mr[:, 0],
+                                 rtol=0, atol=0)   # 1/rank of an exact position
+      torch.testing.assert_close(out['ndcg_w'].cpu().double(), ndw[:, 0],
+                                 rtol=1e-5, atol=1e-6)
+      torch.testing.assert_close(out['mrr_w'].cpu().double(), mrw[:, 0],
+                                 rtol=1e-5, atol=1e-6)
+
+
+def test_keras_metric_objects(cuda_api, oracle_api):
+  scores, labels, _, _ = _batch(32, 40, seed=77)
+  MC = __import__('ranking_b200').keras.metrics
+  m = MC.NDCGMetric(topn=10)
+  m.update_state(labels[:16].cuda(), scores[:16].cuda())
+  m.update_state(labels[16:].cuda(), scores[16:].cuda())
+  ref = oracle_api.metrics_impl.KerasMean(
+      oracle_api.metrics_impl.NDCGMetric(topn=10))
+  ref.update_state(labels[:16].double(), scores[:16].double())
+  ref.update_state(labels[16:].double(), scores[16:].double())
+  assert abs(float(m.result()) - ref.result()) <= 1e-6
+  # docstring example keras/metrics.py:729-733
+  got = MC.NDCGMetric()(torch.tensor([[0., 1., 1.]]).cuda(),
+                        torch.tensor([[3., 1., 2.]]).cuda())
+  assert abs(float(got) - 0.6934264) < 1e-6
+  grp = MC.MetricGroup()
+  grp.update_state(labels.cuda(), scores.cuda())
+  res = grp.result()
+  m10 = MC.NDCGMetric(topn=10)
+  m10.update_state(labels.cuda(), scores.cuda())
+  assert abs(res['metric/ndcg_10'] - float(m10.result())) < 1e-6
+
+
+# ------------------------------ scorer tower --------------------------------
+def _tower_and_params(tfr, d, hidden, out, seed, activation='relu',
+                      precision='fp32'):
+  tower = tfr.keras.layers.create_tower(hidden, out, activation=activation,
+                                        use_batch_norm=False, dropout=0,
+                                        input_dim=d, seed=seed,
+                                        precision=precision)
+  with torch.no_grad():
+    for i in range(len(tower.dims) - 1):
+      tower.bias(i).uniform_(-0.2, 0.2)
+  nl = len(tower.dims) - 1
+  params = {
+      'dense_w': [tower.kernel(i).detach().cpu().double().clone().requires_grad_()
+                  for i in range(nl)],
+      'dense_b': [tower.bias(i).detach().cpu().double().clone().requires_grad_()
+                  for i in range(nl)]}
+  return tower, params
+
+
+def _flat_grad(params):
+  return torch.cat([torch.cat([w.grad.reshape(-1), b.grad.reshape(-1)])
+                    for w, b in zip(params['dense_w'], params['dense_b'])])
+
+
+@pytest.mark.parametrize('shape', [
+    (300, 136, [256, 128, 64], 1, 'relu'),
+    (1000, 17, [33, 9], 1, 'relu'),
+    (257, 40, [], 1, None),          # linear scorer, no hidden layer
+    (513, 24, [48], 2, None),        # two outputs (groupwise scoring), identity act
+    (4100, 136, [256, 128, 64], 1, 'relu'),   # crosses the row-split boundary
+])
+def test_tower_forward_backward(oracle_api, shape):
+  import ranking_b200 as tfr
+  m, d, hidden, out, act = shape
+  tower, params = _tower_and_params(tfr, d, hidden, out, seed=m, activation=act)
+  g = torch.Generator().manual_seed(m)
+  x = torch.randn(m, d, generator=g)
+  up = torch.randn(m, out, generator=g)
+  y = tower(x.cuda())
+  (y * up.cuda()).sum().backward()
+  ref = oracle_api.scorer.tower_forward(x.double(), params, activation=act)
+  (ref * up.double()).sum().backward()
+  assert _rel_err(y, ref) <= RTOL
+  assert _rel_err(tower.flat.grad, _flat_grad(params)) <= 5e-5
+
+
+def test_tower_restore_list_mask(oracle_api):
+  import ranking_b200 as tfr
+  tower, params = _tower_and_params(tfr, 8, [16], 1, seed=1)
+  x = torch.randn(6, 5, 8)
+  mask = torch.rand(6, 5) > 0.3
+  y = tower(x.cuda(), mask=mask.cuda()).reshape(6, 5)
+  ref = oracle_api.scorer.restore_list(
+      oracle_api.scorer.tower_forward(x.double().reshape(30, 8), params,
+                                      activation='relu'), mask)
+  assert _rel_err(y, ref) <= RTOL
+  assert float(y[~mask.cuda()].max()) == pytest.approx(math.log(1e-10), rel=1e-6)
+
+
+def test_dnn_scorer_contract(oracle_api):
+  """keras/model.py:755-817: context first, sorted keys, circular padding,
+  RestoreList fill."""
+  import ranking_b200 as tfr
+  b, n = 4, 6
+  g = torch.Generator().manual_seed(0)
+  ctx = {'c2': torch.randn(b, 2, generator=g), 'c1': torch.randn(b, 1, generator=g)}
+  ex = {'zf': torch.randn(b, n, 3, generator=g), 'af': torch.randn(b, n, 2, generator=g)}
+  mask = torch.tensor([[1, 1, 1, 1, 1, 1], [1, 1, 1, 0, 0, 0],
+                       [1, 0, 0, 0, 0, 0], [1, 1, 1, 1, 1, 0]]).bool()
+  scorer = tfr.keras.model.DNNScorer(hidden_layer_dims=[16, 8], output_units=1,
+                                     activation='relu', use_batch_norm=False,
+                                     dropout=0, seed=5)
+  got = scorer({k: v.cuda() for k, v in ctx.items()},
+               {k: v.cuda() for k, v in ex.items()}, mask.cuda())
+  tower = scorer.tower
+  nl = len(tower.dims) - 1
+  params = {'dense_w': [tower.kernel(i).detach().cpu().double() for i in range(nl)],
+            'dense_b': [tower.bias(i).detach().cpu().double() for i in range(nl)]}
+  ref = oracle_api.scorer.dnn_scorer(
+      {k: v.double() for k, v in ctx.items()},
+      {k: v.double() for k, v in ex.items()}, mask, params, activation='relu')
+  assert tuple(got.shape) == (b, n)
+  assert _rel_err(got, ref) <= RTOL
+
+
+@pytest.mark.parametrize('loss_key,kw', [
+    ('approx_ndcg_loss', {}),
+    ('pairwise_logistic_loss', {}),
+    ('softmax_loss', {}),
+])
+def test_fused_train_step_matches_oracle(oracle_api, loss_key, kw):
+  """One full step: scorer fwd -> loss -> scorer bwd -> Adagrad; loss, flat
+  gradient and updated parameters vs the oracle (autograd + Keras Adagrad)."""
+  import ranking_b200 as tfr
+  b, n, d = 16, 30, 20
+  scores_unused, labels, _, _ = _batch(b, n, seed=13)
+  x = torch.randn(b, n, d, generator=torch.Generator().manual_seed(1))
+  mask = labels >= 0
+  tower, params = _tower_and_params(tfr, d, [32, 16], 1, seed=7)
+  p0 = tower.flat.detach().clone()
+  loss_obj = tfr.keras.losses.get(loss_key, **kw)
+  tr = tfr.train.RankingTrainer(tower, loss_obj, optimizer='adagrad',
+                                learning_rate=0.05)
+  got = tr.train_step(x.cuda(), labels.cuda(), mask=mask.cuda())
+  logits = oracle_api.scorer.restore_list(
+      oracle_api.scorer.tower_forward(x.double().reshape(b * n, d), params,
+                                      activation='relu'), mask)
+  ref = oracle_api.keras_losses.get(loss_key, **kw)(labels.double(), logits)
+  ref.backward()
+  g = _flat_grad(params)
+  assert abs(float(got) - float(ref)) <= RTOL * max(1., abs(float(ref)))
+  assert _rel_err(tr.grads, g) <= 5e-5
+  accum = 0.1 + g * g
+  p_ref = p0.cpu().double() - 0.05 * g / (accum.sqrt() + 1e-7)
+  assert _rel_err(tower.flat, p_ref) <= 1e-5
+
+
+# --------------------- size-independent properties at full size --------------
+def test_full_size_properties_config2():
+  """BASELINE config 2 (B=1024, N=200): properties that need no oracle."""
+  import ranking_b200 as tfr
+  b, n = 1024, 200
+  scores, labels, _, _ = _batch(b, n, seed=1234, zero_rows=False)
+  s = scores.cuda().requires_grad_()
+  y = labels.cuda()
+  loss = tfr.keras.losses.ApproxNDCGLoss(reduction='sum')(y, s)
+  loss.backward()
+  # ApproxNDCG in [-1, 0] per list; loss depends on score differences only.
+  assert -b <= float(loss) <= 0.0
+  assert float(s.grad.sum(1).abs().max()) <= 1e-4 * float(s.grad.abs().max())
+  assert float(s.grad[y < 0].abs().max()) == 0.0
+  # permutation equivariance on a list
+  perm = torch.randperm(n, generator=torch.Generator().manual_seed(1)).cuda()
+  s2 = s.detach()[:, perm].clone().requires_grad_()
+  loss2 = tfr.keras.losses.ApproxNDCGLoss(reduction='sum')(y[:, perm], s2)
+  loss2.backward()
+  assert abs(float(loss2) - float(loss)) <= 1e-4 * abs(float(loss))
+  assert _rel_err(s2.grad, s.grad[:, perm]) <= 1e-4
+  # NDCG metric: 1.0 when scores order the labels, within [0, 1] otherwise
+  m = tfr.metrics_impl.rank_metrics(y, y.clone() + 0.0, None, None, (10, None))
+  has_rel = (labels > 0).any(1)
+  assert torch.allclose(m['ndcg'][has_rel.cuda()], torch.ones(1).cuda())
+  m = tfr.metrics_impl.rank_metrics(y, s.detach(), None, None, (10, None))
+  assert float(m['ndcg'].min()) >= 0.0 and float(m['ndcg'].max()) <= 1.0 + 1e-6
+
+
+def test_full_size_pairwise_n1024_gradient_sums():
+  import ranking_b200 as tfr
+  scores, labels, _, _ = _batch(64, 1024, seed=99, zero_rows=False)
+  s = scores.cuda().requires_grad_()
+  loss = tfr.keras.losses.PairwiseLogisticLoss(
+      lambda_weight=tfr.keras.losses.NDCGLambdaWeight())(labels.cuda(), s)
+  loss.backward()
+  assert float(loss) > 0
+  assert float(s.grad.sum(1).abs().max()) <= 1e-4 * float(s.grad.abs().max())
+
+
+def test_error_behaviour():
+  import ranking_b200 as tfr
+  with pytest.raises(ValueError):
+    tfr.keras.losses.get('no_such_loss')
+  with pytest.raises(ValueError):
+    tfr.keras.metrics.get('no_such_metric')
+  with pytest.raises(ValueError):
+    tfr.keras.losses.DCGLambdaWeight(smooth_fraction=2.0)
+  with pytest.raises(ValueError):   # rank != 2 (losses_impl.py:52-58)
+    tfr.keras.losses.PairwiseLogisticLoss()(torch.zeros(3).cuda(),
+                                            torch.zeros(3).cuda())
+  with pytest.raises(RuntimeError):  # no CPU fallback
+    tfr.keras.losses.PairwiseLogisticLoss()(torch.zeros(1, 3), torch.zeros(1, 3))
