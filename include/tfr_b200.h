@@ -218,6 +218,17 @@ int tfr_mlp_bwd(const float* X, int M, const tfr_mlp_cfg* cfg,
                 const float* params, const float* dscores, const uint8_t* mask,
                 void* workspace, float* grads, int precision, void* stream);
 
+/* Parity helper: one GEMM through the tcgen05 TF32 engine that the scorer tower
+ * uses (D[GM,GN] = A[GM,GK] * B[GK,GN]).  a_mn/b_mn select the operand storage
+ * (0: K contiguous, i.e. A stored [GM,GK], B stored [GN,GK]; 1: M/N contiguous,
+ * i.e. A stored [GK,GM], B stored [GK,GN]); passes 1 = TF32, 3 = 3xTF32 (fp32-
+ * faithful); epi 0 store, 1 bias+act, 2 relu-mask by aux.  See csrc/tc_gemm.cuh. */
+int tfr_tc_gemm(const float* A, int lda, const float* B, int ldb, const float* B_lo,
+                float* C, int ldc, int GM, int GN, int GK, int a_mn, int b_mn,
+                int passes, int split_b, int epi, const float* bias,
+                const float* aux, int act, int store_transposed, int splits,
+                size_t split_stride, void* stream);
+
 /* ---------------------------------------------------------------------------
  * Fused optimizer over the flat parameter buffer (the reference delegates to
  * tf.keras.optimizers; Adagrad is what its examples use:

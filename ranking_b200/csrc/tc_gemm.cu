@@ -1,0 +1,514 @@
+// tcgen05 (UMMA) TF32 GEMM engine for the scorer tower (sm_100a).
+//
+//   * operands are staged global -> shared by TMA (cp.async.bulk.tensor, 128-byte
+//     swizzle) into a ring of stages guarded by mbarriers;
+//   * one elected thread issues tcgen05.mma.kind::tf32 with the fp32 accumulator
+//     tile [128 x N] living in TMEM;
+//   * for the fp32-faithful mode (3xTF32) four "splitter" warps turn each landed
+//     fp32 tile into an exact TF32 hi part (in place) and an fp32 lo residual, so
+//     that D = Ahi*Bhi + Alo*Bhi + Ahi*Blo carries ~22 mantissa bits;
+//   * the same four warps drain TMEM with tcgen05.ld in the epilogue (bias/ReLU,
+//     ReLU-mask, plain or transposed store).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer, warps 2..5 = splitters during the main loop, epilogue afterwards.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace tfr {
+namespace tc {
+
+constexpr int kThreads = 192;
+constexpr int BM = 128;       // UMMA M (cta_group::1)
+constexpr int BK = 32;        // fp32 elements per 128-byte swizzle span
+constexpr int kATileBytes = BM * BK * 4;   // 16 KB
+constexpr int kMaxStages = 4;
+constexpr unsigned kSmemBudget = 227 * 1024 - 2048;
+
+// ------------------------------------------------------------------ PTX -------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("tc_gemm: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor (Blackwell version field set).
+//   K-major : SWIZZLE_128B (layout type 2): rows of 128 B (32 fp32 of K), 16-byte
+//             chunks XOR-ed with (row % 8); 8-row atoms every SBO = 1024 B.
+//   MN-major: for 32-bit operands the only legal layout is SWIZZLE_128B_BASE32B
+//             (layout type 1): rows (= k) of 128 B holding 32 fp32 of M/N, 32-byte
+//             chunks XOR-ed with (k % 4); 4-row atoms every SBO = 512 B, atoms
+//             along M/N every LBO bytes.  TMA writes exactly this image with
+//             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;   // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(layout_type) << 61;
+  return d;
+}
+
+struct KernelArgs {
+  float* C;
+  int ldc;
+  int GM, GN, GK;
+  int n_umma;          // UMMA N of one tile (multiple of 16, <= 256)
+  int b_tile_bytes;    // bytes of one B stage tile (hi part)
+  int stages;
+  int epi, act, store_transposed;
+  const float* bias;
+  const float* aux;
+  int kb_per_split;    // k-blocks (of 32) handled by one blockIdx.z
+  size_t split_stride;
+  uint32_t tmem_cols;
+};
+
+template <bool A_MN, bool B_MN, int PASSES, bool SPLIT_B>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmBlo, const KernelArgs args) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms.
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  constexpr int kACopies = PASSES == 3 ? 2 : 1;
+  constexpr int kBCopies = PASSES == 3 ? 2 : 1;
+  const int a_bytes = kATileBytes * kACopies;
+  const int stage_bytes = a_bytes + args.b_tile_bytes * kBCopies;
+  const int S = args.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S) * stage_bytes);
+  uint64_t* full = bars;               // TMA landed
+  uint64_t* split = bars + kMaxStages;  // hi/lo split done
+  uint64_t* empty = bars + 2 * kMaxStages;  // MMAs that read the stage retired
+  uint64_t* accum = bars + 3 * kMaxStages;  // accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * args.n_umma;
+  const int nkb_total = (args.GK + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * args.kb_per_split;
+  const int kb_end = min(nkb_total, kb_begin + args.kb_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    if (PASSES == 3 && !SPLIT_B) prefetch_tmap(&tmBlo);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&split[s], 128);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, args.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto sA_hi = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };
+  auto sA_lo = [&](int s) { return sA_hi(s) + kATileBytes; };
+  auto sB_hi = [&](int s) { return sA_hi(s) + a_bytes; };
+  auto sB_lo = [&](int s) { return sB_hi(s) + args.b_tile_bytes; };
+
+  if (warp == 0) {
+    // ------------------------------------------------------- TMA producer ----
+    if (lane == 0) {
+      const uint32_t tx_bytes =
+          kATileBytes + args.b_tile_bytes * ((PASSES == 3 && !SPLIT_B) ? 2 : 1);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], tx_bytes);
+        const int k0 = (kb_begin + kb) * BK;
+        if (!A_MN) {
+          tma_load_2d(sA_hi(s), &tmA, &full[s], k0, m0);          // box [128 rows][32 k]
+        } else {
+          for (int i = 0; i < BM / 32; ++i)                        // boxes [32 k][32 m]
+            tma_load_2d(sA_hi(s) + i * 4096, &tmA, &full[s], m0 + 32 * i, k0);
+        }
+        if (!B_MN) {
+          tma_load_2d(sB_hi(s), &tmB, &full[s], k0, n0);           // box [n rows][32 k]
+          if (PASSES == 3 && !SPLIT_B) tma_load_2d(sB_lo(s), &tmBlo, &full[s], k0, n0);
+        } else {
+          const int nbox = args.b_tile_bytes / 4096;
+          for (int j = 0; j < nbox; ++j) {
+            tma_load_2d(sB_hi(s) + j * 4096, &tmB, &full[s], n0 + 32 * j, k0);
+            if (PASSES == 3 && !SPLIT_B)
+              tma_load_2d(sB_lo(s) + j * 4096, &tmBlo, &full[s], n0 + 32 * j, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // --------------------------------------------------------- MMA issuer ----
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) |
+                             (static_cast<uint32_t>(A_MN) << 15) |
+                             (static_cast<uint32_t>(B_MN) << 16) |
+                             (static_cast<uint32_t>(args.n_umma >> 3) << 17) |
+                             (static_cast<uint32_t>(BM >> 4) << 24);
+      const uint32_t a_step = A_MN ? 1024u : 32u;   // bytes per UMMA K step (8 fp32)
+      const uint32_t b_step = B_MN ? 1024u : 32u;
+      const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
+      const uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
+      const uint32_t a_lt = A_MN ? 1u : 2u, b_lt = B_MN ? 1u : 2u;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(PASSES == 3 ? &split[s] : &full[s], ph);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(sA_hi(s)), a_lo = smem_u32(sA_lo(s));
+        const uint32_t b_hi = smem_u32(sB_hi(s)), b_lo = smem_u32(sB_lo(s));
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          const uint64_t da_hi = make_smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
+          const uint64_t db_hi = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
+          umma_tf32(tmem_base, da_hi, db_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+          if (PASSES == 3) {
+            const uint64_t da_lo = make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
+            const uint64_t db_lo = make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
+            umma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
+            umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
+          }
+        }
+        umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
+      }
+      umma_commit(accum);
+    }
+  } else {
+    // ------------------------------------- splitters, then epilogue (warps 2..5)
+    const int t = threadIdx.x - 64;   // 0 .. 127
+    if (PASSES == 3) {
+      const int b_chunks = SPLIT_B ? args.b_tile_bytes / 16 : 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(&full[s], ph);
+        float4* hi = reinterpret_cast<float4*>(sA_hi(s));
+        float4* lo = reinterpret_cast<float4*>(sA_lo(s));
+        for (int pass = 0; pass < (SPLIT_B ? 2 : 1); ++pass) {
+          const int chunks = pass == 0 ? kATileBytes / 16 : b_chunks;
+          if (pass == 1) {
+            hi = reinterpret_cast<float4*>(sB_hi(s));
+            lo = reinterpret_cast<float4*>(sB_lo(s));
+          }
+          for (int c = t; c < chunks; c += 128) {
+            const float4 v = hi[c];
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            l.x = v.x - h.x;
+            l.y = v.y - h.y;
+            l.z = v.z - h.z;
+            l.w = v.w - h.w;
+            hi[c] = h;
+            lo[c] = l;
+          }
+        }
+        fence_proxy_async();       // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(&split[s]);
+      }
+    }
+    // epilogue: TMEM lane quarter is fixed by warp id % 4
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    float* C = args.C + static_cast<size_t>(blockIdx.z) * args.split_stride;
+    for (int c0 = 0; c0 < args.n_umma; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = n0 + c0 + j;
+        if (c0 + j >= args.n_umma || col >= args.GN || row >= args.GM) continue;
+        float x = __uint_as_float(v[j]);
+        if (args.epi == EPI_BIAS_ACT) {
+          x += __ldg(args.bias + col);
+          if (args.act == TFR_ACT_RELU) x = fmaxf(x, 0.f);
+        } else if (args.epi == EPI_MASK_POS) {
+          if (args.act == TFR_ACT_RELU &&
+              !(__ldg(args.aux + static_cast<size_t>(row) * args.ldc + col) > 0.f))
+            x = 0.f;
+        }
+        if (args.store_transposed) C[static_cast<size_t>(col) * args.ldc + row] = x;
+        else C[static_cast<size_t>(row) * args.ldc + col] = x;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, args.tmem_cols);
+}
+
+// ------------------------------------------------------------------ host -------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                             const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeFn>(p);
+  return fn;
+}
+
+// 2D fp32 tensor [outer rows][inner cols], box [box_outer][32 cols], 128B swizzle.
+static int encode_2d(CUtensorMap* tm, const float* ptr, uint64_t inner, uint64_t outer,
+                     uint64_t ld_floats, uint32_t box_outer, bool mn_major) {
+  EncodeFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return TFR_CUDA_ERROR;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_floats * sizeof(float)};
+  cuuint32_t box[2] = {BK, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr %p inner %llu outer %llu ld %llu "
+              "box_outer %u)", (int)r, (const void*)ptr, (unsigned long long)inner,
+              (unsigned long long)outer, (unsigned long long)ld_floats, box_outer);
+    return TFR_CUDA_ERROR;
+  }
+  return TFR_OK;
+}
+
+bool shape_supported(int lda, int ldb) { return lda % 4 == 0 && ldb % 4 == 0; }
+
+template <bool A_MN, bool B_MN, int PASSES, bool SPLIT_B>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo,
+                  const KernelArgs& ka, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kern = tc_gemm_kernel<A_MN, B_MN, PASSES, SPLIT_B>;
+  TFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kThreads, smem, st>>>(tmA, tmB, tmBlo, ka);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+int gemm(const GemmDesc& g, cudaStream_t st) {
+  TFR_REQUIRE(g.A && g.B && g.C, "tc gemm: NULL operand");
+  TFR_REQUIRE(g.GM >= 1 && g.GN >= 1 && g.GK >= 1, "tc gemm: empty problem");
+  TFR_REQUIRE(g.passes == 1 || g.passes == 3, "tc gemm: passes must be 1 or 3");
+  TFR_REQUIRE(g.lda % 4 == 0 && g.ldb % 4 == 0, "tc gemm: leading dimensions must be multiples of 4");
+  TFR_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.B) & 15) == 0,
+              "tc gemm: operands must be 16-byte aligned");
+  const bool pre_split_b = g.passes == 3 && !g.split_b;
+  TFR_REQUIRE(!pre_split_b || g.B_lo != nullptr, "tc gemm: B_lo required for pre-split B");
+  TFR_REQUIRE(!pre_split_b || (reinterpret_cast<uintptr_t>(g.B_lo) & 15) == 0, "tc gemm: B_lo alignment");
+
+  // N tiling: one tile if it fits a single UMMA (N <= 256), else tiles of 256.
+  const int n_umma = g.GN <= 256 ? ((g.GN + 15) / 16) * 16 : 256;
+  const int n_tiles = (g.GN + n_umma - 1) / n_umma;
+  const int b_rows = g.b_mn ? ((n_umma + 31) / 32) * 32 : n_umma;   // rows of 128 B in a B tile
+  const int b_tile_bytes = b_rows * 128;
+  const int copies = g.passes == 3 ? 2 : 1;
+  const int stage_bytes = (kATileBytes + b_tile_bytes) * copies;
+  int stages = (int)(kSmemBudget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  TFR_REQUIRE(stages >= 1, "tc gemm: tile does not fit shared memory");
+  const int nkb_total = (g.GK + BK - 1) / BK;
+  int splits = g.splits < 1 ? 1 : g.splits;
+  int kb_per_split = (nkb_total + splits - 1) / splits;
+  splits = (nkb_total + kb_per_split - 1) / kb_per_split;
+  TFR_REQUIRE(splits == (g.splits < 1 ? 1 : g.splits),
+              "tc gemm: splits %d leave empty k ranges (GK %d)", g.splits, g.GK);
+
+  CUtensorMap tmA, tmB, tmBlo;
+  int rc;
+  if (!g.a_mn) rc = encode_2d(&tmA, g.A, (uint64_t)g.GK, (uint64_t)g.GM, (uint64_t)g.lda, BM, false);
+  else rc = encode_2d(&tmA, g.A, (uint64_t)g.GM, (uint64_t)g.GK, (uint64_t)g.lda, 32, true);
+  if (rc) return rc;
+  if (!g.b_mn) rc = encode_2d(&tmB, g.B, (uint64_t)g.GK, (uint64_t)g.GN, (uint64_t)g.ldb, (uint32_t)n_umma, false);
+  else rc = encode_2d(&tmB, g.B, (uint64_t)g.GN, (uint64_t)g.GK, (uint64_t)g.ldb, 32, true);
+  if (rc) return rc;
+  tmBlo = tmB;
+  if (pre_split_b) {
+    if (!g.b_mn) rc = encode_2d(&tmBlo, g.B_lo, (uint64_t)g.GK, (uint64_t)g.GN, (uint64_t)g.ldb, (uint32_t)n_umma, false);
+    else rc = encode_2d(&tmBlo, g.B_lo, (uint64_t)g.GN, (uint64_t)g.GK, (uint64_t)g.ldb, 32, true);
+    if (rc) return rc;
+  }
+
+  KernelArgs ka;
+  ka.C = g.C; ka.ldc = g.ldc;
+  ka.GM = g.GM; ka.GN = g.GN; ka.GK = g.GK;
+  ka.n_umma = n_umma;
+  ka.b_tile_bytes = b_tile_bytes;
+  ka.stages = stages;
+  ka.epi = g.epi; ka.act = g.act; ka.store_transposed = g.store_transposed;
+  ka.bias = g.bias; ka.aux = g.aux;
+  ka.kb_per_split = kb_per_split;
+  ka.split_stride = g.split_stride;
+  uint32_t cols = 32;
+  while ((int)cols < n_umma) cols <<= 1;
+  ka.tmem_cols = cols;
+  TFR_REQUIRE(g.epi != EPI_BIAS_ACT || g.bias, "tc gemm: bias required");
+  TFR_REQUIRE(g.epi != EPI_MASK_POS || g.aux, "tc gemm: aux required");
+
+  dim3 grid(n_tiles, (g.GM + BM - 1) / BM, splits);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+
+#define TFR_TC_LAUNCH(AMN, BMN, P, SB) \
+  return launch<AMN, BMN, P, SB>(tmA, tmB, tmBlo, ka, grid, smem, st)
+  const int key = (g.a_mn ? 8 : 0) | (g.b_mn ? 4 : 0) | (g.passes == 3 ? 2 : 0) |
+                  ((g.passes == 3 && g.split_b) ? 1 : 0);
+  switch (key) {
+    case 0: TFR_TC_LAUNCH(false, false, 1, false);
+    case 2: TFR_TC_LAUNCH(false, false, 3, false);
+    case 3: TFR_TC_LAUNCH(false, false, 3, true);
+    case 4: TFR_TC_LAUNCH(false, true, 1, false);
+    case 6: TFR_TC_LAUNCH(false, true, 3, false);
+    case 7: TFR_TC_LAUNCH(false, true, 3, true);
+    case 8: TFR_TC_LAUNCH(true, false, 1, false);
+    case 10: TFR_TC_LAUNCH(true, false, 3, false);
+    case 11: TFR_TC_LAUNCH(true, false, 3, true);
+    case 12: TFR_TC_LAUNCH(true, true, 1, false);
+    case 14: TFR_TC_LAUNCH(true, true, 3, false);
+    case 15: TFR_TC_LAUNCH(true, true, 3, true);
+  }
+#undef TFR_TC_LAUNCH
+  set_error("tc gemm: unsupported variant %d", key);
+  return TFR_UNSUPPORTED;
+}
+
+}  // namespace tc
+}  // namespace tfr
+
+// Test / parity entry: raw GEMM through the tensor-core engine.
+extern "C" int tfr_tc_gemm(const float* A, int lda, const float* B, int ldb, const float* B_lo,
+                           float* C, int ldc, int GM, int GN, int GK, int a_mn, int b_mn,
+                           int passes, int split_b, int epi, const float* bias, const float* aux,
+                           int act, int store_transposed, int splits, size_t split_stride,
+                           void* stream) {
+  tfr::tc::GemmDesc g;
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.B_lo = B_lo; g.C = C; g.ldc = ldc;
+  g.GM = GM; g.GN = GN; g.GK = GK; g.a_mn = a_mn; g.b_mn = b_mn; g.passes = passes;
+  g.split_b = split_b; g.epi = epi; g.bias = bias; g.aux = aux; g.act = act;
+  g.store_transposed = store_transposed; g.splits = splits; g.split_stride = split_stride;
+  return tfr::tc::gemm(g, (cudaStream_t)stream);
+}
