@@ -63,6 +63,19 @@ int make_mlp_plan(const tfr_mlp_cfg* cfg, int M, MlpPlan* p) {
   p->partial_stride = align_up(max_wb, 64);
   p->partial_off = w;
   w += (size_t)p->splits * p->partial_stride;
+  p->whi_off = w;
+  w += align_up(p->n_params, 64);
+  p->wlo_off = w;
+  w += align_up(p->n_params, 64);
+  p->tile_slots = 4 * ((M + 127) / 128);
+  p->tile_stride = align_up((size_t)max_hidden, 64);
+  p->tile_off = w;
+  w += (size_t)p->tile_slots * p->tile_stride;
+  p->out_rows = 256;
+  p->out_slots = (M + p->out_rows - 1) / p->out_rows;
+  p->oslot_stride = align_up((size_t)p->dims[L] * (p->dims[L + 1] + 1) + p->dims[L + 1], 64);
+  p->oslot_off = w;
+  w += (size_t)p->out_slots * p->oslot_stride;
   p->ws_floats = w;
   return TFR_OK;
 }
@@ -124,6 +137,10 @@ extern "C" int tfr_mlp_fwd(const float* X, int M, const tfr_mlp_cfg* cfg,
     case TFR_PREC_FP32:
       return mlp_simt_fwd(X, M, p, params, mask, ws_base(workspace), scores_out,
                           (cudaStream_t)stream);
+    case TFR_PREC_TF32X3:
+    case TFR_PREC_TF32:
+      return mlp_tc_fwd(X, M, p, params, mask, ws_base(workspace), scores_out,
+                        precision == TFR_PREC_TF32X3 ? 3 : 1, (cudaStream_t)stream);
     default:
       set_error("precision %d is not available in this build", precision);
       return TFR_UNSUPPORTED;
@@ -142,6 +159,10 @@ extern "C" int tfr_mlp_bwd(const float* X, int M, const tfr_mlp_cfg* cfg,
     case TFR_PREC_FP32:
       return mlp_simt_bwd(X, M, p, params, dscores, mask, ws_base(workspace), grads,
                           (cudaStream_t)stream);
+    case TFR_PREC_TF32X3:
+    case TFR_PREC_TF32:
+      return mlp_tc_bwd(X, M, p, params, dscores, mask, ws_base(workspace), grads,
+                        precision == TFR_PREC_TF32X3 ? 3 : 1, (cudaStream_t)stream);
     default:
       set_error("precision %d is not available in this build", precision);
       return TFR_UNSUPPORTED;

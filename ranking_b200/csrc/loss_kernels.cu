@@ -372,7 +372,12 @@ sorted_ranks_kernel(const float* __restrict__ scores, const float* __restrict__ 
 // ---------------------------------------------------------------------------
 // K2  ApproxNDCG / ApproxMRR
 // ---------------------------------------------------------------------------
-template <int MODE>
+// Each unordered pair {a < b} is evaluated ONCE (sigmoid is antisymmetric about 1/2,
+// sigmoid' is even): the warp that owns row a adds the (a, b) term to its row
+// accumulator and the mirrored term to a per-lane register accumulator of column b
+// (lane l always sees the columns l + 32 t).  T = ceil(N / 32) column registers;
+// T == 0 selects the generic both-ends loop for N > 1024.
+template <int MODE, int T>
 __global__ void __launch_bounds__(kLossThreads)
 approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
                    const float* __restrict__ item_w, int w_per_item,
@@ -417,16 +422,56 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
   __syncthreads();
 
   // pass 1: approx ranks r_i = 0.5 + sum_j sigmoid(z_j - z_i)   (:102-106)
-  for (int i = warp; i < N; i += nwarps) {
-    const float zi = v.z[i];
-    float acc = 0.f;
-    for (int j = lane; j < N; j += 32) {
-      const float d = v.z[j] - zi;
-      const float e = expf(-fabsf(d));
-      acc += d >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+  // [nwarps][N] cross-warp column partials (T > 0), placed after the list view
+  float* colpart = reinterpret_cast<float*>(smem_raw + ((list_smem_bytes(N) + 15) & ~(size_t)15));
+  if (T > 0) {
+    float col[T > 0 ? T : 1];
+#pragma unroll
+    for (int t = 0; t < T; ++t) col[t] = 0.f;
+    for (int i = warp; i < N; i += nwarps) {
+      const float zi = v.z[i];
+      float acc = 0.f;
+      const int t0 = i >> 5;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int j = lane + 32 * t;
+        if (t >= t0 && j > i && j < N) {
+          const float d = v.z[j] - zi;
+          const float e = __expf(-fabsf(d));
+          const float rc = __frcp_rn(1.f + e);
+          const float big = rc, small = e * rc;    // sigmoid(|d|), sigmoid(-|d|)
+          acc += d >= 0.f ? big : small;            // sigmoid(z_j - z_i) -> r_i
+          col[t] += d >= 0.f ? small : big;         // sigmoid(z_i - z_j) -> r_j
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) r[i] = acc;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) r[i] = acc + 0.5f;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int j = lane + 32 * t;
+      if (j < N) colpart[warp * N + j] = col[t];
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += blockDim.x) {
+      // + 0.5 of the reference (:106) + sigmoid(0) = 0.5 of the skipped j == i term
+      float acc = r[i] + 1.0f;
+      for (int w = 0; w < nwarps; ++w) acc += colpart[w * N + i];
+      r[i] = acc;
+    }
+  } else {
+    for (int i = warp; i < N; i += nwarps) {
+      const float zi = v.z[i];
+      float acc = 0.f;
+      for (int j = lane; j < N; j += 32) {
+        const float d = v.z[j] - zi;
+        const float e = __expf(-fabsf(d));
+        const float rc = __frcp_rn(1.f + e);
+        acc += d >= 0.f ? rc : e * rc;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) r[i] = acc + 0.5f;
+    }
   }
   __syncthreads();
 
@@ -467,18 +512,54 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
   // pass 2: grad_k = (1/T) sum_i (c_i - c_k) sigmoid'(z_k - z_i)
   if (grad) {
     const float gs = grad_scale / temperature * (scale_by_weight ? list_w : 1.f);
-    for (int k = warp; k < N; k += nwarps) {
-      float acc = 0.f;
-      if (v.mv[k]) {
+    if (T > 0) {
+      float* gacc = reinterpret_cast<float*>(v.l);   // raw labels are no longer needed
+      float col[T > 0 ? T : 1];
+#pragma unroll
+      for (int t = 0; t < T; ++t) col[t] = 0.f;
+      for (int k = warp; k < N; k += nwarps) {
         const float zk = v.z[k], ck = c[k];
-        for (int i = lane; i < N; i += 32) {
-          const float e = expf(-fabsf(zk - v.z[i]));
-          const float inv = 1.f / (1.f + e);
-          acc += (c[i] - ck) * (e * inv * inv);
+        float acc = 0.f;
+        const int t0 = k >> 5;
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int i = lane + 32 * t;
+          if (t >= t0 && i > k && i < N) {
+            const float e = __expf(-fabsf(zk - v.z[i]));
+            const float rc = __frcp_rn(1.f + e);
+            const float term = (c[i] - ck) * (e * rc * rc);
+            acc += term;        // -> grad_k
+            col[t] -= term;     // -> grad_i (antisymmetric)
+          }
         }
+        acc = warp_sum(acc);
+        if (lane == 0) gacc[k] = acc;
       }
-      acc = warp_sum(acc);
-      if (lane == 0) grad[(size_t)b * N + k] = acc * gs;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int j = lane + 32 * t;
+        if (j < N) colpart[warp * N + j] = col[t];
+      }
+      __syncthreads();
+      for (int k = tid; k < N; k += blockDim.x) {
+        float acc = gacc[k];
+        for (int w = 0; w < nwarps; ++w) acc += colpart[w * N + k];
+        grad[(size_t)b * N + k] = v.mv[k] ? acc * gs : 0.f;
+      }
+    } else {
+      for (int k = warp; k < N; k += nwarps) {
+        float acc = 0.f;
+        if (v.mv[k]) {
+          const float zk = v.z[k], ck = c[k];
+          for (int i = lane; i < N; i += 32) {
+            const float e = __expf(-fabsf(zk - v.z[i]));
+            const float rc = __frcp_rn(1.f + e);
+            acc += (c[i] - ck) * (e * rc * rc);
+          }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) grad[(size_t)b * N + k] = acc * gs;
+      }
     }
   }
   if (tid == 0) {
@@ -725,21 +806,35 @@ extern "C" int tfr_approx_loss_fwd_bwd(const float* scores, const float* labels,
   TFR_REQUIRE(loss != nullptr, "loss must not be NULL");
   TFR_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (NDCG) or 1 (MRR)");
   if (B == 0) return TFR_OK;
-  const size_t smem = list_smem_bytes(N);
   cudaStream_t st = (cudaStream_t)stream;
-  if (mode == 0) {
-    rc = prep_smem(approx_loss_kernel<0>, smem);
-    if (rc) return rc;
-    approx_loss_kernel<0><<<B, kLossThreads, smem, st>>>(scores, labels, item_w, w_per_item,
-                                                        mask, N, temperature, grad_scale,
-                                                        scale_by_weight, grad, loss, weight);
-  } else {
-    rc = prep_smem(approx_loss_kernel<1>, smem);
-    if (rc) return rc;
-    approx_loss_kernel<1><<<B, kLossThreads, smem, st>>>(scores, labels, item_w, w_per_item,
-                                                        mask, N, temperature, grad_scale,
-                                                        scale_by_weight, grad, loss, weight);
+  const int T = N <= 1024 ? (N + 31) / 32 : 0;
+  // column partials of the triangular loop: [kLossThreads / 32][N] floats after `red`
+  const size_t smem = ((list_smem_bytes(N) + 15) & ~(size_t)15) +
+                      (T > 0 ? (size_t)(kLossThreads / 32) * N * 4 : 0);
+#define TFR_APPROX_CASE(MODE_, T_)                                                          \
+  {                                                                                         \
+    rc = prep_smem(approx_loss_kernel<MODE_, T_>, smem);                                    \
+    if (rc) return rc;                                                                      \
+    approx_loss_kernel<MODE_, T_><<<B, kLossThreads, smem, st>>>(                           \
+        scores, labels, item_w, w_per_item, mask, N, temperature, grad_scale,               \
+        scale_by_weight, grad, loss, weight);                                               \
   }
+#define TFR_APPROX_T(MODE_)                                   \
+  if (T == 0) TFR_APPROX_CASE(MODE_, 0)                       \
+  else if (T <= 1) TFR_APPROX_CASE(MODE_, 1)                  \
+  else if (T <= 2) TFR_APPROX_CASE(MODE_, 2)                  \
+  else if (T <= 4) TFR_APPROX_CASE(MODE_, 4)                  \
+  else if (T <= 7) TFR_APPROX_CASE(MODE_, 7)                  \
+  else if (T <= 8) TFR_APPROX_CASE(MODE_, 8)                  \
+  else if (T <= 16) TFR_APPROX_CASE(MODE_, 16)                \
+  else TFR_APPROX_CASE(MODE_, 32)
+  if (mode == 0) {
+    TFR_APPROX_T(0)
+  } else {
+    TFR_APPROX_T(1)
+  }
+#undef TFR_APPROX_T
+#undef TFR_APPROX_CASE
   TFR_LAUNCH_OK();
   return TFR_OK;
 }

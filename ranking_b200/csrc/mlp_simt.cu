@@ -210,7 +210,143 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, size_t str
   out[i] = acc;
 }
 
+// Output-layer backward, finer grain: one block per `rows_per` rows, RL row lanes x
+// K columns.  Per block b it writes slot[b] = { dW[K*O], db[O], csum[K] } where
+// csum[k] = sum_m dH[m, k] (the bias gradient of the last hidden layer).
+__global__ void __launch_bounds__(1024)
+out_layer_bwd2_kernel(const float* __restrict__ H, int M, int K, int O,
+                      const float* __restrict__ W, const float* __restrict__ dS,
+                      const uint8_t* __restrict__ mask, int act, int rows_per, int RL,
+                      float* __restrict__ dH, float* __restrict__ slots, size_t slot_stride) {
+  extern __shared__ float sm[];   // [RL][K * (O + 1) + O]
+  const int KT = blockDim.x / RL;          // threads along k (>= K, multiple of 32)
+  const int k = threadIdx.x % KT, rl = threadIdx.x / KT;
+  const int mbeg = blockIdx.x * rows_per, mend = min(M, mbeg + rows_per);
+  float w[kMaxOut], dw[kMaxOut], db[kMaxOut];
+  float csum = 0.f;
+#pragma unroll
+  for (int o = 0; o < kMaxOut; ++o) {
+    w[o] = (k < K && o < O) ? W[(size_t)k * O + o] : 0.f;
+    dw[o] = 0.f;
+    db[o] = 0.f;
+  }
+  for (int m = mbeg + rl; m < mend; m += RL) {
+    const bool live = !(mask && O == 1 && !mask[m]);
+    float ds[kMaxOut];
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) ds[o] = (o < O && live) ? dS[(size_t)m * O + o] : 0.f;
+    if (k < K) {
+      const float h = H[(size_t)m * K + k];
+      float dh = 0.f;
+#pragma unroll
+      for (int o = 0; o < kMaxOut; ++o) {
+        dh = fmaf(ds[o], w[o], dh);
+        dw[o] = fmaf(h, ds[o], dw[o]);
+      }
+      if (dH) {
+        if (act == TFR_ACT_RELU && !(h > 0.f)) dh = 0.f;
+        dH[(size_t)m * K + k] = dh;
+        csum += dh;
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < kMaxOut; ++o) db[o] += ds[o];
+  }
+  const int per = K * (O + 1) + O;
+  float* mine = sm + (size_t)rl * per;
+  if (k < K) {
+    for (int o = 0; o < O; ++o) mine[k * O + o] = dw[o];
+    mine[K * O + O + k] = csum;
+  }
+  if (k == 0)
+    for (int o = 0; o < O; ++o) mine[K * O + o] = db[o];
+  __syncthreads();
+  float* out = slots + (size_t)blockIdx.x * slot_stride;
+  for (int i = threadIdx.x; i < per; i += blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < RL; ++r) acc += sm[(size_t)r * per + i];
+    out[i] = acc;
+  }
+}
+
+// dst[z][dst_off + i] = sum_{g < group} src[z * group + g][src_off + i], i < n.
+__global__ void __launch_bounds__(256)
+regroup_sum_kernel(const float* __restrict__ src, int slots_in, size_t src_stride,
+                   size_t src_off, int n, int group, float* __restrict__ dst,
+                   size_t dst_stride, size_t dst_off) {
+  const int z = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+  for (int g = 0; g < group; ++g) {
+    const int s = z * group + g;
+    if (s < slots_in) acc += src[(size_t)s * src_stride + src_off + i];
+  }
+  dst[(size_t)z * dst_stride + dst_off + i] = acc;
+}
+
 // ------------------------------------------------------------- host side ---
+int mlp_out_layer_bwd2(const float* H, int M, int K, int O, const float* W, const float* dS,
+                       const uint8_t* mask, int act, int rows_per, float* dH, float* slots,
+                       size_t slot_stride, cudaStream_t st) {
+  const int K32 = ((K + 31) / 32) * 32;
+  int RL = 1, threads = K32;
+  if (K32 <= 256) { RL = 256 / K32; threads = RL * K32; }
+  const int blocks = (M + rows_per - 1) / rows_per;
+  const size_t smem = (size_t)RL * (K * (O + 1) + O) * sizeof(float);
+  if (smem > 48 * 1024)
+    TFR_CUDA_OK(cudaFuncSetAttribute(out_layer_bwd2_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  out_layer_bwd2_kernel<<<blocks, threads, smem, st>>>(H, M, K, O, W, dS, mask, act, rows_per, RL,
+                                                      dH, slots, slot_stride);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+int mlp_regroup_sum(const float* src, int slots_in, size_t src_stride, size_t src_off, int n,
+                    int group, float* dst, int slots_out, size_t dst_stride, size_t dst_off,
+                    cudaStream_t st) {
+  dim3 grid((n + 255) / 256, slots_out);
+  regroup_sum_kernel<<<grid, 256, 0, st>>>(src, slots_in, src_stride, src_off, n, group, dst,
+                                          dst_stride, dst_off);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+int mlp_out_layer_fwd(const float* H, int M, int K, int O, const float* W, const float* bias,
+                      const uint8_t* mask, float* scores, cudaStream_t st) {
+  const int rows_per_block = 8;
+  out_layer_fwd_kernel<<<(M + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(
+      H, M, K, O, W, bias, mask, scores);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+int mlp_out_layer_bwd(const float* H, int M, int K, int O, const float* W, const float* dS,
+                      const uint8_t* mask, int act, int rows_per, int splits, float* dH,
+                      float* partial, size_t pstride, cudaStream_t st) {
+  const int threads = ((K + 31) / 32) * 32;
+  out_layer_bwd_kernel<<<splits, threads, 0, st>>>(H, M, K, O, W, dS, mask, act, rows_per, dH,
+                                                  partial, pstride);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+int mlp_colsum(const float* dZ, int M, int N, int rows_per, int splits, float* partial,
+               size_t pstride, size_t col_offset, cudaStream_t st) {
+  colsum_kernel<<<splits, 256, 0, st>>>(dZ, M, N, rows_per, partial, pstride, col_offset);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+int mlp_reduce_partials(const float* partial, int splits, size_t stride, size_t n, float* out,
+                        cudaStream_t st) {
+  reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, splits, stride, n,
+                                                                     out);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
 int mlp_simt_fwd(const float* X, int M, const MlpPlan& p, const float* params,
                  const uint8_t* mask, float* ws, float* scores, cudaStream_t st) {
   const int L = p.n_dense - 1;  // hidden layers

@@ -1,0 +1,172 @@
+// K5/K6 tensor-core path: the scorer tower's Dense layers on the tcgen05 TF32
+// engine (tc_gemm.cu).  passes = 3 is the fp32-faithful 3xTF32 mode used for the
+// fp32 configuration; passes = 1 is plain TF32.
+//
+//   forward  H_d   = act(A_d W_d + b_d)        A K-major, W MN-major (pre-split hi/lo)
+//   backward dW_d  = A_d^T dZ_d                both operands MN-major, split on the fly,
+//                                              rows split over CTAs -> partials -> reduce
+//            dZ_d-1 = (dZ_d W_d^T) * act'(H)   dZ K-major, W K-major (pre-split hi/lo)
+// The [K -> output_units] layer and the bias column sums stay on CUDA cores
+// (GEMV / reductions, HBM-bound).
+#include "common.cuh"
+#include "mlp.h"
+#include "tc_gemm.cuh"
+
+namespace tfr {
+
+__global__ void __launch_bounds__(256)
+split_params_kernel(const float* __restrict__ p, size_t n, float* __restrict__ hi,
+                    float* __restrict__ lo) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = p[i];
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));   // round-to-nearest TF32
+  const float h = __uint_as_float(r);
+  hi[i] = h;
+  lo[i] = v - h;
+}
+
+static int check_dims(const MlpPlan& p) {
+  const int L = p.n_dense - 1;
+  for (int d = 0; d <= L; ++d)
+    if (p.dims[d] % 4 != 0) {
+      set_error("tensor-core scorer path needs layer widths that are multiples of 4 "
+                "(dims[%d] = %d); use precision fp32", d, p.dims[d]);
+      return TFR_UNSUPPORTED;
+    }
+  return TFR_OK;
+}
+
+static int split_params(const MlpPlan& p, const float* params, float* ws, int passes,
+                        cudaStream_t st) {
+  if (passes != 3) return TFR_OK;
+  split_params_kernel<<<(unsigned)((p.n_params + 255) / 256), 256, 0, st>>>(
+      params, p.n_params, ws + p.whi_off, ws + p.wlo_off);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+int mlp_tc_fwd(const float* X, int M, const MlpPlan& p, const float* params,
+               const uint8_t* mask, float* ws, float* scores, int passes, cudaStream_t st) {
+  int rc = check_dims(p);
+  if (rc) return rc;
+  rc = split_params(p, params, ws, passes, st);
+  if (rc) return rc;
+  const int L = p.n_dense - 1;
+  const float* whi = passes == 3 ? ws + p.whi_off : params;
+  const float* wlo = passes == 3 ? ws + p.wlo_off : nullptr;
+  const float* in = X;
+  for (int d = 0; d < L; ++d) {
+    tc::GemmDesc g{};
+    g.A = in; g.lda = p.dims[d];
+    g.B = whi + p.w_off[d]; g.ldb = p.dims[d + 1];
+    g.B_lo = wlo ? wlo + p.w_off[d] : nullptr;
+    g.C = ws + p.act_off[d]; g.ldc = p.dims[d + 1];
+    g.GM = M; g.GN = p.dims[d + 1]; g.GK = p.dims[d];
+    g.a_mn = 0; g.b_mn = 1; g.passes = passes; g.split_b = 0;
+    g.epi = tc::EPI_BIAS_ACT; g.bias = params + p.b_off[d]; g.act = p.activation;
+    g.splits = 1; g.split_stride = 0;
+    rc = tc::gemm(g, st);
+    if (rc) return rc;
+    in = g.C;
+  }
+  return mlp_out_layer_fwd(in, M, p.dims[L], p.dims[L + 1], params + p.w_off[L],
+                           params + p.b_off[L], mask, scores, st);
+}
+
+int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
+               const float* dscores, const uint8_t* mask, float* ws, float* grads,
+               int passes, cudaStream_t st) {
+  int rc = check_dims(p);
+  if (rc) return rc;
+  const int L = p.n_dense - 1;
+  float* partial = ws + p.partial_off;
+  const size_t pstride = p.partial_stride;
+  const int rows_per = p.rows_per_split, splits = p.splits;
+  const float* whi = passes == 3 ? ws + p.whi_off : params;   // written by the forward
+  const float* wlo = passes == 3 ? ws + p.wlo_off : nullptr;
+  float* dz_cur = ws + p.dz_off[0];
+  float* dz_nxt = ws + p.dz_off[1];
+  float* tiles = ws + p.tile_off;
+  float* oslots = ws + p.oslot_off;
+  {
+    // Output layer (GEMV-shaped, CUDA cores): dZ of the last hidden layer, plus per
+    // 256-row block {dW_out, db_out, column sums of dZ}; regrouped to the
+    // `splits` partial slots and reduced.
+    const int K = p.dims[L], O = p.dims[L + 1];
+    const float* H = L > 0 ? ws + p.act_off[L - 1] : X;
+    rc = mlp_out_layer_bwd2(H, M, K, O, params + p.w_off[L], dscores, mask,
+                            L > 0 ? p.activation : TFR_ACT_NONE, p.out_rows,
+                            L > 0 ? dz_cur : nullptr, oslots, p.oslot_stride, st);
+    if (rc) return rc;
+    const int group = rows_per / p.out_rows;
+    rc = mlp_regroup_sum(oslots, p.out_slots, p.oslot_stride, 0, K * O + O, group, partial,
+                         splits, pstride, 0, st);
+    if (rc) return rc;
+    rc = mlp_reduce_partials(partial, splits, pstride, (size_t)K * O + O, grads + p.w_off[L], st);
+    if (rc) return rc;
+    if (L > 0) {  // bias partials of hidden layer L-1 (its dZ was just produced)
+      rc = mlp_regroup_sum(oslots, p.out_slots, p.oslot_stride, (size_t)K * O + O, K, group,
+                           partial, splits, pstride, (size_t)p.dims[L - 1] * K, st);
+      if (rc) return rc;
+    }
+  }
+  for (int d = L - 1; d >= 0; --d) {
+    const int Kin = p.dims[d], Nout = p.dims[d + 1];
+    const float* A = d > 0 ? ws + p.act_off[d - 1] : X;
+    {
+      // dW[Kin, Nout] = A^T dZ.  Pick the orientation with fewer UMMA cycles:
+      //   direct : GM = Kin (tiles of 128), GN = Nout
+      //   swapped: GM = Nout,               GN = Kin, stored transposed
+      auto cost = [](int gm, int gn) {
+        const int n16 = (gn + 15) / 16 * 16;
+        const int ntiles = (n16 + 255) / 256;
+        return (long long)((gm + 127) / 128) * ntiles * (n16 < 256 ? n16 : 256);
+      };
+      const bool swapped = cost(Nout, Kin) < cost(Kin, Nout);
+      tc::GemmDesc g{};
+      if (!swapped) {
+        g.A = A; g.lda = Kin; g.B = dz_cur; g.ldb = Nout;
+        g.GM = Kin; g.GN = Nout; g.store_transposed = 0;
+      } else {
+        g.A = dz_cur; g.lda = Nout; g.B = A; g.ldb = Kin;
+        g.GM = Nout; g.GN = Kin; g.store_transposed = 1;
+      }
+      g.B_lo = nullptr;
+      g.C = partial; g.ldc = Nout;
+      g.GK = M;
+      g.a_mn = 1; g.b_mn = 1; g.passes = passes; g.split_b = 1;
+      g.epi = tc::EPI_STORE;
+      g.splits = splits; g.split_stride = pstride;
+      rc = tc::gemm(g, st);
+      if (rc) return rc;
+    }
+    // (the bias region partial[z][Kin*Nout ..] was filled when dZ_d was produced)
+    rc = mlp_reduce_partials(partial, splits, pstride, (size_t)Kin * Nout + Nout,
+                             grads + p.w_off[d], st);
+    if (rc) return rc;
+    if (d > 0) {
+      tc::GemmDesc g{};
+      g.A = dz_cur; g.lda = Nout;
+      g.B = whi + p.w_off[d]; g.ldb = Nout;     // W [Kin rows (GN), Nout (GK)] : K-major
+      g.B_lo = wlo ? wlo + p.w_off[d] : nullptr;
+      g.C = dz_nxt; g.ldc = Kin;
+      g.GM = M; g.GN = Kin; g.GK = Nout;
+      g.a_mn = 0; g.b_mn = 0; g.passes = passes; g.split_b = 0;
+      g.epi = tc::EPI_MASK_POS; g.aux = ws + p.act_off[d - 1]; g.act = p.activation;
+      g.splits = 1; g.split_stride = 0;
+      g.colsum = tiles; g.colsum_stride = (int)p.tile_stride;
+      rc = tc::gemm(g, st);
+      if (rc) return rc;
+      // column sums of dZ_{d-1}: 4 quarters x (rows_per / 128) tiles per split slot
+      rc = mlp_regroup_sum(tiles, p.tile_slots, p.tile_stride, 0, Kin, 4 * (rows_per / 128),
+                           partial, splits, pstride, (size_t)p.dims[d - 1] * Kin, st);
+      if (rc) return rc;
+      float* t = dz_cur; dz_cur = dz_nxt; dz_nxt = t;
+    }
+  }
+  return TFR_OK;
+}
+
+}  // namespace tfr

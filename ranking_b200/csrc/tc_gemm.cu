@@ -132,6 +132,16 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Round-to-nearest TF32 (low 13 mantissa bits cleared).  With RN the residual
+// lo = x - hi is at most 2^-12 |x| and zero-mean, so the dropped lo*lo term of the
+// 3xTF32 product is ~2^-24 and unbiased (a truncating split leaves a one-sided
+// 2^-20 bias that accumulates over long reductions).
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
 // UMMA shared-memory matrix descriptor (Blackwell version field set).
 //   K-major : SWIZZLE_128B (layout type 2): rows of 128 B (32 fp32 of K), 16-byte
 //             chunks XOR-ed with (row % 8); 8-row atoms every SBO = 1024 B.
@@ -164,6 +174,8 @@ struct KernelArgs {
   int kb_per_split;    // k-blocks (of 32) handled by one blockIdx.z
   size_t split_stride;
   uint32_t tmem_cols;
+  float* colsum;       // optional [4 * m_tiles][colsum_stride]: column sums of the
+  int colsum_stride;   //   stored tile per 32-row quarter (bias gradients)
 };
 
 template <bool A_MN, bool B_MN, int PASSES, bool SPLIT_B>
@@ -284,7 +296,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
       }
-      umma_commit(accum);
+      if (nkb > 0) umma_commit(accum);
     }
   } else {
     // ------------------------------------- splitters, then epilogue (warps 2..5)
@@ -306,10 +318,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int c = t; c < chunks; c += 128) {
             const float4 v = hi[c];
             float4 h, l;
-            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+            h.x = tf32_rn(v.x);
+            h.y = tf32_rn(v.y);
+            h.z = tf32_rn(v.z);
+            h.w = tf32_rn(v.w);
             l.x = v.x - h.x;
             l.y = v.y - h.y;
             l.z = v.z - h.z;
@@ -323,30 +335,72 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     // epilogue: TMEM lane quarter is fixed by warp id % 4
-    mbar_wait(accum, 0);
+    if (nkb > 0) mbar_wait(accum, 0);   // an empty k range (split tail) stores zeros
     tc_fence_after();
     const int q = warp & 3;
-    const int row = m0 + q * 32 + lane;
     float* C = args.C + static_cast<size_t>(blockIdx.z) * args.split_stride;
-    for (int c0 = 0; c0 < args.n_umma; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
+    if (args.store_transposed) {
+      // lane = row: consecutive lanes hit consecutive addresses of C^T.
+      const int row = m0 + q * 32 + lane;
+      for (int c0 = 0; c0 < args.n_umma; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = n0 + c0 + j;
-        if (c0 + j >= args.n_umma || col >= args.GN || row >= args.GM) continue;
-        float x = __uint_as_float(v[j]);
-        if (args.epi == EPI_BIAS_ACT) {
-          x += __ldg(args.bias + col);
-          if (args.act == TFR_ACT_RELU) x = fmaxf(x, 0.f);
-        } else if (args.epi == EPI_MASK_POS) {
-          if (args.act == TFR_ACT_RELU &&
-              !(__ldg(args.aux + static_cast<size_t>(row) * args.ldc + col) > 0.f))
-            x = 0.f;
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + c0 + j;
+          if (c0 + j >= args.n_umma || col >= args.GN || row >= args.GM) continue;
+          const float x = nkb > 0 ? __uint_as_float(v[j]) : 0.f;
+          C[static_cast<size_t>(col) * args.ldc + row] = x;
         }
-        if (args.store_transposed) C[static_cast<size_t>(col) * args.ldc + row] = x;
-        else C[static_cast<size_t>(row) * args.ldc + col] = x;
+      }
+    } else {
+      // Row-major store: transpose each 32x32 block through shared memory (the
+      // pipeline stages are idle now) so that a warp writes 128 contiguous bytes
+      // of one row per instruction; bias / ReLU mask / column sums ride along.
+      float* tb = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+      const int rows_here = min(32, args.GM - (m0 + q * 32));
+      for (int c0 = 0; c0 < args.n_umma; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = nkb > 0 ? __uint_as_float(v[j]) : 0.f;
+        __syncwarp();
+        const int col = n0 + c0 + lane;
+        const bool col_ok = (c0 + lane < args.n_umma) && col < args.GN;
+        const float bv = (args.epi == EPI_BIAS_ACT && col_ok) ? __ldg(args.bias + col) : 0.f;
+        const size_t off0 = static_cast<size_t>(m0 + q * 32) * args.ldc + col;
+        // ReLU mask source: issue all 32 independent loads before any store (the
+        // stores may alias them as far as the compiler knows).
+        float keep[32];
+        if (args.epi == EPI_MASK_POS && args.act == TFR_ACT_RELU) {
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr)
+            keep[rr] = (col_ok && rr < rows_here)
+                           ? __ldg(args.aux + off0 + static_cast<size_t>(rr) * args.ldc)
+                           : 1.f;
+        }
+        float csum = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          if (rr < rows_here) {
+            float x = tb[rr * 33 + lane];
+            if (args.epi == EPI_BIAS_ACT) {
+              x += bv;
+              if (args.act == TFR_ACT_RELU) x = fmaxf(x, 0.f);
+            } else if (args.epi == EPI_MASK_POS && args.act == TFR_ACT_RELU) {
+              if (!(keep[rr] > 0.f)) x = 0.f;
+            }
+            if (col_ok) {
+              C[off0 + static_cast<size_t>(rr) * args.ldc] = x;
+              csum += x;
+            }
+          }
+        }
+        if (args.colsum && col_ok)
+          args.colsum[static_cast<size_t>(blockIdx.y * 4 + q) * args.colsum_stride + col] = csum;
+        __syncwarp();
       }
     }
   }
@@ -435,9 +489,7 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   const int nkb_total = (g.GK + BK - 1) / BK;
   int splits = g.splits < 1 ? 1 : g.splits;
   int kb_per_split = (nkb_total + splits - 1) / splits;
-  splits = (nkb_total + kb_per_split - 1) / kb_per_split;
-  TFR_REQUIRE(splits == (g.splits < 1 ? 1 : g.splits),
-              "tc gemm: splits %d leave empty k ranges (GK %d)", g.splits, g.GK);
+  // (a split whose k range is empty stores zeros, so any split count is legal)
 
   CUtensorMap tmA, tmB, tmBlo;
   int rc;
@@ -467,6 +519,10 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   uint32_t cols = 32;
   while ((int)cols < n_umma) cols <<= 1;
   ka.tmem_cols = cols;
+  ka.colsum = g.colsum;
+  ka.colsum_stride = g.colsum_stride;
+  TFR_REQUIRE(!g.colsum || (!g.store_transposed && splits == 1),
+              "tc gemm: colsum output needs a row-major, unsplit store");
   TFR_REQUIRE(g.epi != EPI_BIAS_ACT || g.bias, "tc gemm: bias required");
   TFR_REQUIRE(g.epi != EPI_MASK_POS || g.aux, "tc gemm: aux required");
 
@@ -505,7 +561,7 @@ extern "C" int tfr_tc_gemm(const float* A, int lda, const float* B, int ldb, con
                            int passes, int split_b, int epi, const float* bias, const float* aux,
                            int act, int store_transposed, int splits, size_t split_stride,
                            void* stream) {
-  tfr::tc::GemmDesc g;
+  tfr::tc::GemmDesc g{};
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.B_lo = B_lo; g.C = C; g.ldc = ldc;
   g.GM = GM; g.GN = GN; g.GK = GK; g.a_mn = a_mn; g.b_mn = b_mn; g.passes = passes;
   g.split_b = split_b; g.epi = epi; g.bias = bias; g.aux = aux; g.act = act;

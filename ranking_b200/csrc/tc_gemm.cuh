@@ -35,6 +35,8 @@ struct GemmDesc {
   int store_transposed;          // write element (r, c) to C[c * ldc + r]
   int splits;                    // split the GK loop over blockIdx.z; split z writes to
   size_t split_stride;           //   C + z * split_stride (floats); k range rounded to 32
+  float* colsum;                 // optional: per 32-row quarter column sums of the stored
+  int colsum_stride;             //   tile, slot (m_tile * 4 + quarter), row pitch in floats
 };
 
 // Returns a tfr_status.  Requirements (checked): lda/ldb multiples of 4 floats,

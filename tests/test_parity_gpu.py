@@ -225,6 +225,7 @@ def test_keras_metric_objects(cuda_api, oracle_api):
 # ------------------------------ scorer tower --------------------------------
 def _tower_and_params(tfr, d, hidden, out, seed, activation='relu',
                       precision='fp32'):
+  torch.manual_seed(seed)
   tower = tfr.keras.layers.create_tower(hidden, out, activation=activation,
                                         use_batch_norm=False, dropout=0,
                                         input_dim=d, seed=seed,
@@ -268,6 +269,55 @@ def test_tower_forward_backward(oracle_api, shape):
   assert _rel_err(tower.flat.grad, _flat_grad(params)) <= 5e-5
 
 
+@pytest.mark.parametrize('precision,tol_fwd,tol_bwd', [('tf32x3', 1e-5, 5e-5),
+                                                       ('tf32', 5e-3, 0.15)])
+@pytest.mark.parametrize('shape', [
+    (300, 136, [256, 128, 64], 1, 'relu'),
+    (4100, 136, [256, 128, 64], 1, 'relu'),    # several row splits
+    (1000, 16, [32, 8], 1, 'relu'),
+    (513, 24, [48], 2, None),
+    # N tile > 256 columns.  Identity activation: with ReLU a pre-activation within
+    # rounding distance of 0 flips its mask and moves one dW entry by ~1e-3, which
+    # says nothing about the GEMMs (3.3M hidden units here).
+    (6400, 256, [512, 64], 1, None),
+])
+def test_tower_tensor_core_path(oracle_api, shape, precision, tol_fwd, tol_bwd):
+  """tcgen05 scorer path: 3xTF32 must stay fp32-faithful (1e-5), TF32 is looser.
+
+  With ReLU, a hidden pre-activation that lies within rounding distance of zero
+  can take the other branch than in the fp64 oracle; that moves a handful of
+  gradient entries by O(1e-3) and is a property of ReLU, not of the GEMMs.  The
+  gradient check therefore uses the relative L2 error for ReLU towers and the
+  max-norm error for identity towers."""
+  import ranking_b200 as tfr
+  torch.manual_seed(1234)
+  m, d, hidden, out, act = shape
+  tower, params = _tower_and_params(tfr, d, hidden, out, seed=m, activation=act,
+                                    precision=precision)
+  g = torch.Generator().manual_seed(m)
+  x = torch.randn(m, d, generator=g)
+  up = torch.randn(m, out, generator=g)
+  y = tower(x.cuda())
+  (y * up.cuda()).sum().backward()
+  ref = oracle_api.scorer.tower_forward(x.double(), params, activation=act)
+  (ref * up.double()).sum().backward()
+  assert _rel_err(y, ref) <= tol_fwd, _rel_err(y, ref)
+  got, want = tower.flat.grad.detach().cpu().double(), _flat_grad(params)
+  if act is None:
+    assert _rel_err(got, want) <= tol_bwd, _rel_err(got, want)
+  else:
+    l2 = float((got - want).norm() / want.norm())
+    assert l2 <= tol_bwd, l2
+    assert _rel_err(got, want) <= max(100 * tol_bwd, 5e-3)
+
+
+def test_tower_tensor_core_rejects_unaligned_widths():
+  import ranking_b200 as tfr
+  tower, _ = _tower_and_params(tfr, 17, [33], 1, seed=1, precision='tf32x3')
+  with pytest.raises(ValueError):
+    tower(torch.randn(64, 17).cuda())
+
+
 def test_tower_restore_list_mask(oracle_api):
   import ranking_b200 as tfr
   tower, params = _tower_and_params(tfr, 8, [16], 1, seed=1)
@@ -307,12 +357,13 @@ def test_dnn_scorer_contract(oracle_api):
   assert _rel_err(got, ref) <= RTOL
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
 @pytest.mark.parametrize('loss_key,kw', [
     ('approx_ndcg_loss', {}),
     ('pairwise_logistic_loss', {}),
     ('softmax_loss', {}),
 ])
-def test_fused_train_step_matches_oracle(oracle_api, loss_key, kw):
+def test_fused_train_step_matches_oracle(oracle_api, loss_key, kw, precision):
   """One full step: scorer fwd -> loss -> scorer bwd -> Adagrad; loss, flat
   gradient and updated parameters vs the oracle (autograd + Keras Adagrad)."""
   import ranking_b200 as tfr
@@ -320,7 +371,8 @@ def test_fused_train_step_matches_oracle(oracle_api, loss_key, kw):
   scores_unused, labels, _, _ = _batch(b, n, seed=13)
   x = torch.randn(b, n, d, generator=torch.Generator().manual_seed(1))
   mask = labels >= 0
-  tower, params = _tower_and_params(tfr, d, [32, 16], 1, seed=7)
+  tower, params = _tower_and_params(tfr, d, [32, 16], 1, seed=7,
+                                    precision=precision)
   p0 = tower.flat.detach().clone()
   loss_obj = tfr.keras.losses.get(loss_key, **kw)
   tr = tfr.train.RankingTrainer(tower, loss_obj, optimizer='adagrad',

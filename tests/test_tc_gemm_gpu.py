@@ -37,7 +37,7 @@ def run_gemm(gm, gn, gk, a_mn, b_mn, passes, split_b, epi=0, act=0, transposed=0
     ref = torch.where(aux.double() > 0, ref, torch.zeros_like(ref))
   a_store = (A.t().contiguous() if a_mn else A.contiguous()).cuda()
   if passes == 3 and not split_b:
-    b_hi = (B.view(torch.int32) & -8192).view(torch.float32)
+    b_hi = ((B.view(torch.int32) + 4096) & -8192).view(torch.float32)   # RN to TF32
     b_lo = B - b_hi
   else:
     b_hi, b_lo = B, None
@@ -52,10 +52,11 @@ def run_gemm(gm, gn, gk, a_mn, b_mn, passes, split_b, epi=0, act=0, transposed=0
     stride = 0
     C = torch.full((gn, gm) if transposed else (gm, gn), float('nan'), device='cuda')
   ldc = gm if transposed else gn
+  bias_d, aux_d = bias.cuda(), aux.cuda()    # keep alive until the sync below
   rc = _C.lib.tfr_tc_gemm(
       _C.ptr(a_store), a_store.shape[1], _C.ptr(b_store), b_store.shape[1],
       _C.ptr(b_lo_store), _C.ptr(C), ldc, gm, gn, gk, a_mn, b_mn, passes, split_b,
-      epi, _C.ptr(bias.cuda()), _C.ptr(aux.cuda()), act, transposed, splits, stride,
+      epi, _C.ptr(bias_d), _C.ptr(aux_d), act, transposed, splits, stride,
       _C.stream())
   _C.check(rc)
   torch.cuda.synchronize()
