@@ -229,6 +229,10 @@ int tfr_tc_gemm(const float* A, int lda, const float* B, int ldb, const float* B
                 const float* aux, int act, int store_transposed, int splits,
                 size_t split_stride, void* stream);
 
+/* Profiling aid for the engine above: device buffer [num_SMs][8] of int64 that each
+ * GEMM launch fills with per-warp-role mbarrier wait cycles (NULL disables). */
+int tfr_tc_set_debug(long long* buf);
+
 /* ---------------------------------------------------------------------------
  * Fused optimizer over the flat parameter buffer (the reference delegates to
  * tf.keras.optimizers; Adagrad is what its examples use:

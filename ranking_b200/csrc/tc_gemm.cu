@@ -10,8 +10,11 @@
 //   * the same four warps drain TMEM with tcgen05.ld in the epilogue (bias/ReLU,
 //     ReLU-mask, plain or transposed store).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
-// issuer, warps 2..5 = splitters during the main loop, epilogue afterwards.
+// The kernel is persistent: one CTA per SM walks a static list of output tiles.
+// Warp roles (448 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer, warps 2..9 = hi/lo splitters, warps 10..13 = epilogue.  The accumulator is
+// double-buffered in TMEM, so the epilogue of tile i overlaps the main loop of
+// tile i+1 and the prologue (barrier init, TMEM allocation) is paid once per SM.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -20,12 +23,16 @@
 namespace tfr {
 namespace tc {
 
-constexpr int kThreads = 192;
+constexpr int kSplitWarps = 8;
+constexpr int kSplitThreads = kSplitWarps * 32;
+constexpr int kEpiWarp0 = 2 + kSplitWarps;          // first epilogue warp
+constexpr int kThreads = (kEpiWarp0 + 4) * 32;      // 448
+constexpr int kEpiSmemBytes = 4 * 32 * 37 * 4;   // per-epilogue-warp transpose buffers (>= [32][36])
 constexpr int BM = 128;       // UMMA M (cta_group::1)
 constexpr int BK = 32;        // fp32 elements per 128-byte swizzle span
 constexpr int kATileBytes = BM * BK * 4;   // 16 KB
 constexpr int kMaxStages = 4;
-constexpr unsigned kSmemBudget = 227 * 1024 - 2048;
+constexpr unsigned kSmemBudget = 227 * 1024 - 2048 - kEpiSmemBytes;
 
 // ------------------------------------------------------------------ PTX -------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -54,8 +61,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must trap instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __forceinline__ long long mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return 0;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) {
@@ -64,6 +71,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+  return clock64() - t0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -171,11 +179,14 @@ struct KernelArgs {
   int epi, act, store_transposed;
   const float* bias;
   const float* aux;
-  int kb_per_split;    // k-blocks (of 32) handled by one blockIdx.z
+  int kb_per_split;    // k-blocks (of 32) handled by one k split
+  int m_tiles, n_tiles, splits;
   size_t split_stride;
   uint32_t tmem_cols;
   float* colsum;       // optional [4 * m_tiles][colsum_stride]: column sums of the
   int colsum_stride;   //   stored tile per 32-row quarter (bias gradients)
+  long long* dbg;      // optional [gridDim.x][8] wait-cycle counters per warp role
+  int vec_ok;          // C / aux / bias / colsum allow 16-byte vector access
 };
 
 template <bool A_MN, bool B_MN, int PASSES, bool SPLIT_B>
@@ -184,27 +195,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmBlo, const KernelArgs args) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms.
-  unsigned char* smem = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // (pointer arithmetic, not an integer round trip: keeps the shared address space so
+  // the compiler emits LDS/STS and knows these never alias global memory)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int kACopies = PASSES == 3 ? 2 : 1;
   constexpr int kBCopies = PASSES == 3 ? 2 : 1;
   const int a_bytes = kATileBytes * kACopies;
   const int stage_bytes = a_bytes + args.b_tile_bytes * kBCopies;
   const int S = args.stages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(S) * stage_bytes);
-  uint64_t* full = bars;               // TMA landed
-  uint64_t* split = bars + kMaxStages;  // hi/lo split done
-  uint64_t* empty = bars + 2 * kMaxStages;  // MMAs that read the stage retired
-  uint64_t* accum = bars + 3 * kMaxStages;  // accumulator complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 1);
+  unsigned char* epi_smem = smem + static_cast<size_t>(S) * stage_bytes;   // 4 x [32][33] floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + kEpiSmemBytes);
+  uint64_t* full = bars;                         // TMA landed
+  uint64_t* split = bars + kMaxStages;           // hi/lo split done
+  uint64_t* empty = bars + 2 * kMaxStages;       // MMAs that read the stage retired
+  uint64_t* acc_full = bars + 3 * kMaxStages;    // [2] accumulator buffer complete
+  uint64_t* acc_empty = bars + 3 * kMaxStages + 2;   // [2] accumulator buffer drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM;
-  const int n0 = blockIdx.x * args.n_umma;
   const int nkb_total = (args.GK + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * args.kb_per_split;
-  const int kb_end = min(nkb_total, kb_begin + args.kb_per_split);
-  const int nkb = kb_end - kb_begin;
+  const int tiles_mn = args.m_tiles * args.n_tiles;
+  const int total_tiles = tiles_mn * args.splits;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -212,14 +223,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (PASSES == 3 && !SPLIT_B) prefetch_tmap(&tmBlo);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&split[s], 128);
+      mbar_init(&split[s], kSplitWarps);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accum, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, args.tmem_cols);
+    tmem_alloc(tmem_slot, 2 * args.tmem_cols);   // two accumulator buffers
     tmem_relinquish();
   }
   tc_fence_before();
@@ -231,35 +245,56 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto sA_lo = [&](int s) { return sA_hi(s) + kATileBytes; };
   auto sB_hi = [&](int s) { return sA_hi(s) + a_bytes; };
   auto sB_lo = [&](int s) { return sB_hi(s) + args.b_tile_bytes; };
+  // tile -> (split z, m tile, n tile): consecutive CTAs work on neighbouring rows.
+  auto decode = [&](int tile, int& m0, int& n0, int& z, int& kb_begin, int& nkb) {
+    z = tile / tiles_mn;
+    const int r = tile - z * tiles_mn;
+    m0 = (r / args.n_tiles) * BM;
+    n0 = (r % args.n_tiles) * args.n_umma;
+    kb_begin = z * args.kb_per_split;
+    const int kb_end = min(nkb_total, kb_begin + args.kb_per_split);
+    nkb = max(kb_end - kb_begin, 0);
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------- TMA producer ----
     if (lane == 0) {
       const uint32_t tx_bytes =
           kATileBytes + args.b_tile_bytes * ((PASSES == 3 && !SPLIT_B) ? 2 : 1);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], tx_bytes);
-        const int k0 = (kb_begin + kb) * BK;
-        if (!A_MN) {
-          tma_load_2d(sA_hi(s), &tmA, &full[s], k0, m0);          // box [128 rows][32 k]
-        } else {
-          for (int i = 0; i < BM / 32; ++i)                        // boxes [32 k][32 m]
-            tma_load_2d(sA_hi(s) + i * 4096, &tmA, &full[s], m0 + 32 * i, k0);
-        }
-        if (!B_MN) {
-          tma_load_2d(sB_hi(s), &tmB, &full[s], k0, n0);           // box [n rows][32 k]
-          if (PASSES == 3 && !SPLIT_B) tma_load_2d(sB_lo(s), &tmBlo, &full[s], k0, n0);
-        } else {
-          const int nbox = args.b_tile_bytes / 4096;
-          for (int j = 0; j < nbox; ++j) {
-            tma_load_2d(sB_hi(s) + j * 4096, &tmB, &full[s], n0 + 32 * j, k0);
-            if (PASSES == 3 && !SPLIT_B)
-              tma_load_2d(sB_lo(s) + j * 4096, &tmBlo, &full[s], n0 + 32 * j, k0);
+      uint32_t it = 0;
+      long long w_empty = 0;
+      const long long t_start = clock64();
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m0, n0, z, kb_begin, nkb;
+        decode(tile, m0, n0, z, kb_begin, nkb);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          w_empty += mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], tx_bytes);
+          const int k0 = (kb_begin + kb) * BK;
+          if (!A_MN) {
+            tma_load_2d(sA_hi(s), &tmA, &full[s], k0, m0);          // box [128 rows][32 k]
+          } else {
+            for (int i = 0; i < BM / 32; ++i)                        // boxes [32 k][32 m]
+              tma_load_2d(sA_hi(s) + i * 4096, &tmA, &full[s], m0 + 32 * i, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sB_hi(s), &tmB, &full[s], k0, n0);           // box [n rows][32 k]
+            if (PASSES == 3 && !SPLIT_B) tma_load_2d(sB_lo(s), &tmBlo, &full[s], k0, n0);
+          } else {
+            const int nbox = args.b_tile_bytes / 4096;
+            for (int j = 0; j < nbox; ++j) {
+              tma_load_2d(sB_hi(s) + j * 4096, &tmB, &full[s], n0 + 32 * j, k0);
+              if (PASSES == 3 && !SPLIT_B)
+                tma_load_2d(sB_lo(s) + j * 4096, &tmBlo, &full[s], n0 + 32 * j, k0);
+            }
           }
         }
+      }
+      if (args.dbg) {
+        args.dbg[blockIdx.x * 8 + 0] = w_empty;
+        args.dbg[blockIdx.x * 8 + 1] = clock64() - t_start;
       }
     }
   } else if (warp == 1) {
@@ -275,138 +310,263 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
       const uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
       const uint32_t a_lt = A_MN ? 1u : 2u, b_lt = B_MN ? 1u : 2u;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(PASSES == 3 ? &split[s] : &full[s], ph);
+      uint32_t it = 0, tcount = 0;
+      long long w_acc = 0, w_full = 0;
+      const long long t_start = clock64();
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        int m0, n0, z, kb_begin, nkb;
+        decode(tile, m0, n0, z, kb_begin, nkb);
+        const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+        w_acc += mbar_wait(&acc_empty[ab], aph ^ 1);   // epilogue has drained this buffer
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(sA_hi(s)), a_lo = smem_u32(sA_lo(s));
-        const uint32_t b_hi = smem_u32(sB_hi(s)), b_lo = smem_u32(sB_lo(s));
+        const uint32_t tmem_d = tmem_base + ab * args.tmem_cols;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          w_full += mbar_wait(PASSES == 3 ? &split[s] : &full[s], ph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(sA_hi(s)), a_lo = smem_u32(sA_lo(s));
+          const uint32_t b_hi = smem_u32(sB_hi(s)), b_lo = smem_u32(sB_lo(s));
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {
-          const uint64_t da_hi = make_smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
-          const uint64_t db_hi = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
-          umma_tf32(tmem_base, da_hi, db_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
-          if (PASSES == 3) {
-            const uint64_t da_lo = make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
-            const uint64_t db_lo = make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
-            umma_tf32(tmem_base, da_lo, db_hi, idesc, 1u);
-            umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t da_hi = make_smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
+            const uint64_t db_hi = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
+            umma_tf32(tmem_d, da_hi, db_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+            if (PASSES == 3) {
+              const uint64_t da_lo = make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
+              const uint64_t db_lo = make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
+              umma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
+              umma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
+            }
           }
+          umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
         }
-        umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
+        if (nkb > 0) umma_commit(&acc_full[ab]);
+        else mbar_arrive(&acc_full[ab]);         // empty k range: epilogue stores zeros
       }
-      if (nkb > 0) umma_commit(accum);
+      if (args.dbg) {
+        args.dbg[blockIdx.x * 8 + 2] = w_acc;
+        args.dbg[blockIdx.x * 8 + 3] = w_full;
+        args.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
+      }
+    }
+  } else if (warp < kEpiWarp0) {
+    // ------------------------------------------------ hi/lo splitters (warps 2..9)
+    if (PASSES == 3) {
+      const int t = threadIdx.x - 64;   // 0 .. kSplitThreads - 1
+      const int b_chunks = SPLIT_B ? args.b_tile_bytes / 16 : 0;
+      uint32_t it = 0;
+      long long w_tma = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m0, n0, z, kb_begin, nkb;
+        decode(tile, m0, n0, z, kb_begin, nkb);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          w_tma += mbar_wait(&full[s], ph);
+          float4* __restrict__ hi = reinterpret_cast<float4*>(sA_hi(s));
+          float4* __restrict__ lo = reinterpret_cast<float4*>(sA_lo(s));
+          for (int pass = 0; pass < (SPLIT_B ? 2 : 1); ++pass) {
+            const int chunks = pass == 0 ? kATileBytes / 16 : b_chunks;
+            if (pass == 1) {
+              hi = reinterpret_cast<float4*>(sB_hi(s));
+              lo = reinterpret_cast<float4*>(sB_lo(s));
+            }
+            // 4 independent 16-byte loads in flight per thread, then convert + store
+            for (int c = t; c < chunks; c += 4 * kSplitThreads) {
+              float4 v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (c + u * kSplitThreads < chunks) v[u] = hi[c + u * kSplitThreads];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (c + u * kSplitThreads < chunks) {
+                  float4 h, l;
+                  h.x = tf32_rn(v[u].x);
+                  h.y = tf32_rn(v[u].y);
+                  h.z = tf32_rn(v[u].z);
+                  h.w = tf32_rn(v[u].w);
+                  l.x = v[u].x - h.x;
+                  l.y = v[u].y - h.y;
+                  l.z = v[u].z - h.z;
+                  l.w = v[u].w - h.w;
+                  hi[c + u * kSplitThreads] = h;
+                  lo[c + u * kSplitThreads] = l;
+                }
+              }
+            }
+          }
+          fence_proxy_async();       // generic-proxy writes -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split[s]);   // one arrival per splitter warp
+        }
+      }
+      if (args.dbg && t == 0) args.dbg[blockIdx.x * 8 + 5] = w_tma;
     }
   } else {
-    // ------------------------------------- splitters, then epilogue (warps 2..5)
-    const int t = threadIdx.x - 64;   // 0 .. 127
-    if (PASSES == 3) {
-      const int b_chunks = SPLIT_B ? args.b_tile_bytes / 16 : 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(&full[s], ph);
-        float4* hi = reinterpret_cast<float4*>(sA_hi(s));
-        float4* lo = reinterpret_cast<float4*>(sA_lo(s));
-        for (int pass = 0; pass < (SPLIT_B ? 2 : 1); ++pass) {
-          const int chunks = pass == 0 ? kATileBytes / 16 : b_chunks;
-          if (pass == 1) {
-            hi = reinterpret_cast<float4*>(sB_hi(s));
-            lo = reinterpret_cast<float4*>(sB_lo(s));
-          }
-          for (int c = t; c < chunks; c += 128) {
-            const float4 v = hi[c];
-            float4 h, l;
-            h.x = tf32_rn(v.x);
-            h.y = tf32_rn(v.y);
-            h.z = tf32_rn(v.z);
-            h.w = tf32_rn(v.w);
-            l.x = v.x - h.x;
-            l.y = v.y - h.y;
-            l.z = v.z - h.z;
-            l.w = v.w - h.w;
-            hi[c] = h;
-            lo[c] = l;
-          }
-        }
-        fence_proxy_async();       // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(&split[s]);
-      }
-    }
-    // epilogue: TMEM lane quarter is fixed by warp id % 4
-    if (nkb > 0) mbar_wait(accum, 0);   // an empty k range (split tail) stores zeros
-    tc_fence_after();
+    // ---------------------------------------------------- epilogue (warps 10..13)
+    // TMEM lane quarter is fixed by warp id % 4.  While these warps drain buffer
+    // `ab`, the MMA warp already fills the other buffer with the next tile.
     const int q = warp & 3;
-    float* C = args.C + static_cast<size_t>(blockIdx.z) * args.split_stride;
-    if (args.store_transposed) {
-      // lane = row: consecutive lanes hit consecutive addresses of C^T.
-      const int row = m0 + q * 32 + lane;
-      for (int c0 = 0; c0 < args.n_umma; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-        tmem_ld_wait();
+    float* tb = reinterpret_cast<float*>(epi_smem) + (warp - kEpiWarp0) * (32 * 37);
+    uint32_t tcount = 0;
+    long long w_accfull = 0;
+    const long long t_start = clock64();
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      int m0, n0, z, kb_begin, nkb;
+      decode(tile, m0, n0, z, kb_begin, nkb);
+      const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+      w_accfull += mbar_wait(&acc_full[ab], aph);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + ab * args.tmem_cols +
+                              (static_cast<uint32_t>(q * 32) << 16);
+      float* C = args.C + static_cast<size_t>(z) * args.split_stride;
+      if (args.store_transposed) {
+        // lane = row: consecutive lanes hit consecutive addresses of C^T.
+        const int row = m0 + q * 32 + lane;
+        for (int c0 = 0; c0 < args.n_umma; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_d + c0, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = n0 + c0 + j;
-          if (c0 + j >= args.n_umma || col >= args.GN || row >= args.GM) continue;
-          const float x = nkb > 0 ? __uint_as_float(v[j]) : 0.f;
-          C[static_cast<size_t>(col) * args.ldc + row] = x;
+          for (int j = 0; j < 32; ++j) {
+            const int col = n0 + c0 + j;
+            if (c0 + j >= args.n_umma || col >= args.GN || row >= args.GM) continue;
+            const float x = nkb > 0 ? __uint_as_float(v[j]) : 0.f;
+            C[static_cast<size_t>(col) * args.ldc + row] = x;
+          }
         }
-      }
-    } else {
-      // Row-major store: transpose each 32x32 block through shared memory (the
-      // pipeline stages are idle now) so that a warp writes 128 contiguous bytes
-      // of one row per instruction; bias / ReLU mask / column sums ride along.
-      float* tb = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
-      const int rows_here = min(32, args.GM - (m0 + q * 32));
-      for (int c0 = 0; c0 < args.n_umma; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-        tmem_ld_wait();
+      } else if (args.vec_ok) {
+        // Row-major store, vectorised: each 32x32 block goes through shared memory
+        // ([32][36] floats, 16-byte rows) so that one warp instruction stores
+        // 4 rows x 128 contiguous bytes (STG.128); bias / ReLU mask / column sums
+        // ride along.  8 STS.128 + 8 LDS.128 + 8 STG.128 per block.
+        float4* tb4 = reinterpret_cast<float4*>(tb);
+        const int rows_here = min(32, args.GM - (m0 + q * 32));
+        const int r4 = lane >> 3, c4 = lane & 7;
+        const bool masked = args.epi == EPI_MASK_POS && args.act == TFR_ACT_RELU;
+        const size_t rstep = static_cast<size_t>(4) * args.ldc;
+        const size_t row_off = static_cast<size_t>(m0 + q * 32 + r4) * args.ldc;
+        // ReLU mask source for one 32x32 block: 8 independent 16-byte loads.
+        auto load_keep = [&](int c0, float4 (&k)[8]) {
+          const int col = n0 + c0 + c4 * 4;
+          const bool ok = (c0 + c4 * 4 < args.n_umma) && col < args.GN;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) tb[lane * 33 + j] = nkb > 0 ? __uint_as_float(v[j]) : 0.f;
-        __syncwarp();
-        const int col = n0 + c0 + lane;
-        const bool col_ok = (c0 + lane < args.n_umma) && col < args.GN;
-        const float bv = (args.epi == EPI_BIAS_ACT && col_ok) ? __ldg(args.bias + col) : 0.f;
-        const size_t off0 = static_cast<size_t>(m0 + q * 32) * args.ldc + col;
-        // ReLU mask source: issue all 32 independent loads before any store (the
-        // stores may alias them as far as the compiler knows).
-        float keep[32];
-        if (args.epi == EPI_MASK_POS && args.act == TFR_ACT_RELU) {
+          for (int i = 0; i < 8; ++i)
+            k[i] = (ok && i * 4 + r4 < rows_here)
+                       ? __ldg(reinterpret_cast<const float4*>(args.aux + row_off + col + i * rstep))
+                       : make_float4(1.f, 1.f, 1.f, 1.f);
+        };
+        float4 keep[8], keep_next[8];
+        if (masked) load_keep(0, keep);
+        for (int c0 = 0; c0 < args.n_umma; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_d + c0, v);
+          // prefetch the next block's mask while this one is transposed and stored
+          if (masked && c0 + 32 < args.n_umma) load_keep(c0 + 32, keep_next);
+          const int col = n0 + c0 + c4 * 4;
+          const bool col_ok = (c0 + c4 * 4 < args.n_umma) && col < args.GN;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (args.epi == EPI_BIAS_ACT && col_ok)
+            bv = __ldg(reinterpret_cast<const float4*>(args.bias + col));
+          tmem_ld_wait();
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr)
-            keep[rr] = (col_ok && rr < rows_here)
-                           ? __ldg(args.aux + off0 + static_cast<size_t>(rr) * args.ldc)
-                           : 1.f;
+          for (int j = 0; j < 8; ++j) {
+            float4 t4;
+            t4.x = nkb > 0 ? __uint_as_float(v[4 * j + 0]) : 0.f;
+            t4.y = nkb > 0 ? __uint_as_float(v[4 * j + 1]) : 0.f;
+            t4.z = nkb > 0 ? __uint_as_float(v[4 * j + 2]) : 0.f;
+            t4.w = nkb > 0 ? __uint_as_float(v[4 * j + 3]) : 0.f;
+            tb4[lane * 9 + j] = t4;
+          }
+          __syncwarp();
+          const size_t off0 = row_off + col;
+          float4 xs[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) xs[i] = tb4[(i * 4 + r4) * 9 + c4];
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 x = xs[i];
+            if (args.epi == EPI_BIAS_ACT) {
+              x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+              if (args.act == TFR_ACT_RELU) {
+                x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f);
+                x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+              }
+            } else if (masked) {
+              if (!(keep[i].x > 0.f)) x.x = 0.f;
+              if (!(keep[i].y > 0.f)) x.y = 0.f;
+              if (!(keep[i].z > 0.f)) x.z = 0.f;
+              if (!(keep[i].w > 0.f)) x.w = 0.f;
+            }
+            if (col_ok && i * 4 + r4 < rows_here) {
+              *reinterpret_cast<float4*>(C + off0 + i * rstep) = x;
+              cs.x += x.x; cs.y += x.y; cs.z += x.z; cs.w += x.w;
+            }
+          }
+          if (args.colsum) {
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
+              cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
+              cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+            }
+            if (r4 == 0 && col_ok)
+              *reinterpret_cast<float4*>(
+                  args.colsum + static_cast<size_t>((m0 / BM) * 4 + q) * args.colsum_stride + col) = cs;
+          }
+          if (masked) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) keep[i] = keep_next[i];
+          }
+          __syncwarp();
         }
-        float csum = 0.f;
+      } else {
+        // Row-major store, scalar fallback (unaligned leading dimension / width).
+        const int rows_here = min(32, args.GM - (m0 + q * 32));
+        for (int c0 = 0; c0 < args.n_umma; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_d + c0, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-          if (rr < rows_here) {
-            float x = tb[rr * 33 + lane];
+          for (int j = 0; j < 32; ++j) tb[lane * 37 + j] = nkb > 0 ? __uint_as_float(v[j]) : 0.f;
+          __syncwarp();
+          const int col = n0 + c0 + lane;
+          const bool col_ok = (c0 + lane < args.n_umma) && col < args.GN;
+          const float bv = (args.epi == EPI_BIAS_ACT && col_ok) ? __ldg(args.bias + col) : 0.f;
+          const size_t off0 = static_cast<size_t>(m0 + q * 32) * args.ldc + col;
+          float csum = 0.f;
+          for (int rr = 0; rr < rows_here; ++rr) {
+            float x = tb[rr * 37 + lane];
             if (args.epi == EPI_BIAS_ACT) {
               x += bv;
               if (args.act == TFR_ACT_RELU) x = fmaxf(x, 0.f);
-            } else if (args.epi == EPI_MASK_POS && args.act == TFR_ACT_RELU) {
-              if (!(keep[rr] > 0.f)) x = 0.f;
+            } else if (args.epi == EPI_MASK_POS && args.act == TFR_ACT_RELU && col_ok) {
+              if (!(__ldg(args.aux + off0 + static_cast<size_t>(rr) * args.ldc) > 0.f)) x = 0.f;
             }
             if (col_ok) {
               C[off0 + static_cast<size_t>(rr) * args.ldc] = x;
               csum += x;
             }
           }
+          if (args.colsum && col_ok)
+            args.colsum[static_cast<size_t>((m0 / BM) * 4 + q) * args.colsum_stride + col] = csum;
+          __syncwarp();
         }
-        if (args.colsum && col_ok)
-          args.colsum[static_cast<size_t>(blockIdx.y * 4 + q) * args.colsum_stride + col] = csum;
-        __syncwarp();
       }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);   // 128 arrivals free the accumulator buffer
+    }
+    if (args.dbg && threadIdx.x == kEpiWarp0 * 32) {
+      args.dbg[blockIdx.x * 8 + 6] = w_accfull;
+      args.dbg[blockIdx.x * 8 + 7] = clock64() - t_start;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, args.tmem_cols);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * args.tmem_cols);
 }
 
 // ------------------------------------------------------------------ host -------
@@ -454,6 +614,8 @@ static int encode_2d(CUtensorMap* tm, const float* ptr, uint64_t inner, uint64_t
 }
 
 bool shape_supported(int lda, int ldb) { return lda % 4 == 0 && ldb % 4 == 0; }
+
+static long long* g_dbg = nullptr;   // set by tfr_tc_set_debug (profiling aid)
 
 template <bool A_MN, bool B_MN, int PASSES, bool SPLIT_B>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo,
@@ -518,7 +680,14 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   ka.split_stride = g.split_stride;
   uint32_t cols = 32;
   while ((int)cols < n_umma) cols <<= 1;
-  ka.tmem_cols = cols;
+  ka.tmem_cols = cols;     // per accumulator buffer; the kernel allocates two
+  ka.dbg = g_dbg;
+  ka.vec_ok = (g.ldc % 4 == 0) && (g.GN % 4 == 0) && (g.split_stride % 4 == 0) &&
+              ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
+              (!g.aux || (reinterpret_cast<uintptr_t>(g.aux) & 15) == 0) &&
+              (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) &&
+              (!g.colsum || ((reinterpret_cast<uintptr_t>(g.colsum) & 15) == 0 &&
+                             g.colsum_stride % 4 == 0));
   ka.colsum = g.colsum;
   ka.colsum_stride = g.colsum_stride;
   TFR_REQUIRE(!g.colsum || (!g.store_transposed && splits == 1),
@@ -526,8 +695,19 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   TFR_REQUIRE(g.epi != EPI_BIAS_ACT || g.bias, "tc gemm: bias required");
   TFR_REQUIRE(g.epi != EPI_MASK_POS || g.aux, "tc gemm: aux required");
 
-  dim3 grid(n_tiles, (g.GM + BM - 1) / BM, splits);
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  ka.m_tiles = (g.GM + BM - 1) / BM;
+  ka.n_tiles = n_tiles;
+  ka.splits = splits;
+  const int total_tiles = ka.m_tiles * ka.n_tiles * splits;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    TFR_CUDA_OK(cudaGetDevice(&dev));
+    TFR_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
+  const size_t smem = (size_t)stages * stage_bytes + kEpiSmemBytes + 1024 /*align*/ +
+                      256 /*barriers*/;
 
 #define TFR_TC_LAUNCH(AMN, BMN, P, SB) \
   return launch<AMN, BMN, P, SB>(tmA, tmB, tmBlo, ka, grid, smem, st)
@@ -554,6 +734,14 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
 
 }  // namespace tc
 }  // namespace tfr
+
+// Profiling aid: [num_ctas][8] int64 wait-cycle counters written by each launch
+// {producer wait-empty, producer total, mma wait-acc-empty, mma wait-operands, mma total,
+//  splitter wait-tma, epilogue wait-acc-full, epilogue total}.  NULL disables.
+extern "C" int tfr_tc_set_debug(long long* buf) {
+  tfr::tc::g_dbg = buf;
+  return 0;
+}
 
 // Test / parity entry: raw GEMM through the tensor-core engine.
 extern "C" int tfr_tc_gemm(const float* A, int lda, const float* B, int ldb, const float* B_lo,
