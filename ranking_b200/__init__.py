@@ -12,6 +12,8 @@ from ranking_b200 import keras
 from ranking_b200 import losses_impl
 from ranking_b200 import metrics_impl
 from ranking_b200 import utils
+from ranking_b200 import dp
+from ranking_b200 import model
 from ranking_b200 import train
 
 __version__ = '0.1.0'

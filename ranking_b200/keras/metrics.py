@@ -7,7 +7,8 @@ keras/metrics.py:156-193): state = (sum v*w, sum w) kept on the device;
 evaluated with ONE kernel launch through `MetricGroup`.
 """
 import torch
-import torch.distributed as dist
+
+from ranking_b200 import dp
 
 from ranking_b200 import metrics_impl
 from ranking_b200.keras import utils
@@ -49,8 +50,8 @@ class _RankingMetric(object):
 
   def all_reduce(self, group=None):
     """Data-parallel evaluation: SUM the (sum v*w, sum w) pair across ranks."""
-    if self._state is not None and dist.is_available() and dist.is_initialized():
-      dist.all_reduce(self._state, op=dist.ReduceOp.SUM, group=group)
+    if self._state is not None:
+      dp.all_reduce_sum_(self._state, group)
 
   def result(self):
     if self._state is None:
@@ -163,8 +164,8 @@ class MetricGroup(object):
     self._state = upd if self._state is None else self._state + upd
 
   def all_reduce(self, group=None):
-    if self._state is not None and dist.is_available() and dist.is_initialized():
-      dist.all_reduce(self._state, op=dist.ReduceOp.SUM, group=group)
+    if self._state is not None:
+      dp.all_reduce_sum_(self._state, group)
 
   def result(self):
     t = len(self.topns)

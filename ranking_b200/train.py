@@ -15,9 +15,9 @@ flat fp32 gradient and a 1/world_size factor inside the optimizer kernel.
 import ctypes
 
 import torch
-import torch.distributed as dist
 
 from ranking_b200 import _C
+from ranking_b200 import dp
 
 _OPT = {'sgd': 0, 'adagrad': 1}
 
@@ -41,8 +41,7 @@ class RankingTrainer(object):
     self.accum = torch.full_like(tower.flat.data, initial_accumulator_value)
     self.grads = torch.zeros_like(tower.flat.data)
     self.group = process_group
-    self.world = dist.get_world_size(process_group) if (
-        dist.is_available() and dist.is_initialized()) else 1
+    self.world = dp.world_size(process_group)
     self._shape = None
     self.launches_per_step = None
 
@@ -80,12 +79,11 @@ class RankingTrainer(object):
     _C.check(_C.lib.tfr_mlp_bwd(_C.ptr(x), m, cfg, _C.ptr(t.flat.data),
                                 _C.ptr(self.dscores), _C.ptr(m8), _C.ptr(self.ws),
                                 _C.ptr(self.grads), t._precision, st))
-    if self.world > 1:
-      dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
+    dp.all_reduce_sum_(self.grads, self.group)   # the one collective of the step
     _C.check(_C.lib.tfr_optimizer_step(
         _C.ptr(t.flat.data), _C.ptr(self.grads), _C.ptr(self.accum),
-        self.grads.numel(), self.opt_kind, self.lr, self.eps, 1.0 / self.world,
-        st))
+        self.grads.numel(), self.opt_kind, self.lr, self.eps,
+        dp.replica_grad_scale(self.group), st))
     return self.total2[0]
 
   # -- evaluation --------------------------------------------------------------

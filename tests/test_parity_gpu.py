@@ -391,6 +391,63 @@ def test_fused_train_step_matches_oracle(oracle_api, loss_key, kw, precision):
   assert _rel_err(tower.flat, p_ref) <= 1e-5
 
 
+def test_groupwise_scoring_matches_oracle(oracle_api):
+  """BASELINE config 4 structure (groupwise group_size=2 + softmax), small sizes:
+  logits, loss and parameter gradients vs the oracle restatement of
+  model.py:164-421 (no-shuffle permutation)."""
+  import ranking_b200 as tfr
+  b, n, d, gs = 6, 9, 8, 2
+  g = torch.Generator().manual_seed(4)
+  x = torch.randn(b, n, d, generator=g)
+  labels = torch.randint(0, 3, (b, n), generator=g).float()
+  labels[0, 5:] = -1.
+  labels[3, 1:] = -1.       # a single valid item: windows wrap onto itself
+  valid = labels >= 0
+  tower, params = _tower_and_params(tfr, gs * d, [16, 8], gs, seed=3)
+  model = tfr.model.GroupwiseRankingModel(tfr.model.TowerGroupScoreFn(tower), gs)
+  logits = model.compute_logits(x.cuda(), valid.cuda())
+  loss = tfr.keras.losses.SoftmaxLoss()(labels.cuda(), logits)
+  loss.backward()
+
+  def score_fn(gf):
+    bg = gf.shape[0]
+    return oracle_api.scorer.tower_forward(gf.reshape(bg, gs * d), params,
+                                           activation='relu')
+  ref_logits = oracle_api.scorer.groupwise_logits(x.double(), valid, gs, score_fn)
+  ref_loss = oracle_api.keras_losses.SoftmaxLoss()(labels.double(), ref_logits)
+  ref_loss.backward()
+  assert _rel_err(logits, ref_logits) <= RTOL
+  assert abs(float(loss.detach()) - float(ref_loss.detach())) <= RTOL
+  assert _rel_err(tower.flat.grad, _flat_grad(params)) <= 5e-5
+  # reference golden (model_test.py:223-277): dummy score fn = 1 + feature + #rows
+  dummy = lambda gf: (1. + gf).reshape(-1, 2) + float(gf.shape[0])
+  m2 = tfr.model.GroupwiseRankingModel(dummy, 2)
+  out = m2.compute_logits(torch.tensor([[[1.], [2.], [3.]]]).cuda(),
+                          torch.tensor([[True, True, False]]).cuda())
+  assert out.tolist() == [[5., 6., 0.]]
+  out = m2.compute_logits(torch.tensor([[[1.], [2.], [0.]]]).cuda(),
+                          torch.tensor([[True, True, True]]).cuda(), num_shuffles=2)
+  assert out.tolist() == [[8., 9., 7.]]
+
+
+def test_two_gpu_data_parallel_step_equals_single_gpu():
+  """8-list batch on 1 GPU vs 2 ranks x 4 lists over NCCL: same parameters after
+  one step (needs 2 GPUs; skipped on the 1-GPU test box)."""
+  if torch.cuda.device_count() < 2:
+    pytest.skip('needs 2 GPUs')
+  import subprocess
+  import sys
+  import os
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  out = subprocess.run(
+      [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+       '--nproc-per-node', '2', '--master-addr', '127.0.0.1', '--master-port',
+       '29611', os.path.join(root, 'tools', 'dp_equivalence.py')],
+      capture_output=True, text=True, timeout=300)
+  assert out.returncode == 0, out.stdout + out.stderr
+  assert 'DP_EQUIVALENCE_OK' in out.stdout, out.stdout + out.stderr
+
+
 # --------------------- size-independent properties at full size --------------
 def test_full_size_properties_config2():
   """BASELINE config 2 (B=1024, N=200): properties that need no oracle."""
