@@ -76,42 +76,59 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-  """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+  """Streams `nvidia-smi -lms` clocks / throttle reasons for the whole run and
+  keeps the samples that fall inside marked (timed) windows."""
+
+  Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+  NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
   def __init__(self, index):
     super().__init__(daemon=True)
     self.index = index
-    self.stop_flag = threading.Event()
-    self.samples = []
+    self.samples = []     # (t, sm_mhz, reasons)
     self.max_mhz = None
-    self.reasons = set()
+    self.windows = []
+    self.proc = None
 
   def run(self):
-    q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
-    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-             'sw_power_cap']
-    while not self.stop_flag.is_set():
-      try:
-        out = subprocess.run(
-            ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-             '--format=csv,noheader,nounits'], capture_output=True, text=True,
-            timeout=5).stdout.strip().split(',')
-        self.samples.append(float(out[0]))
-        self.max_mhz = float(out[1])
-        for nm, v in zip(names, out[2:]):
-          if v.strip().lower().startswith('active'):
-            self.reasons.add(nm)
-      except Exception:   # nvidia-smi missing / parse error: report nothing
-        pass
-      self.stop_flag.wait(0.1)
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+           '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE,
+          stderr=subprocess.DEVNULL, text=True)
+      for line in self.proc.stdout:
+        out = line.strip().split(',')
+        try:
+          mhz = float(out[0])
+          self.max_mhz = float(out[1])
+        except (ValueError, IndexError):
+          continue
+        reasons = {nm for nm, v in zip(self.NAMES, out[2:])
+                   if v.strip().lower().startswith('active')}
+        self.samples.append((time.perf_counter(), mhz, reasons))
+    except Exception:   # nvidia-smi missing: report nothing
+      pass
+
+  def stop(self):
+    if self.proc is not None:
+      self.proc.terminate()
+
+  def mark(self, t0, t1):
+    self.windows.append((t0, t1))
 
   def summary(self):
-    s = sorted(self.samples)
-    return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz,
-            'reasons': sorted(self.reasons), 'samples': len(s)}
+    inside = [s for s in self.samples
+              if any(t0 - 0.02 <= s[0] <= t1 + 0.02 for t0, t1 in self.windows)]
+    use = inside if inside else self.samples
+    mhz = sorted(s[1] for s in use)
+    reasons = set()
+    for s in use:
+      reasons |= s[2]
+    return {'sm_mhz': mhz[len(mhz) // 2] if mhz else None, 'sm_max_mhz': self.max_mhz,
+            'reasons': sorted(reasons), 'samples_in_timed_regions': len(inside),
+            'samples_total': len(self.samples)}
 
 
 # ------------------------------------------------------------------------------
@@ -234,7 +251,9 @@ def run_gpu(args):
   sampler = ClockSampler(local_rank)
   if rank == 0:
     sampler.start()
+    time.sleep(0.3)      # let the sampling stream start
   launches0 = _C.lib.tfr_launch_count()
+  t_val0 = time.perf_counter()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   ev0.record(stream)
   for i in range(args.steps):
@@ -243,8 +262,7 @@ def run_gpu(args):
   sync_all()
   launches = _C.lib.tfr_launch_count() - launches0
   ms_total = ev0.elapsed_time(ev1)
-  if rank == 0:
-    sampler.stop_flag.set()
+  sampler.mark(t_val0, time.perf_counter())
   t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -267,6 +285,9 @@ def run_gpu(args):
   e1.record(stream)
   sync_all()
   wall = time.perf_counter() - t0
+  sampler.mark(t0, time.perf_counter())
+  if rank == 0:
+    sampler.stop()
   e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
   t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
   if world > 1:

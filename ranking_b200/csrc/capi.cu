@@ -58,8 +58,21 @@ int make_mlp_plan(const tfr_mlp_cfg* cfg, int M, MlpPlan* p) {
     p->dz_off[i] = w;
     w += align_up((size_t)M * max_hidden, 64);
   }
-  p->rows_per_split = 2048;
-  p->splits = M > 0 ? (M + p->rows_per_split - 1) / p->rows_per_split : 1;
+  // Row splits of the dW GEMMs / bias partials: about one per SM, so that the
+  // persistent GEMM's tile list (m_tiles x splits) divides evenly over the SMs.
+  {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess ||
+          cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+          num_sms <= 0)
+        num_sms = 148;   // B200 (also the answer on a CPU-only build box)
+    }
+    const int per = (M + num_sms - 1) / num_sms;
+    p->rows_per_split = per < 256 ? 256 : ((per + 127) / 128) * 128;
+    p->splits = M > 0 ? (M + p->rows_per_split - 1) / p->rows_per_split : 1;
+  }
   p->partial_stride = align_up(max_wb, 64);
   p->partial_off = w;
   w += (size_t)p->splits * p->partial_stride;
@@ -71,7 +84,7 @@ int make_mlp_plan(const tfr_mlp_cfg* cfg, int M, MlpPlan* p) {
   p->tile_stride = align_up((size_t)max_hidden, 64);
   p->tile_off = w;
   w += (size_t)p->tile_slots * p->tile_stride;
-  p->out_rows = 256;
+  p->out_rows = 64;
   p->out_slots = (M + p->out_rows - 1) / p->out_rows;
   p->oslot_stride = align_up((size_t)p->dims[L] * (p->dims[L + 1] + 1) + p->dims[L + 1], 64);
   p->oslot_off = w;

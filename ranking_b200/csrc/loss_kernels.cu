@@ -372,13 +372,20 @@ sorted_ranks_kernel(const float* __restrict__ scores, const float* __restrict__ 
 // ---------------------------------------------------------------------------
 // K2  ApproxNDCG / ApproxMRR
 // ---------------------------------------------------------------------------
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Each unordered pair {a < b} is evaluated ONCE (sigmoid is antisymmetric about 1/2,
 // sigmoid' is even): the warp that owns row a adds the (a, b) term to its row
 // accumulator and the mirrored term to a per-lane register accumulator of column b
 // (lane l always sees the columns l + 32 t).  T = ceil(N / 32) column registers;
 // T == 0 selects the generic both-ends loop for N > 1024.
 template <int MODE, int T>
-__global__ void __launch_bounds__(kLossThreads)
+__global__ void __launch_bounds__(kLossThreads, T <= 8 ? 7 : 2)   // 7 CTAs/SM: B=1024 in one wave
 approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
                    const float* __restrict__ item_w, int w_per_item,
                    const uint8_t* __restrict__ mask, int N, float temperature,
@@ -425,24 +432,30 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
   // [nwarps][N] cross-warp column partials (T > 0), placed after the list view
   float* colpart = reinterpret_cast<float*>(smem_raw + ((list_smem_bytes(N) + 15) & ~(size_t)15));
   if (T > 0) {
-    float col[T > 0 ? T : 1];
+    // Column operands live in registers for the whole pass: zc[t] = z'[lane + 32 t]
+    // with z' = z * log2(e), so that sigmoid(d) = 1 / (1 + 2^-d') needs one ex2.
+    float col[T > 0 ? T : 1], zc[T > 0 ? T : 1];
 #pragma unroll
-    for (int t = 0; t < T; ++t) col[t] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int j = lane + 32 * t;
+      col[t] = 0.f;
+      zc[t] = j < N ? v.z[j] * kLog2e : 0.f;
+    }
     for (int i = warp; i < N; i += nwarps) {
-      const float zi = v.z[i];
+      const float zi = v.z[i] * kLog2e;
       float acc = 0.f;
       const int t0 = i >> 5;
 #pragma unroll
       for (int t = 0; t < T; ++t) {
+        if (t < t0) continue;                       // warp-uniform: block left of the diagonal
         const int j = lane + 32 * t;
-        if (t >= t0 && j > i && j < N) {
-          const float d = v.z[j] - zi;
-          const float e = __expf(-fabsf(d));
-          const float rc = __frcp_rn(1.f + e);
-          const float big = rc, small = e * rc;    // sigmoid(|d|), sigmoid(-|d|)
-          acc += d >= 0.f ? big : small;            // sigmoid(z_j - z_i) -> r_i
-          col[t] += d >= 0.f ? small : big;         // sigmoid(z_i - z_j) -> r_j
-        }
+        const bool on = (t > t0 || j > i) && j < N;
+        const float d = zc[t] - zi;
+        const float e = exp2f_approx(-fabsf(d));
+        const float rc = __frcp_rn(1.f + e);
+        const float big = rc, small = e * rc;       // sigmoid(|d|), sigmoid(-|d|)
+        acc += on ? (d >= 0.f ? big : small) : 0.f;    // sigmoid(z_j - z_i) -> r_i
+        col[t] += on ? (d >= 0.f ? small : big) : 0.f; // sigmoid(z_i - z_j) -> r_j
       }
       acc = warp_sum(acc);
       if (lane == 0) r[i] = acc;
@@ -514,23 +527,28 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
     const float gs = grad_scale / temperature * (scale_by_weight ? list_w : 1.f);
     if (T > 0) {
       float* gacc = reinterpret_cast<float*>(v.l);   // raw labels are no longer needed
-      float col[T > 0 ? T : 1];
+      float col[T > 0 ? T : 1], zc[T > 0 ? T : 1], cc[T > 0 ? T : 1];
 #pragma unroll
-      for (int t = 0; t < T; ++t) col[t] = 0.f;
+      for (int t = 0; t < T; ++t) {
+        const int j = lane + 32 * t;
+        col[t] = 0.f;
+        zc[t] = j < N ? v.z[j] * kLog2e : 0.f;
+        cc[t] = j < N ? c[j] : 0.f;
+      }
       for (int k = warp; k < N; k += nwarps) {
-        const float zk = v.z[k], ck = c[k];
+        const float zk = v.z[k] * kLog2e, ck = c[k];
         float acc = 0.f;
         const int t0 = k >> 5;
 #pragma unroll
         for (int t = 0; t < T; ++t) {
+          if (t < t0) continue;
           const int i = lane + 32 * t;
-          if (t >= t0 && i > k && i < N) {
-            const float e = __expf(-fabsf(zk - v.z[i]));
-            const float rc = __frcp_rn(1.f + e);
-            const float term = (c[i] - ck) * (e * rc * rc);
-            acc += term;        // -> grad_k
-            col[t] -= term;     // -> grad_i (antisymmetric)
-          }
+          const bool on = (t > t0 || i > k) && i < N;
+          const float e = exp2f_approx(-fabsf(zk - zc[t]));
+          const float rc = __frcp_rn(1.f + e);
+          const float term = on ? (cc[t] - ck) * (e * rc * rc) : 0.f;
+          acc += term;        // -> grad_k
+          col[t] -= term;     // -> grad_i (antisymmetric)
         }
         acc = warp_sum(acc);
         if (lane == 0) gacc[k] = acc;

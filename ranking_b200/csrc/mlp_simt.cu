@@ -122,16 +122,23 @@ __global__ void __launch_bounds__(256)
 out_layer_fwd_kernel(const float* __restrict__ H, int M, int K, int O,
                      const float* __restrict__ W, const float* __restrict__ bias,
                      const uint8_t* __restrict__ mask, float* __restrict__ scores) {
+  // one warp per 4 consecutive rows: 4 independent row loads in flight per lane
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const float* h = H + (size_t)row * K;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 4;
+  if (row0 >= M) return;
   for (int o = 0; o < O; ++o) {
-    float acc = 0.f;
-    for (int k = lane; k < K; k += 32) acc = fmaf(h[k], W[(size_t)k * O + o], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      float v = acc + bias[o];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < K; k += 32) {
+      const float w = W[(size_t)k * O + o];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        if (row0 + r < M) acc[r] = fmaf(H[(size_t)(row0 + r) * K + k], w, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = warp_sum(acc[r]);
+    if (lane < 4 && row0 + lane < M) {
+      const int row = row0 + lane;
+      float v = (lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3]) + bias[o];
       if (mask && O == 1 && !mask[row]) v = kLogEpsilon;
       scores[(size_t)row * O + o] = v;
     }
@@ -206,6 +213,7 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, size_t str
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float acc = 0.f;
+#pragma unroll 8
   for (int z = 0; z < splits; ++z) acc += partial[(size_t)z * stride + i];
   out[i] = acc;
 }
@@ -230,6 +238,7 @@ out_layer_bwd2_kernel(const float* __restrict__ H, int M, int K, int O,
     dw[o] = 0.f;
     db[o] = 0.f;
   }
+#pragma unroll 4
   for (int m = mbeg + rl; m < mend; m += RL) {
     const bool live = !(mask && O == 1 && !mask[m]);
     float ds[kMaxOut];
@@ -278,6 +287,7 @@ regroup_sum_kernel(const float* __restrict__ src, int slots_in, size_t src_strid
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float acc = 0.f;
+#pragma unroll 8
   for (int g = 0; g < group; ++g) {
     const int s = z * group + g;
     if (s < slots_in) acc += src[(size_t)s * src_stride + src_off + i];
@@ -315,7 +325,7 @@ int mlp_regroup_sum(const float* src, int slots_in, size_t src_stride, size_t sr
 
 int mlp_out_layer_fwd(const float* H, int M, int K, int O, const float* W, const float* bias,
                       const uint8_t* mask, float* scores, cudaStream_t st) {
-  const int rows_per_block = 8;
+  const int rows_per_block = 32;
   out_layer_fwd_kernel<<<(M + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(
       H, M, K, O, W, bias, mask, scores);
   TFR_LAUNCH_OK();
@@ -365,11 +375,8 @@ int mlp_simt_fwd(const float* X, int M, const MlpPlan& p, const float* params,
     in = g.C;
   }
   const int K = p.dims[L], O = p.dims[L + 1];
-  const int rows_per_block = 8;
-  out_layer_fwd_kernel<<<(M + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(
-      in, M, K, O, params + p.w_off[L], params + p.b_off[L], mask, scores);
-  TFR_LAUNCH_OK();
-  return TFR_OK;
+  return mlp_out_layer_fwd(in, M, K, O, params + p.w_off[L], params + p.b_off[L], mask, scores,
+                           st);
 }
 
 int mlp_simt_bwd(const float* X, int M, const MlpPlan& p, const float* params,

@@ -17,6 +17,8 @@
 // tile i+1 and the prologue (barrier init, TMEM allocation) is paid once per SM.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_gemm.cuh"
 
@@ -174,6 +176,9 @@ struct KernelArgs {
   int ldc;
   int GM, GN, GK;
   int n_umma;          // UMMA N of one tile (multiple of 16, <= 256)
+  int bk;              // k extent of one pipeline stage: 32, or 16 when both operands
+                       //   are MN-major (smaller stages -> deeper ring for the dW GEMMs)
+  int a_tile_bytes;    // bytes of one A stage tile (hi part) = 128 * bk * 4
   int b_tile_bytes;    // bytes of one B stage tile (hi part)
   int stages;
   int epi, act, store_transposed;
@@ -200,7 +205,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int kACopies = PASSES == 3 ? 2 : 1;
   constexpr int kBCopies = PASSES == 3 ? 2 : 1;
-  const int a_bytes = kATileBytes * kACopies;
+  const int a_bytes = args.a_tile_bytes * kACopies;
   const int stage_bytes = a_bytes + args.b_tile_bytes * kBCopies;
   const int S = args.stages;
   unsigned char* epi_smem = smem + static_cast<size_t>(S) * stage_bytes;   // 4 x [32][33] floats
@@ -213,7 +218,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb_total = (args.GK + BK - 1) / BK;
+  const int bk = args.bk;
+  const int box_bytes = bk * 128;            // one MN-major TMA box: [bk rows][128 B]
+  const int nkb_total = (args.GK + bk - 1) / bk;
   const int tiles_mn = args.m_tiles * args.n_tiles;
   const int total_tiles = tiles_mn * args.splits;
 
@@ -242,7 +249,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   auto sA_hi = [&](int s) { return smem + static_cast<size_t>(s) * stage_bytes; };
-  auto sA_lo = [&](int s) { return sA_hi(s) + kATileBytes; };
+  auto sA_lo = [&](int s) { return sA_hi(s) + args.a_tile_bytes; };
   auto sB_hi = [&](int s) { return sA_hi(s) + a_bytes; };
   auto sB_lo = [&](int s) { return sB_hi(s) + args.b_tile_bytes; };
   // tile -> (split z, m tile, n tile): consecutive CTAs work on neighbouring rows.
@@ -260,7 +267,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------- TMA producer ----
     if (lane == 0) {
       const uint32_t tx_bytes =
-          kATileBytes + args.b_tile_bytes * ((PASSES == 3 && !SPLIT_B) ? 2 : 1);
+          args.a_tile_bytes + args.b_tile_bytes * ((PASSES == 3 && !SPLIT_B) ? 2 : 1);
       uint32_t it = 0;
       long long w_empty = 0;
       const long long t_start = clock64();
@@ -272,22 +279,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t ph = (it / S) & 1;
           w_empty += mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], tx_bytes);
-          const int k0 = (kb_begin + kb) * BK;
+          const int k0 = (kb_begin + kb) * bk;
           if (!A_MN) {
             tma_load_2d(sA_hi(s), &tmA, &full[s], k0, m0);          // box [128 rows][32 k]
           } else {
             for (int i = 0; i < BM / 32; ++i)                        // boxes [32 k][32 m]
-              tma_load_2d(sA_hi(s) + i * 4096, &tmA, &full[s], m0 + 32 * i, k0);
+              tma_load_2d(sA_hi(s) + i * box_bytes, &tmA, &full[s], m0 + 32 * i, k0);
           }
           if (!B_MN) {
             tma_load_2d(sB_hi(s), &tmB, &full[s], k0, n0);           // box [n rows][32 k]
             if (PASSES == 3 && !SPLIT_B) tma_load_2d(sB_lo(s), &tmBlo, &full[s], k0, n0);
           } else {
-            const int nbox = args.b_tile_bytes / 4096;
+            const int nbox = args.b_tile_bytes / box_bytes;
             for (int j = 0; j < nbox; ++j) {
-              tma_load_2d(sB_hi(s) + j * 4096, &tmB, &full[s], n0 + 32 * j, k0);
+              tma_load_2d(sB_hi(s) + j * box_bytes, &tmB, &full[s], n0 + 32 * j, k0);
               if (PASSES == 3 && !SPLIT_B)
-                tma_load_2d(sB_lo(s) + j * 4096, &tmBlo, &full[s], n0 + 32 * j, k0);
+                tma_load_2d(sB_lo(s) + j * box_bytes, &tmBlo, &full[s], n0 + 32 * j, k0);
             }
           }
         }
@@ -307,7 +314,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                              (static_cast<uint32_t>(BM >> 4) << 24);
       const uint32_t a_step = A_MN ? 1024u : 32u;   // bytes per UMMA K step (8 fp32)
       const uint32_t b_step = B_MN ? 1024u : 32u;
-      const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
+      const uint32_t a_lbo = A_MN ? (uint32_t)box_bytes : 16u;
+      const uint32_t b_lbo = B_MN ? (uint32_t)box_bytes : 16u;
+      const int ksteps = bk / 8;
       const uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
       const uint32_t a_lt = A_MN ? 1u : 2u, b_lt = B_MN ? 1u : 2u;
       uint32_t it = 0, tcount = 0;
@@ -327,8 +336,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t a_hi = smem_u32(sA_hi(s)), a_lo = smem_u32(sA_lo(s));
           const uint32_t b_hi = smem_u32(sB_hi(s)), b_lo = smem_u32(sB_lo(s));
-#pragma unroll
-          for (int ks = 0; ks < BK / 8; ++ks) {
+#pragma unroll 4
+          for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t da_hi = make_smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
             const uint64_t db_hi = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
             umma_tf32(tmem_d, da_hi, db_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
@@ -367,7 +376,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float4* __restrict__ hi = reinterpret_cast<float4*>(sA_hi(s));
           float4* __restrict__ lo = reinterpret_cast<float4*>(sA_lo(s));
           for (int pass = 0; pass < (SPLIT_B ? 2 : 1); ++pass) {
-            const int chunks = pass == 0 ? kATileBytes / 16 : b_chunks;
+            const int chunks = pass == 0 ? args.a_tile_bytes / 16 : b_chunks;
             if (pass == 1) {
               hi = reinterpret_cast<float4*>(sB_hi(s));
               lo = reinterpret_cast<float4*>(sB_lo(s));
@@ -639,16 +648,21 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   TFR_REQUIRE(!pre_split_b || (reinterpret_cast<uintptr_t>(g.B_lo) & 15) == 0, "tc gemm: B_lo alignment");
 
   // N tiling: one tile if it fits a single UMMA (N <= 256), else tiles of 256.
-  const int n_umma = g.GN <= 256 ? ((g.GN + 15) / 16) * 16 : 256;
+  static const int n_cap = getenv("TFR_TC_NCAP") ? atoi(getenv("TFR_TC_NCAP")) : 256;
+  const int n_umma = g.GN <= n_cap ? ((g.GN + 15) / 16) * 16 : n_cap;
   const int n_tiles = (g.GN + n_umma - 1) / n_umma;
-  const int b_rows = g.b_mn ? ((n_umma + 31) / 32) * 32 : n_umma;   // rows of 128 B in a B tile
-  const int b_tile_bytes = b_rows * 128;
+  // Stage depth in k: the 128 B swizzle pins K-major tiles to 32 fp32 of k; MN-major tiles
+  // may use 16 k-rows, which halves the stage and doubles the ring depth (the dW GEMMs
+  // stream both operands from HBM and are latency-bound with 2-3 stages).
+  const int bk = 32;   // (16-row MN-major stages were measured slower: more TMA boxes per byte)
+  const int a_tile_bytes = g.a_mn ? (BM / 32) * bk * 128 : kATileBytes;
+  const int b_tile_bytes = g.b_mn ? ((n_umma + 31) / 32) * bk * 128 : n_umma * 128;
   const int copies = g.passes == 3 ? 2 : 1;
-  const int stage_bytes = (kATileBytes + b_tile_bytes) * copies;
+  const int stage_bytes = (a_tile_bytes + b_tile_bytes) * copies;
   int stages = (int)(kSmemBudget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   TFR_REQUIRE(stages >= 1, "tc gemm: tile does not fit shared memory");
-  const int nkb_total = (g.GK + BK - 1) / BK;
+  const int nkb_total = (g.GK + bk - 1) / bk;
   int splits = g.splits < 1 ? 1 : g.splits;
   int kb_per_split = (nkb_total + splits - 1) / splits;
   // (a split whose k range is empty stores zeros, so any split count is legal)
@@ -656,15 +670,15 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   CUtensorMap tmA, tmB, tmBlo;
   int rc;
   if (!g.a_mn) rc = encode_2d(&tmA, g.A, (uint64_t)g.GK, (uint64_t)g.GM, (uint64_t)g.lda, BM, false);
-  else rc = encode_2d(&tmA, g.A, (uint64_t)g.GM, (uint64_t)g.GK, (uint64_t)g.lda, 32, true);
+  else rc = encode_2d(&tmA, g.A, (uint64_t)g.GM, (uint64_t)g.GK, (uint64_t)g.lda, (uint32_t)bk, true);
   if (rc) return rc;
   if (!g.b_mn) rc = encode_2d(&tmB, g.B, (uint64_t)g.GK, (uint64_t)g.GN, (uint64_t)g.ldb, (uint32_t)n_umma, false);
-  else rc = encode_2d(&tmB, g.B, (uint64_t)g.GN, (uint64_t)g.GK, (uint64_t)g.ldb, 32, true);
+  else rc = encode_2d(&tmB, g.B, (uint64_t)g.GN, (uint64_t)g.GK, (uint64_t)g.ldb, (uint32_t)bk, true);
   if (rc) return rc;
   tmBlo = tmB;
   if (pre_split_b) {
     if (!g.b_mn) rc = encode_2d(&tmBlo, g.B_lo, (uint64_t)g.GK, (uint64_t)g.GN, (uint64_t)g.ldb, (uint32_t)n_umma, false);
-    else rc = encode_2d(&tmBlo, g.B_lo, (uint64_t)g.GN, (uint64_t)g.GK, (uint64_t)g.ldb, 32, true);
+    else rc = encode_2d(&tmBlo, g.B_lo, (uint64_t)g.GN, (uint64_t)g.GK, (uint64_t)g.ldb, (uint32_t)bk, true);
     if (rc) return rc;
   }
 
@@ -673,6 +687,8 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   ka.GM = g.GM; ka.GN = g.GN; ka.GK = g.GK;
   ka.n_umma = n_umma;
   ka.b_tile_bytes = b_tile_bytes;
+  ka.bk = bk;
+  ka.a_tile_bytes = a_tile_bytes;
   ka.stages = stages;
   ka.epi = g.epi; ka.act = g.act; ka.store_transposed = g.store_transposed;
   ka.bias = g.bias; ka.aux = g.aux;
