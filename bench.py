@@ -247,11 +247,11 @@ def run_gpu(args):
   # ---- value: inputs resident, device-timed ----------------------------------
   for i in range(args.warmup):
     trainer.train_step(*resident[i % N_RESIDENT])
-  sync_all()
   sampler = ClockSampler(local_rank)
   if rank == 0:
     sampler.start()
-    time.sleep(0.3)      # let the sampling stream start
+    time.sleep(0.3)      # let the sampling stream start (before the barrier!)
+  sync_all()
   launches0 = _C.lib.tfr_launch_count()
   t_val0 = time.perf_counter()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -80,11 +80,13 @@ int make_mlp_plan(const tfr_mlp_cfg* cfg, int M, MlpPlan* p) {
   w += align_up(p->n_params, 64);
   p->wlo_off = w;
   w += align_up(p->n_params, 64);
-  p->tile_slots = 4 * ((M + 127) / 128);
+  p->tile_slots = 4 * 1024;   // upper bound: 4 quarters x persistent CTAs (<= SM count)
   p->tile_stride = align_up((size_t)max_hidden, 64);
   p->tile_off = w;
   w += (size_t)p->tile_slots * p->tile_stride;
-  p->out_rows = 64;
+  // output-layer backward: about 4 blocks per SM, each owning one slot
+  p->out_rows = M > 0 ? ((M + 591) / 592 + 3) / 4 * 4 : 4;
+  if (p->out_rows < 16) p->out_rows = 16;
   p->out_slots = (M + p->out_rows - 1) / p->out_rows;
   p->oslot_stride = align_up((size_t)p->dims[L] * (p->dims[L + 1] + 1) + p->dims[L + 1], 64);
   p->oslot_off = w;

@@ -228,6 +228,19 @@ __device__ inline float load_list(const ListView& v, const float* scores,
   return zmin;
 }
 
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+__device__ __forceinline__ float exp2f_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float log2f_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---------------------------------------------------------------------------
 // K1
 // ---------------------------------------------------------------------------
@@ -235,17 +248,19 @@ template <int PHI>
 __device__ __forceinline__ void phi_eval(float x, float& f, float& df) {
   if (PHI == TFR_PHI_LOGISTIC) {
     // relu(-x) + log1p(exp(-|x|)); d/dx = -sigmoid(-x)   (losses_impl.py:936-940)
-    const float e = expf(-fabsf(x));
-    f = fmaxf(-x, 0.f) + log1pf(e);
-    df = -(x >= 0.f ? e / (1.f + e) : 1.f / (1.f + e));
+    // MUFU path: e = 2^(-|x| log2 e), log1p(e) = lg2(1 + e) ln 2, 1/(1+e) by rcp
+    const float e = exp2f_approx(-fabsf(x) * kLog2e);
+    const float rc = __frcp_rn(1.f + e);
+    f = fmaxf(-x, 0.f) + log2f_approx(1.f + e) * kLn2;
+    df = -(x >= 0.f ? e * rc : rc);
   } else if (PHI == TFR_PHI_HINGE) {
     const float m = 1.f - x;  // relu(1 - x)            (losses_impl.py:946-948)
     f = fmaxf(m, 0.f);
     df = m > 0.f ? -1.f : 0.f;
   } else {
     // sigmoid(-x); d/dx = -sigmoid(x) sigmoid(-x)       (losses_impl.py:954-958)
-    const float e = expf(-fabsf(x));
-    const float inv = 1.f / (1.f + e);
+    const float e = exp2f_approx(-fabsf(x) * kLog2e);
+    const float inv = __frcp_rn(1.f + e);
     f = x > 0.f ? e * inv : inv;
     df = -e * inv * inv;
   }
@@ -372,12 +387,6 @@ sorted_ranks_kernel(const float* __restrict__ scores, const float* __restrict__ 
 // ---------------------------------------------------------------------------
 // K2  ApproxNDCG / ApproxMRR
 // ---------------------------------------------------------------------------
-constexpr float kLog2e = 1.4426950408889634f;
-__device__ __forceinline__ float exp2f_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 // Each unordered pair {a < b} is evaluated ONCE (sigmoid is antisymmetric about 1/2,
 // sigmoid' is even): the warp that owns row a adds the (a, b) term to its row

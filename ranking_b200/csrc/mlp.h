@@ -57,6 +57,8 @@ int mlp_out_layer_bwd2(const float* H, int M, int K, int O, const float* W, cons
 int mlp_regroup_sum(const float* src, int slots_in, size_t src_stride, size_t src_off, int n,
                     int group, float* dst, int slots_out, size_t dst_stride, size_t dst_off,
                     cudaStream_t st);
+int mlp_reduce2(const float* srcA, int slotsA, size_t strideA, size_t nA, const float* srcB,
+                int slotsB, size_t strideB, size_t nB, float* out, cudaStream_t st);
 int mlp_colsum(const float* dZ, int M, int N, int rows_per, int splits, float* partial,
                size_t pstride, size_t col_offset, cudaStream_t st);
 int mlp_reduce_partials(const float* partial, int splits, size_t stride, size_t n, float* out,

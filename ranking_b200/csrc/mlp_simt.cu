@@ -295,7 +295,45 @@ regroup_sum_kernel(const float* __restrict__ src, int slots_in, size_t src_strid
   dst[(size_t)z * dst_stride + dst_off + i] = acc;
 }
 
+// out[i] = sum over slots of srcA (i < nA) or srcB (nA <= i < nA + nB): the weight
+// part of a layer gradient comes from the dW split partials, the bias part straight
+// from the per-CTA column sums.  16 outputs x 16 slot lanes per block, fixed order.
+__global__ void __launch_bounds__(256)
+reduce2_kernel(const float* __restrict__ srcA, int slotsA, size_t strideA, size_t nA,
+               const float* __restrict__ srcB, int slotsB, size_t strideB, size_t nB,
+               float* __restrict__ out) {
+  __shared__ float part[16][17];
+  const int o = threadIdx.x & 15, sl = threadIdx.x >> 4;
+  const size_t i = (size_t)blockIdx.x * 16 + o;
+  float acc = 0.f;
+  if (i < nA) {
+#pragma unroll 4
+    for (int z = sl; z < slotsA; z += 16) acc += srcA[(size_t)z * strideA + i];
+  } else if (i < nA + nB) {
+    const size_t j = i - nA;
+#pragma unroll 4
+    for (int z = sl; z < slotsB; z += 16) acc += srcB[(size_t)z * strideB + j];
+  }
+  part[sl][o] = acc;
+  __syncthreads();
+  if (sl == 0 && i < nA + nB) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 16; ++l) t += part[l][o];
+    out[i] = t;
+  }
+}
+
 // ------------------------------------------------------------- host side ---
+int mlp_reduce2(const float* srcA, int slotsA, size_t strideA, size_t nA, const float* srcB,
+                int slotsB, size_t strideB, size_t nB, float* out, cudaStream_t st) {
+  const size_t n = nA + nB;
+  reduce2_kernel<<<(unsigned)((n + 15) / 16), 256, 0, st>>>(srcA, slotsA, strideA, nA, srcB,
+                                                          slotsB, strideB, nB, out);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
 int mlp_out_layer_bwd2(const float* H, int M, int K, int O, const float* W, const float* dS,
                        const uint8_t* mask, int act, int rows_per, float* dH, float* slots,
                        size_t slot_stride, cudaStream_t st) {

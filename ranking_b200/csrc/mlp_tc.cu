@@ -83,7 +83,7 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
   const int L = p.n_dense - 1;
   float* partial = ws + p.partial_off;
   const size_t pstride = p.partial_stride;
-  const int rows_per = p.rows_per_split, splits = p.splits;
+  const int splits = p.splits;
   const float* whi = passes == 3 ? ws + p.whi_off : params;   // written by the forward
   const float* wlo = passes == 3 ? ws + p.wlo_off : nullptr;
   float* dz_cur = ws + p.dz_off[0];
@@ -100,18 +100,16 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
                             L > 0 ? p.activation : TFR_ACT_NONE, p.out_rows,
                             L > 0 ? dz_cur : nullptr, oslots, p.oslot_stride, st);
     if (rc) return rc;
-    const int group = rows_per / p.out_rows;
-    rc = mlp_regroup_sum(oslots, p.out_slots, p.oslot_stride, 0, K * O + O, group, partial,
-                         splits, pstride, 0, st);
+    // out-layer gradient: [K*O + O] summed over the block slots
+    rc = mlp_reduce2(oslots, p.out_slots, p.oslot_stride, (size_t)K * O + O, nullptr, 0, 0, 0,
+                     grads + p.w_off[L], st);
     if (rc) return rc;
-    rc = mlp_reduce_partials(partial, splits, pstride, (size_t)K * O + O, grads + p.w_off[L], st);
-    if (rc) return rc;
-    if (L > 0) {  // bias partials of hidden layer L-1 (its dZ was just produced)
-      rc = mlp_regroup_sum(oslots, p.out_slots, p.oslot_stride, (size_t)K * O + O, K, group,
-                           partial, splits, pstride, (size_t)p.dims[L - 1] * K, st);
-      if (rc) return rc;
-    }
   }
+  // Source of the bias partials of the layer being processed: per-slot column sums of
+  // its dZ, produced by whichever kernel wrote that dZ.
+  const float* bsrc = oslots + (size_t)p.dims[L] * p.dims[L + 1] + p.dims[L + 1];
+  int bslots = p.out_slots;
+  size_t bstride = p.oslot_stride;
   for (int d = L - 1; d >= 0; --d) {
     const int Kin = p.dims[d], Nout = p.dims[d + 1];
     const float* A = d > 0 ? ws + p.act_off[d - 1] : X;
@@ -142,9 +140,8 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
       rc = tc::gemm(g, st);
       if (rc) return rc;
     }
-    // (the bias region partial[z][Kin*Nout ..] was filled when dZ_d was produced)
-    rc = mlp_reduce_partials(partial, splits, pstride, (size_t)Kin * Nout + Nout,
-                             grads + p.w_off[d], st);
+    rc = mlp_reduce2(partial, splits, pstride, (size_t)Kin * Nout, bsrc, bslots, bstride,
+                     (size_t)Nout, grads + p.w_off[d], st);
     if (rc) return rc;
     if (d > 0) {
       tc::GemmDesc g{};
@@ -156,13 +153,13 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
       g.a_mn = 0; g.b_mn = 0; g.passes = passes; g.split_b = 0;
       g.epi = tc::EPI_MASK_POS; g.aux = ws + p.act_off[d - 1]; g.act = p.activation;
       g.splits = 1; g.split_stride = 0;
-      g.colsum = tiles; g.colsum_stride = (int)p.tile_stride;
+      int cslots = 0;
+      g.colsum = tiles; g.colsum_stride = (int)p.tile_stride; g.colsum_slots_out = &cslots;
       rc = tc::gemm(g, st);
       if (rc) return rc;
-      // column sums of dZ_{d-1}: 4 quarters x (rows_per / 128) tiles per split slot
-      rc = mlp_regroup_sum(tiles, p.tile_slots, p.tile_stride, 0, Kin, 4 * (rows_per / 128),
-                           partial, splits, pstride, (size_t)p.dims[d - 1] * Kin, st);
-      if (rc) return rc;
+      bsrc = tiles;            // column sums of dZ_{d-1}: one slot per CTA and quarter
+      bslots = cslots;
+      bstride = p.tile_stride;
       float* t = dz_cur; dz_cur = dz_nxt; dz_nxt = t;
     }
   }

@@ -188,8 +188,9 @@ struct KernelArgs {
   int m_tiles, n_tiles, splits;
   size_t split_stride;
   uint32_t tmem_cols;
-  float* colsum;       // optional [4 * m_tiles][colsum_stride]: column sums of the
-  int colsum_stride;   //   stored tile per 32-row quarter (bias gradients)
+  float* colsum;       // optional [4 * gridDim.x][colsum_stride]: column sums of everything
+  int colsum_stride;   //   this CTA stored, per 32-row quarter (bias gradients)
+  int colsum_cols;     // GN rounded up to 4 (0 when colsum is off): smem accumulators
   long long* dbg;      // optional [gridDim.x][8] wait-cycle counters per warp role
   int vec_ok;          // C / aux / bias / colsum allow 16-byte vector access
 };
@@ -209,7 +210,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stage_bytes = a_bytes + args.b_tile_bytes * kBCopies;
   const int S = args.stages;
   unsigned char* epi_smem = smem + static_cast<size_t>(S) * stage_bytes;   // 4 x [32][33] floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + kEpiSmemBytes);
+  float* cacc_base = reinterpret_cast<float*>(epi_smem + kEpiSmemBytes);   // [4][colsum_cols]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + kEpiSmemBytes +
+                                               4 * args.colsum_cols * sizeof(float));
   uint64_t* full = bars;                         // TMA landed
   uint64_t* split = bars + kMaxStages;           // hi/lo split done
   uint64_t* empty = bars + 2 * kMaxStages;       // MMAs that read the stage retired
@@ -418,6 +421,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // `ab`, the MMA warp already fills the other buffer with the next tile.
     const int q = warp & 3;
     float* tb = reinterpret_cast<float*>(epi_smem) + (warp - kEpiWarp0) * (32 * 37);
+    // per-warp running column sums over all tiles of this CTA (one slot per CTA and
+    // quarter instead of one per tile: 592 slots to reduce instead of 6400)
+    float* cacc = cacc_base + (warp - kEpiWarp0) * args.colsum_cols;
+    for (int c = lane; c < args.colsum_cols; c += 32) cacc[c] = 0.f;
+    __syncwarp();
     uint32_t tcount = 0;
     long long w_accfull = 0;
     const long long t_start = clock64();
@@ -522,9 +530,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
               cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
             }
-            if (r4 == 0 && col_ok)
-              *reinterpret_cast<float4*>(
-                  args.colsum + static_cast<size_t>((m0 / BM) * 4 + q) * args.colsum_stride + col) = cs;
+            if (r4 == 0 && col_ok) {   // lanes 0..7 own disjoint 4-column groups
+              float4* a4 = reinterpret_cast<float4*>(cacc + col);
+              float4 a = *a4;
+              a.x += cs.x; a.y += cs.y; a.z += cs.z; a.w += cs.w;
+              *a4 = a;
+            }
           }
           if (masked) {
 #pragma unroll
@@ -560,13 +571,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               csum += x;
             }
           }
-          if (args.colsum && col_ok)
-            args.colsum[static_cast<size_t>((m0 / BM) * 4 + q) * args.colsum_stride + col] = csum;
+          if (args.colsum && col_ok) cacc[col] += csum;
           __syncwarp();
         }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[ab]);   // 128 arrivals free the accumulator buffer
+    }
+    if (args.colsum) {
+      __syncwarp();
+      float* dst = args.colsum + static_cast<size_t>(blockIdx.x * 4 + q) * args.colsum_stride;
+      for (int c = lane; c < args.GN; c += 32) dst[c] = cacc[c];
     }
     if (args.dbg && threadIdx.x == kEpiWarp0 * 32) {
       args.dbg[blockIdx.x * 8 + 6] = w_accfull;
@@ -659,7 +674,9 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   const int b_tile_bytes = g.b_mn ? ((n_umma + 31) / 32) * bk * 128 : n_umma * 128;
   const int copies = g.passes == 3 ? 2 : 1;
   const int stage_bytes = (a_tile_bytes + b_tile_bytes) * copies;
-  int stages = (int)(kSmemBudget / stage_bytes);
+  const int colsum_cols = g.colsum ? ((g.GN + 3) / 4) * 4 : 0;
+  TFR_REQUIRE(colsum_cols <= 1024, "tc gemm: colsum output supports GN <= 1024");
+  int stages = (int)((kSmemBudget - 4 * colsum_cols * sizeof(float)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   TFR_REQUIRE(stages >= 1, "tc gemm: tile does not fit shared memory");
   const int nkb_total = (g.GK + bk - 1) / bk;
@@ -706,6 +723,7 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
                              g.colsum_stride % 4 == 0));
   ka.colsum = g.colsum;
   ka.colsum_stride = g.colsum_stride;
+  ka.colsum_cols = colsum_cols;
   TFR_REQUIRE(!g.colsum || (!g.store_transposed && splits == 1),
               "tc gemm: colsum output needs a row-major, unsplit store");
   TFR_REQUIRE(g.epi != EPI_BIAS_ACT || g.bias, "tc gemm: bias required");
@@ -722,8 +740,9 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
     TFR_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
-  const size_t smem = (size_t)stages * stage_bytes + kEpiSmemBytes + 1024 /*align*/ +
-                      256 /*barriers*/;
+  const size_t smem = (size_t)stages * stage_bytes + kEpiSmemBytes +
+                      4 * colsum_cols * sizeof(float) + 1024 /*align*/ + 256 /*barriers*/;
+  if (g.colsum_slots_out) *g.colsum_slots_out = 4 * (int)grid.x;
 
 #define TFR_TC_LAUNCH(AMN, BMN, P, SB) \
   return launch<AMN, BMN, P, SB>(tmA, tmB, tmBlo, ka, grid, smem, st)

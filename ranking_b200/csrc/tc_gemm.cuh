@@ -35,8 +35,9 @@ struct GemmDesc {
   int store_transposed;          // write element (r, c) to C[c * ldc + r]
   int splits;                    // split the GK loop over blockIdx.z; split z writes to
   size_t split_stride;           //   C + z * split_stride (floats); k range rounded to 32
-  float* colsum;                 // optional: per 32-row quarter column sums of the stored
-  int colsum_stride;             //   tile, slot (m_tile * 4 + quarter), row pitch in floats
+  float* colsum;                 // optional: column sums of everything each CTA stored, slot
+  int colsum_stride;             //   (cta * 4 + 32-row quarter), row pitch in floats;
+  int* colsum_slots_out;         //   receives the number of slots written (4 * CTAs)
 };
 
 // Returns a tfr_status.  Requirements (checked): lda/ldb multiples of 4 floats,
