@@ -307,6 +307,10 @@ def run_gpu(args):
     act_bytes = sum(dims[1:]) * 4 * N           # per list, one pass over H1..H3
     gemm_bytes_per_list = 2 * D * 4 * N + 4 * act_bytes + 3 * act_bytes
     hbm_achieved = gemm_bytes_per_list * B / (gemm_ms * 1e-3) / 1e9
+    traffic = None      # dram__bytes_read + write of these kernels, from the committed ncu capture
+    tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if os.path.exists(tpath) and args.precision == 'tf32x3':
+      traffic = json.load(open(tpath))
     loss_bytes = (12 * N + 16) * B
     line = {
         'metric': 'lists_per_sec', 'value': value, 'unit': 'lists/s',
@@ -323,7 +327,8 @@ def run_gpu(args):
             'bound': 'tensor', 'achieved': achieved, 'peak': peak,
             'unit': 'TFLOP/s', 'frac': achieved / peak,
             'peak_source': peaks['source'] + ' bf16 sustained',
-            'traffic': None,
+            'traffic': traffic['scorer_gemm_dram_bytes_per_step'] if traffic else None,
+            'traffic_source': traffic['source'] if traffic else None,
             'algorithmic_flops_per_step': step_fl * B,
             'kernel_ms_per_step': gemm_ms,
             'note': '3xTF32 issues 3 TF32 MMAs per algorithmic product, so the '
