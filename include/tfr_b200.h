@@ -200,9 +200,32 @@ typedef struct {
   int32_t n_dense;                        /* Dense layers incl. the output one */
   int32_t dims[TFR_MLP_MAX_LAYERS + 1];   /* dims[0] = D, dims[i] = units of Dense i */
   int32_t activation;                     /* tfr_activation, hidden layers */
+  /* create_tower options (keras/layers.py:65-76).  Layer order per hidden layer:
+   * Dense -> [BatchNormalization] -> activation -> [Dropout]. */
+  int32_t use_batch_norm;                 /* BN after every hidden Dense (:71-72) */
+  int32_t input_batch_norm;               /* BN on the inputs (:67-68) */
+  float bn_epsilon;                       /* Keras default 1e-3 */
+  float bn_momentum;                      /* `batch_norm_moment`, default 0.999 */
+  float dropout;                          /* rate in [0, 1) (:74-75) */
+  int32_t training;                       /* 1: batch statistics, moving-average update,
+                                             dropout active; 0: inference */
+  uint64_t dropout_seed;                  /* vary per step; same value -> same mask.
+                                             Dropout mask: element i (row-major) of hidden
+                                             layer d is dropped iff u < dropout, with
+                                             u = (splitmix64_mix(s + 0x9E3779B97F4A7C15 *
+                                             (i + 1)) >> 40) * 2^-24 and
+                                             s = seed * 0x100000001B3 + d + 1; kept
+                                             values are scaled by 1 / (1 - dropout). */
+  float* bn_state;                        /* device, tfr_mlp_bn_state_count floats: per BN
+                                             layer (input BN first) moving_mean[w] then
+                                             moving_variance[w]; required with any BN */
 } tfr_mlp_cfg;
 
+/* Flat parameter layout: W_0 [dims0, dims1] (Keras kernel layout), b_0, W_1, b_1, ...
+ * then, if input_batch_norm, gamma[D], beta[D]; then for every hidden layer with BN
+ * gamma[h], beta[h].  Gradients use the same layout. */
 size_t tfr_mlp_param_count(const tfr_mlp_cfg* cfg);
+size_t tfr_mlp_bn_state_count(const tfr_mlp_cfg* cfg);
 /* bytes of caller-provided workspace that carries activations from fwd to bwd */
 size_t tfr_mlp_workspace_bytes(const tfr_mlp_cfg* cfg, int M);
 

@@ -48,10 +48,36 @@ def init_tower_params(input_dim, hidden_layer_dims, output_units, seed=1238,
   return p
 
 
-def _batch_norm_train(x, gamma, beta):
+def _batch_norm_train(x, gamma, beta, moving=None, momentum=0.999):
+  """tf.keras BatchNormalization, non-fused rank-2 path, training=True: population
+  variance; `moving` = [moving_mean, moving_variance] is updated in place as
+  moving * momentum + batch * (1 - momentum)."""
   mean = x.mean(0, keepdim=True)
   var = x.var(0, unbiased=False, keepdim=True)
+  if moving is not None:
+    with torch.no_grad():
+      moving[0].mul_(momentum).add_(mean.reshape(-1) * (1 - momentum))
+      moving[1].mul_(momentum).add_(var.reshape(-1) * (1 - momentum))
   return (x - mean) * torch.rsqrt(var + BN_EPSILON) * gamma + beta
+
+
+def _batch_norm_infer(x, gamma, beta, moving):
+  """training=False: the moving statistics normalise."""
+  return (x - moving[0]) * torch.rsqrt(moving[1] + BN_EPSILON) * gamma + beta
+
+
+def init_bn_moving(input_dim, hidden_layer_dims, input_batch_norm=False,
+                   use_batch_norm=False, dtype=torch.float32):
+  """Keras initial moving statistics: mean zeros, variance ones.
+  {'input': [mean, var], 0: [...], 1: [...]}"""
+  out = {}
+  if input_batch_norm:
+    out['input'] = [torch.zeros(input_dim, dtype=dtype),
+                    torch.ones(input_dim, dtype=dtype)]
+  if use_batch_norm:
+    for i, h in enumerate(hidden_layer_dims):
+      out[i] = [torch.zeros(h, dtype=dtype), torch.ones(h, dtype=dtype)]
+  return out
 
 
 def _act(x, activation):
@@ -67,18 +93,31 @@ def _act(x, activation):
 
 
 def tower_forward(x, params, activation=None, use_batch_norm=False,
-                  input_batch_norm=False):
-  """create_tower forward in training mode with dropout=0
-  (keras/layers.py:65-77): [BN] -> (Dense -> [BN] -> act) x L -> Dense."""
+                  input_batch_norm=False, training=True, bn_moving=None,
+                  momentum=0.999, keep_masks=None):
+  """create_tower forward (keras/layers.py:65-77):
+  [BN] -> (Dense -> [BN] -> act -> [Dropout]) x L -> Dense.
+  Dropout is random in the reference; `keep_masks` (one {0,1} tensor per hidden
+  layer, already divided by keep probability or not — see below) lets a test
+  replay a given mask: h = h * keep_masks[i] (the caller includes the 1/(1-p)
+  scale)."""
+  def bn(h, g, b, key):
+    mv = None if bn_moving is None else bn_moving[key]
+    if training:
+      return _batch_norm_train(h, g, b, mv, momentum)
+    return _batch_norm_infer(h, g, b, mv)
+
   h = x
   if input_batch_norm:
-    h = _batch_norm_train(h, params['in_bn_gamma'], params['in_bn_beta'])
+    h = bn(h, params['in_bn_gamma'], params['in_bn_beta'], 'input')
   n_hidden = len(params['dense_w']) - 1
   for i in range(n_hidden):
     h = h @ params['dense_w'][i] + params['dense_b'][i]
     if use_batch_norm:
-      h = _batch_norm_train(h, params['bn_gamma'][i], params['bn_beta'][i])
+      h = bn(h, params['bn_gamma'][i], params['bn_beta'][i], i)
     h = _act(h, activation)
+    if keep_masks is not None:
+      h = h * keep_masks[i]
   return h @ params['dense_w'][-1] + params['dense_b'][-1]
 
 

@@ -39,7 +39,11 @@ class LambdaCfg(C.Structure):
 
 class MlpCfg(C.Structure):
   _fields_ = [('n_dense', C.c_int32), ('dims', C.c_int32 * (MLP_MAX_LAYERS + 1)),
-              ('activation', C.c_int32)]
+              ('activation', C.c_int32),
+              ('use_batch_norm', C.c_int32), ('input_batch_norm', C.c_int32),
+              ('bn_epsilon', C.c_float), ('bn_momentum', C.c_float),
+              ('dropout', C.c_float), ('training', C.c_int32),
+              ('dropout_seed', C.c_uint64), ('bn_state', C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -65,6 +69,7 @@ _SIGNATURES = {
                               _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'tfr_weighted_sum': (_I, [_P, _P, _I, _F, _P, _P]),
     'tfr_mlp_param_count': (C.c_size_t, [C.POINTER(MlpCfg)]),
+    'tfr_mlp_bn_state_count': (C.c_size_t, [C.POINTER(MlpCfg)]),
     'tfr_mlp_workspace_bytes': (C.c_size_t, [C.POINTER(MlpCfg), _I]),
     'tfr_mlp_fwd': (_I, [_P, _I, C.POINTER(MlpCfg), _P, _P, _P, _P, _I, _P]),
     'tfr_mlp_bwd': (_I, [_P, _I, C.POINTER(MlpCfg), _P, _P, _P, _P, _P, _I, _P]),

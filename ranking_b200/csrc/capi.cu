@@ -47,12 +47,65 @@ int make_mlp_plan(const tfr_mlp_cfg* cfg, int M, MlpPlan* p) {
     if (wb > max_wb) max_wb = wb;
     if (d < L && p->dims[d + 1] > max_hidden) max_hidden = p->dims[d + 1];
   }
+  // BatchNormalization / Dropout options
+  TFR_REQUIRE(cfg->dropout >= 0.f && cfg->dropout < 1.f, "dropout %g must be in [0, 1)",
+              (double)cfg->dropout);
+  p->use_bn = cfg->use_batch_norm != 0 && L > 0;
+  p->input_bn = cfg->input_batch_norm != 0;
+  p->training = cfg->training != 0;
+  p->bn_eps = cfg->bn_epsilon;
+  p->bn_mom = cfg->bn_momentum;
+  p->dropout = L > 0 ? cfg->dropout : 0.f;
+  p->seed = cfg->dropout_seed;
+  p->bn_state = cfg->bn_state;
+  if (p->use_bn || p->input_bn) {
+    TFR_REQUIRE(cfg->bn_epsilon > 0.f, "bn_epsilon must be > 0");
+    TFR_REQUIRE(cfg->bn_momentum >= 0.f && cfg->bn_momentum <= 1.f,
+                "bn_momentum %g must be in [0, 1]", (double)cfg->bn_momentum);
+  }
+  size_t soff = 0;
+  int max_bn_w = 1;
+  if (p->input_bn) {
+    p->gin_off = off; off += p->dims[0];
+    p->bein_off = off; off += p->dims[0];
+    p->stin_off = soff; soff += 2 * (size_t)p->dims[0];
+    max_bn_w = p->dims[0];
+  }
+  if (p->use_bn)
+    for (int d = 0; d < L; ++d) {
+      p->g_off[d] = off; off += p->dims[d + 1];
+      p->be_off[d] = off; off += p->dims[d + 1];
+      p->st_off[d] = soff; soff += 2 * (size_t)p->dims[d + 1];
+      if (p->dims[d + 1] > max_bn_w) max_bn_w = p->dims[d + 1];
+    }
+  p->n_state = soff;
   p->n_params = off;
   // workspace
   size_t w = 0;
   for (int d = 0; d < L; ++d) {
     p->act_off[d] = w;
     w += align_up((size_t)M * p->dims[d + 1], 64);
+  }
+  if (p->use_bn)
+    for (int d = 0; d < L; ++d) {
+      p->xhat_off[d] = w;
+      w += align_up((size_t)M * p->dims[d + 1], 64);
+      p->bnstat_off[d] = w;
+      w += align_up(2 * (size_t)p->dims[d + 1], 64);
+    }
+  if (p->input_bn) {
+    p->xin_off = w;
+    w += align_up((size_t)M * p->dims[0], 64);
+    p->bnstat_in_off = w;
+    w += align_up(2 * (size_t)p->dims[0], 64);
+    if (p->dims[0] > max_hidden) max_hidden = p->dims[0];   // dZ ping-pong also holds dL/dXin
+  }
+  if (p->use_bn || p->input_bn) {
+    p->red_rows = 256;
+    p->red_blocks = M > 0 ? (M + p->red_rows - 1) / p->red_rows : 1;
+    p->red_stride = align_up(2 * (size_t)max_bn_w, 64);
+    p->red_off = w;
+    w += (size_t)p->red_blocks * p->red_stride + align_up(2 * (size_t)max_bn_w, 64);
   }
   for (int i = 0; i < 2; ++i) {
     p->dz_off[i] = w;
@@ -117,7 +170,7 @@ optimizer_kernel(float* __restrict__ params, const float* __restrict__ grads,
 using namespace tfr;
 
 extern "C" const char* tfr_last_error(void) { return g_err; }
-extern "C" int tfr_version(void) { return 1; }
+extern "C" int tfr_version(void) { return 2; }
 extern "C" unsigned long long tfr_launch_count(void) {
   return __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
 }
@@ -126,6 +179,12 @@ extern "C" size_t tfr_mlp_param_count(const tfr_mlp_cfg* cfg) {
   MlpPlan p;
   if (make_mlp_plan(cfg, 0, &p)) return 0;
   return p.n_params;
+}
+
+extern "C" size_t tfr_mlp_bn_state_count(const tfr_mlp_cfg* cfg) {
+  MlpPlan p;
+  if (make_mlp_plan(cfg, 0, &p)) return 0;
+  return p.n_state;
 }
 
 extern "C" size_t tfr_mlp_workspace_bytes(const tfr_mlp_cfg* cfg, int M) {
@@ -147,6 +206,7 @@ extern "C" int tfr_mlp_fwd(const float* X, int M, const tfr_mlp_cfg* cfg,
   int rc = make_mlp_plan(cfg, M, &p);
   if (rc) return rc;
   TFR_REQUIRE(X && params && workspace && scores_out, "NULL argument");
+  TFR_REQUIRE(!(p.use_bn || p.input_bn) || p.bn_state, "cfg->bn_state must be set with BN");
   if (M == 0) return TFR_OK;
   switch (precision) {
     case TFR_PREC_FP32:
@@ -169,6 +229,7 @@ extern "C" int tfr_mlp_bwd(const float* X, int M, const tfr_mlp_cfg* cfg,
   int rc = make_mlp_plan(cfg, M, &p);
   if (rc) return rc;
   TFR_REQUIRE(X && params && workspace && dscores && grads, "NULL argument");
+  TFR_REQUIRE(!(p.use_bn || p.input_bn) || p.bn_state, "cfg->bn_state must be set with BN");
   if (M == 0) return TFR_OK;
   switch (precision) {
     case TFR_PREC_FP32:

@@ -26,8 +26,37 @@ struct MlpPlan {
   int tile_slots;
   size_t oslot_off, oslot_stride;      // [ceil(M / out_rows)][oslot_stride]
   int out_rows, out_slots;
+  // BatchNormalization / Dropout (create_tower options)
+  int use_bn, input_bn, training;
+  float bn_eps, bn_mom, dropout;
+  unsigned long long seed;
+  float* bn_state;                              // moving mean / variance (device)
+  size_t g_off[TFR_MLP_MAX_LAYERS], be_off[TFR_MLP_MAX_LAYERS];   // gamma / beta of hidden BN d
+  size_t gin_off, bein_off;                     // input BN gamma / beta
+  size_t st_off[TFR_MLP_MAX_LAYERS], stin_off;  // offsets into bn_state (mean; var at +w)
+  size_t n_state;
+  size_t xhat_off[TFR_MLP_MAX_LAYERS];          // normalised pre-activations of hidden layer d
+  size_t xin_off;                               // batch-normalised inputs
+  size_t bnstat_off[TFR_MLP_MAX_LAYERS], bnstat_in_off;   // batch mean[w], rstd[w] (fwd -> bwd)
+  size_t red_off, red_stride;                   // column-reduction partials [red_blocks][stride]
+  int red_rows, red_blocks;
   size_t ws_floats;
+  bool post() const { return use_bn || dropout > 0.f; }   // hidden layers need a post pass
 };
+
+// BatchNormalization / Dropout passes shared by both scorer paths (mlp_norm.cu).
+// Forward, hidden layer d: Z (in the xhat buffer when BN) -> H (act buffer).
+int mlp_hidden_post_fwd(int d, int M, const MlpPlan& p, const float* params, float* ws,
+                        cudaStream_t st);
+// Backward, hidden layer d: dz holds dL/dH_d on entry, dL/dZ_d on exit; writes the
+// BN gamma / beta gradients.
+int mlp_hidden_pre_bwd(int d, int M, const MlpPlan& p, const float* params, float* ws,
+                       float* dz, float* grads, cudaStream_t st);
+// Input BN: X -> ws + xin_off; and its parameter gradients from dL/dXin.
+int mlp_input_bn_fwd(const float* X, int M, const MlpPlan& p, const float* params, float* ws,
+                     cudaStream_t st);
+int mlp_input_bn_bwd(const float* X, int M, const MlpPlan& p, const float* params, float* ws,
+                     const float* dxin, float* grads, cudaStream_t st);
 
 // Returns 0 on success and fills `p`; sets the error string otherwise.
 int make_mlp_plan(const tfr_mlp_cfg* cfg, int M, MlpPlan* p);

@@ -399,18 +399,25 @@ int mlp_simt_fwd(const float* X, int M, const MlpPlan& p, const float* params,
                  const uint8_t* mask, float* ws, float* scores, cudaStream_t st) {
   const int L = p.n_dense - 1;  // hidden layers
   const float* in = X;
+  if (p.input_bn) {
+    int rc = mlp_input_bn_fwd(X, M, p, params, ws, st);
+    if (rc) return rc;
+    in = ws + p.xin_off;
+  }
   for (int d = 0; d < L; ++d) {
     GemmArgs g{};
     g.A = in; g.lda = p.dims[d];
     g.B = params + p.w_off[d]; g.ldb = p.dims[d + 1];
-    g.C = ws + p.act_off[d]; g.ldc = p.dims[d + 1];
+    g.C = ws + (p.use_bn ? p.xhat_off[d] : p.act_off[d]); g.ldc = p.dims[d + 1];
     g.M = M; g.N = p.dims[d + 1]; g.K = p.dims[d];
     g.bias = params + p.b_off[d];
-    g.act = p.activation;
+    g.act = p.use_bn ? TFR_ACT_NONE : p.activation;   // BN sits before the activation
     g.k_per_split = g.K; g.split_stride = 0;
     int rc = launch_gemm<false, false, EPI_BIAS_ACT>(g, 1, st);
     if (rc) return rc;
-    in = g.C;
+    rc = mlp_hidden_post_fwd(d, M, p, params, ws, st);
+    if (rc) return rc;
+    in = ws + p.act_off[d];
   }
   const int K = p.dims[L], O = p.dims[L + 1];
   return mlp_out_layer_fwd(in, M, K, O, params + p.w_off[L], params + p.b_off[L], mask, scores,
@@ -426,15 +433,18 @@ int mlp_simt_bwd(const float* X, int M, const MlpPlan& p, const float* params,
   const int rows_per = p.rows_per_split, splits = p.splits;
   float* dz_cur = ws + p.dz_off[0];
   float* dz_nxt = ws + p.dz_off[1];
+  const float* X0 = p.input_bn ? ws + p.xin_off : X;   // what Dense 0 consumed
+  // With BN / dropout the producers emit raw dL/dH; mlp_hidden_pre_bwd turns it into dL/dZ.
+  const int mact = p.post() ? TFR_ACT_NONE : p.activation;
 
   // output layer
   {
     const int K = p.dims[L], O = p.dims[L + 1];
-    const float* H = L > 0 ? ws + p.act_off[L - 1] : X;
+    const float* H = L > 0 ? ws + p.act_off[L - 1] : X0;
     const int threads = ((K + 31) / 32) * 32;
     out_layer_bwd_kernel<<<splits, threads, 0, st>>>(
-        H, M, K, O, params + p.w_off[L], dscores, mask, L > 0 ? p.activation : TFR_ACT_NONE,
-        rows_per, L > 0 ? dz_cur : nullptr, partial, pstride);
+        H, M, K, O, params + p.w_off[L], dscores, mask, L > 0 ? mact : TFR_ACT_NONE,
+        rows_per, (L > 0 || p.input_bn) ? dz_cur : nullptr, partial, pstride);
     TFR_LAUNCH_OK();
     const size_t n = (size_t)K * O + O;
     reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, splits, pstride, n,
@@ -444,7 +454,11 @@ int mlp_simt_bwd(const float* X, int M, const MlpPlan& p, const float* params,
   // hidden layers, last to first: dz_cur = dZ_d  [M, dims[d+1]]
   for (int d = L - 1; d >= 0; --d) {
     const int Kin = p.dims[d], Nout = p.dims[d + 1];
-    const float* A = d > 0 ? ws + p.act_off[d - 1] : X;
+    const float* A = d > 0 ? ws + p.act_off[d - 1] : X0;
+    if (p.post()) {
+      int rc = mlp_hidden_pre_bwd(d, M, p, params, ws, dz_cur, grads, st);
+      if (rc) return rc;
+    }
     colsum_kernel<<<splits, 256, 0, st>>>(dz_cur, M, Nout, rows_per, partial, pstride,
                                           (size_t)Kin * Nout);
     TFR_LAUNCH_OK();
@@ -462,20 +476,21 @@ int mlp_simt_bwd(const float* X, int M, const MlpPlan& p, const float* params,
     reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(partial, splits, pstride, n,
                                                                        grads + p.w_off[d]);
     TFR_LAUNCH_OK();
-    if (d > 0) {  // dZ_{d-1} = (dZ_d W_d^T) * act'(H_{d-1})
+    if (d > 0 || p.input_bn) {  // dZ_{d-1} = (dZ_d W_d^T) * act'(H_{d-1});  d == 0: dL/dXin
       GemmArgs g{};
       g.A = dz_cur; g.lda = Nout;
       g.B = params + p.w_off[d]; g.ldb = Nout;   // opB(B)[nout, kin] = W[kin, nout]
       g.C = dz_nxt; g.ldc = Kin;
       g.M = M; g.N = Kin; g.K = Nout;
-      g.aux = ws + p.act_off[d - 1];
-      g.act = p.activation;
+      g.aux = d > 0 ? ws + p.act_off[d - 1] : nullptr;
+      g.act = d > 0 ? mact : TFR_ACT_NONE;
       g.k_per_split = g.K; g.split_stride = 0;
       int rc = launch_gemm<false, true, EPI_MASK_POS>(g, 1, st);
       if (rc) return rc;
       float* t = dz_cur; dz_cur = dz_nxt; dz_nxt = t;
     }
   }
+  if (p.input_bn) return mlp_input_bn_bwd(X, M, p, params, ws, dz_cur, grads, st);
   return TFR_OK;
 }
 

@@ -57,19 +57,27 @@ int mlp_tc_fwd(const float* X, int M, const MlpPlan& p, const float* params,
   const float* whi = passes == 3 ? ws + p.whi_off : params;
   const float* wlo = passes == 3 ? ws + p.wlo_off : nullptr;
   const float* in = X;
+  if (p.input_bn) {
+    rc = mlp_input_bn_fwd(X, M, p, params, ws, st);
+    if (rc) return rc;
+    in = ws + p.xin_off;
+  }
   for (int d = 0; d < L; ++d) {
     tc::GemmDesc g{};
     g.A = in; g.lda = p.dims[d];
     g.B = whi + p.w_off[d]; g.ldb = p.dims[d + 1];
     g.B_lo = wlo ? wlo + p.w_off[d] : nullptr;
-    g.C = ws + p.act_off[d]; g.ldc = p.dims[d + 1];
+    g.C = ws + (p.use_bn ? p.xhat_off[d] : p.act_off[d]); g.ldc = p.dims[d + 1];
     g.GM = M; g.GN = p.dims[d + 1]; g.GK = p.dims[d];
     g.a_mn = 0; g.b_mn = 1; g.passes = passes; g.split_b = 0;
-    g.epi = tc::EPI_BIAS_ACT; g.bias = params + p.b_off[d]; g.act = p.activation;
+    g.epi = tc::EPI_BIAS_ACT; g.bias = params + p.b_off[d];
+    g.act = p.use_bn ? TFR_ACT_NONE : p.activation;   // BN sits before the activation
     g.splits = 1; g.split_stride = 0;
     rc = tc::gemm(g, st);
     if (rc) return rc;
-    in = g.C;
+    rc = mlp_hidden_post_fwd(d, M, p, params, ws, st);
+    if (rc) return rc;
+    in = ws + p.act_off[d];
   }
   return mlp_out_layer_fwd(in, M, p.dims[L], p.dims[L + 1], params + p.w_off[L],
                            params + p.b_off[L], mask, scores, st);
@@ -90,15 +98,19 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
   float* dz_nxt = ws + p.dz_off[1];
   float* tiles = ws + p.tile_off;
   float* oslots = ws + p.oslot_off;
+  const float* X0 = p.input_bn ? ws + p.xin_off : X;   // what Dense 0 consumed
+  // With BN / dropout the producers emit raw dL/dH; mlp_hidden_pre_bwd turns it into dL/dZ.
+  const int mact = p.post() ? TFR_ACT_NONE : p.activation;
   {
     // Output layer (GEMV-shaped, CUDA cores): dZ of the last hidden layer, plus per
     // 256-row block {dW_out, db_out, column sums of dZ}; regrouped to the
     // `splits` partial slots and reduced.
     const int K = p.dims[L], O = p.dims[L + 1];
-    const float* H = L > 0 ? ws + p.act_off[L - 1] : X;
+    const float* H = L > 0 ? ws + p.act_off[L - 1] : X0;
     rc = mlp_out_layer_bwd2(H, M, K, O, params + p.w_off[L], dscores, mask,
-                            L > 0 ? p.activation : TFR_ACT_NONE, p.out_rows,
-                            L > 0 ? dz_cur : nullptr, oslots, p.oslot_stride, st);
+                            L > 0 ? mact : TFR_ACT_NONE, p.out_rows,
+                            (L > 0 || p.input_bn) ? dz_cur : nullptr, oslots, p.oslot_stride,
+                            st);
     if (rc) return rc;
     // out-layer gradient: [K*O + O] summed over the block slots
     rc = mlp_reduce2(oslots, p.out_slots, p.oslot_stride, (size_t)K * O + O, nullptr, 0, 0, 0,
@@ -112,7 +124,16 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
   size_t bstride = p.oslot_stride;
   for (int d = L - 1; d >= 0; --d) {
     const int Kin = p.dims[d], Nout = p.dims[d + 1];
-    const float* A = d > 0 ? ws + p.act_off[d - 1] : X;
+    const float* A = d > 0 ? ws + p.act_off[d - 1] : X0;
+    if (p.post()) {
+      rc = mlp_hidden_pre_bwd(d, M, p, params, ws, dz_cur, grads, st);
+      if (rc) return rc;
+      rc = mlp_colsum(dz_cur, M, Nout, p.rows_per_split, splits, tiles, p.tile_stride, 0, st);
+      if (rc) return rc;
+      bsrc = tiles;
+      bslots = splits;
+      bstride = p.tile_stride;
+    }
     {
       // dW[Kin, Nout] = A^T dZ.  Pick the orientation with fewer UMMA cycles:
       //   direct : GM = Kin (tiles of 128), GN = Nout
@@ -143,7 +164,7 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
     rc = mlp_reduce2(partial, splits, pstride, (size_t)Kin * Nout, bsrc, bslots, bstride,
                      (size_t)Nout, grads + p.w_off[d], st);
     if (rc) return rc;
-    if (d > 0) {
+    if (d > 0 || p.input_bn) {   // d == 0 with input BN: dL/dXin for its gamma / beta
       tc::GemmDesc g{};
       g.A = dz_cur; g.lda = Nout;
       g.B = whi + p.w_off[d]; g.ldb = Nout;     // W [Kin rows (GN), Nout (GK)] : K-major
@@ -151,10 +172,14 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
       g.C = dz_nxt; g.ldc = Kin;
       g.GM = M; g.GN = Kin; g.GK = Nout;
       g.a_mn = 0; g.b_mn = 0; g.passes = passes; g.split_b = 0;
-      g.epi = tc::EPI_MASK_POS; g.aux = ws + p.act_off[d - 1]; g.act = p.activation;
+      const bool masked = d > 0 && mact != TFR_ACT_NONE;
+      g.epi = masked ? tc::EPI_MASK_POS : tc::EPI_STORE;
+      g.aux = masked ? ws + p.act_off[d - 1] : nullptr; g.act = mact;
       g.splits = 1; g.split_stride = 0;
       int cslots = 0;
-      g.colsum = tiles; g.colsum_stride = (int)p.tile_stride; g.colsum_slots_out = &cslots;
+      if (d > 0 && !p.post()) {
+        g.colsum = tiles; g.colsum_stride = (int)p.tile_stride; g.colsum_slots_out = &cslots;
+      }
       rc = tc::gemm(g, st);
       if (rc) return rc;
       bsrc = tiles;            // column sums of dZ_{d-1}: one slot per CTA and quarter
@@ -163,6 +188,7 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
       float* t = dz_cur; dz_cur = dz_nxt; dz_nxt = t;
     }
   }
+  if (p.input_bn) return mlp_input_bn_bwd(X, M, p, params, ws, dz_cur, grads, st);
   return TFR_OK;
 }
 

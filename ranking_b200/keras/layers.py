@@ -40,10 +40,12 @@ class _TowerFn(torch.autograd.Function):
     # The workspace carries the activations to backward; one per forward call
     # so that several forwards may be outstanding (caching allocator: cheap).
     ws = tower._new_workspace(m)
-    _C.check(_C.lib.tfr_mlp_fwd(_C.ptr(x), m, ctypes.byref(tower._cfg),
+    cfg = tower._run_cfg()
+    _C.check(_C.lib.tfr_mlp_fwd(_C.ptr(x), m, ctypes.byref(cfg),
                                 _C.ptr(flat), _C.ptr(mask), _C.ptr(ws),
                                 _C.ptr(out), tower._precision, _C.stream()))
     ctx.tower = tower
+    ctx.cfg = cfg      # backward sees the mode (training / inference) of ITS forward
     ctx.ws = ws
     ctx.save_for_backward(x, flat, mask)
     return out
@@ -55,7 +57,7 @@ class _TowerFn(torch.autograd.Function):
     m = x.shape[0]
     grads = torch.empty_like(flat)
     ws = ctx.ws
-    _C.check(_C.lib.tfr_mlp_bwd(_C.ptr(x), m, ctypes.byref(tower._cfg),
+    _C.check(_C.lib.tfr_mlp_bwd(_C.ptr(x), m, ctypes.byref(ctx.cfg),
                                 _C.ptr(flat), _C.ptr(g_out.contiguous()),
                                 _C.ptr(mask), _C.ptr(ws), _C.ptr(grads),
                                 tower._precision, _C.stream()))
@@ -63,10 +65,16 @@ class _TowerFn(torch.autograd.Function):
 
 
 class Tower(torch.nn.Module):
-  """Feed-forward tower: (Dense -> activation) x L -> Dense(output_units)."""
+  """Feed-forward tower (keras/layers.py:65-77):
+  [BN] -> (Dense -> [BN] -> activation -> [Dropout]) x L -> Dense(output_units).
+
+  `module.train()` / `module.eval()` select batch statistics + dropout vs moving
+  statistics, as Keras' `training` argument does."""
 
   def __init__(self, input_dim, hidden_layer_dims, output_units, activation=None,
-               precision='fp32', seed=None, device='cuda'):
+               precision='fp32', seed=None, device='cuda', input_batch_norm=False,
+               use_batch_norm=False, batch_norm_moment=0.999, dropout=0.0,
+               batch_norm_epsilon=1e-3):
     super().__init__()
     self.input_dim = int(input_dim)
     self.hidden_layer_dims = [int(h) for h in hidden_layer_dims]
@@ -80,6 +88,22 @@ class Tower(torch.nn.Module):
     for i, d in enumerate(dims):
       cfg.dims[i] = d
     cfg.activation = _activation_enum(activation)
+    if not 0.0 <= float(dropout) < 1.0:
+      raise ValueError('dropout must be in [0, 1)')
+    cfg.use_batch_norm = int(bool(use_batch_norm) and len(self.hidden_layer_dims) > 0)
+    cfg.input_batch_norm = int(bool(input_batch_norm))
+    cfg.bn_epsilon = float(batch_norm_epsilon)
+    cfg.bn_momentum = float(batch_norm_moment)
+    cfg.dropout = float(dropout) if self.hidden_layer_dims else 0.0
+    cfg.training = 1
+    cfg.dropout_seed = 0
+    cfg.bn_state = None
+    self.use_batch_norm = bool(cfg.use_batch_norm)
+    self.input_batch_norm = bool(cfg.input_batch_norm)
+    self.dropout = float(cfg.dropout)
+    self._dropout_base = int(seed if seed is not None else
+                             torch.seed()) & 0xFFFFFFFF
+    self._dropout_calls = 0
     self._cfg = cfg
     self.dims = dims
     self.set_precision(precision)
@@ -101,7 +125,51 @@ class Tower(torch.nn.Module):
       flat[off:off + fi * fo] = w.reshape(-1)
       self.offsets.append((off, off + fi * fo, off + fi * fo + fo))
       off += fi * fo + fo
+    # BatchNormalization parameters follow the Dense ones: gamma (ones), beta (zeros);
+    # moving_mean (zeros) / moving_variance (ones) live in `bn_state`.
+    self.bn_offsets = {}        # 'input' | hidden index -> (gamma_off, beta_off, width)
+    self.bn_state_offsets = {}  # same keys -> (mean_off, var_off, width)
+    soff = 0
+    bn_layers = (['input'] if self.input_batch_norm else []) + (
+        list(range(len(self.hidden_layer_dims))) if self.use_batch_norm else [])
+    state = []
+    for key in bn_layers:
+      w_ = dims[0] if key == 'input' else dims[key + 1]
+      flat[off:off + w_] = 1.0
+      self.bn_offsets[key] = (off, off + w_, w_)
+      off += 2 * w_
+      self.bn_state_offsets[key] = (soff, soff + w_, w_)
+      state += [torch.zeros(w_), torch.ones(w_)]
+      soff += 2 * w_
+    assert off == n and soff == _C.lib.tfr_mlp_bn_state_count(ctypes.byref(cfg))
     self.flat = torch.nn.Parameter(flat.to(device))
+    self.register_buffer(
+        'bn_state', torch.cat(state).to(device) if state else
+        torch.zeros(0, device=device))
+
+  def _run_cfg(self, training=None):
+    """A per-call copy of the config: mode, dropout seed, BN state pointer."""
+    cfg = _C.MlpCfg()
+    ctypes.memmove(ctypes.byref(cfg), ctypes.byref(self._cfg), ctypes.sizeof(cfg))
+    training = self.training if training is None else training
+    cfg.training = int(bool(training))
+    if training and self.dropout > 0:
+      self._dropout_calls += 1
+    cfg.dropout_seed = (self._dropout_base << 32) | (self._dropout_calls & 0xFFFFFFFF)
+    cfg.bn_state = self.bn_state.data_ptr() if self.bn_state.numel() else None
+    return cfg
+
+  def bn_gamma(self, key):
+    a, b, w_ = self.bn_offsets[key]
+    return self.flat[a:a + w_]
+
+  def bn_beta(self, key):
+    a, b, w_ = self.bn_offsets[key]
+    return self.flat[b:b + w_]
+
+  def bn_moving(self, key):
+    a, b, w_ = self.bn_state_offsets[key]
+    return self.bn_state[a:a + w_], self.bn_state[b:b + w_]
 
   def set_precision(self, precision):
     if precision not in _PRECISIONS:
@@ -151,24 +219,18 @@ def create_tower(hidden_layer_dims, output_units, activation=None,
                  input_dim=None, precision='fp32', seed=None, **kwargs):
   """keras/layers.py:26-77.  Same arguments and defaults as the reference.
 
-  The CUDA tower covers the Dense/activation chain.  BatchNormalization and
-  Dropout (both ON by default in the reference) are not in the fused kernels yet:
-  pass `use_batch_norm=False, dropout=0` (DESIGN.md "out of scope / next").
+  BatchNormalization (batch statistics in `train()` mode, moving statistics in
+  `eval()` mode) and Dropout run as HBM-bound passes next to the Dense GEMMs
+  (csrc/mlp_norm.cu); the headline benchmark configuration uses neither.
   `input_dim` is required here because torch modules are built eagerly (Keras
   infers it at first call); `DNNScorer` supplies it automatically.
   """
-  if input_batch_norm or use_batch_norm:
-    raise NotImplementedError(
-        'BatchNormalization inside create_tower is not implemented in the CUDA '
-        'tower yet; pass use_batch_norm=False, input_batch_norm=False.')
-  if dropout:
-    raise NotImplementedError(
-        'Dropout inside create_tower is not implemented in the CUDA tower yet; '
-        'pass dropout=0.')
   if input_dim is None:
     raise ValueError('create_tower needs input_dim')
   return Tower(input_dim, hidden_layer_dims, output_units, activation,
-               precision=precision, seed=seed)
+               precision=precision, seed=seed, input_batch_norm=input_batch_norm,
+               use_batch_norm=use_batch_norm, batch_norm_moment=batch_norm_moment,
+               dropout=dropout)
 
 
 class FlattenList(torch.nn.Module):

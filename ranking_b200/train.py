@@ -67,7 +67,8 @@ class RankingTrainer(object):
     t = self.tower
     m = b * n
     st = _C.stream()
-    cfg = ctypes.byref(t._cfg)
+    run_cfg = t._run_cfg(training=True)
+    cfg = ctypes.byref(run_cfg)
     m8 = None
     if mask is not None:
       m8 = mask.reshape(-1).to(torch.uint8).contiguous()
@@ -93,7 +94,8 @@ class RankingTrainer(object):
     self._ensure(b, n)
     t = self.tower
     m8 = None if mask is None else mask.reshape(-1).to(torch.uint8).contiguous()
-    _C.check(_C.lib.tfr_mlp_fwd(_C.ptr(x), b * n, ctypes.byref(t._cfg),
+    _C.check(_C.lib.tfr_mlp_fwd(_C.ptr(x), b * n,
+                                ctypes.byref(t._run_cfg(training=False)),
                                 _C.ptr(t.flat.data), _C.ptr(m8), _C.ptr(self.ws),
                                 _C.ptr(self.scores), t._precision, _C.stream()))
     return self.scores

@@ -311,6 +311,234 @@ def test_tower_tensor_core_path(oracle_api, shape, precision, tol_fwd, tol_bwd):
     assert _rel_err(got, want) <= max(100 * tol_bwd, 5e-3)
 
 
+# ---------------------- BatchNormalization / Dropout ------------------------
+def _bn_tower_and_params(tfr, d, hidden, out, seed, activation, precision,
+                         input_bn, use_bn, dropout=0.0, moment=0.9):
+  tower = tfr.keras.layers.create_tower(
+      hidden, out, activation=activation, input_batch_norm=input_bn,
+      use_batch_norm=use_bn, batch_norm_moment=moment, dropout=dropout,
+      input_dim=d, seed=seed, precision=precision)
+  g = torch.Generator().manual_seed(seed + 7)
+  with torch.no_grad():
+    for i in range(len(tower.dims) - 1):
+      tower.bias(i).copy_(torch.rand(tower.dims[i + 1], generator=g) * 0.4 - 0.2)
+    for key in tower.bn_offsets:
+      w = tower.bn_offsets[key][2]
+      tower.bn_gamma(key).copy_(torch.rand(w, generator=g) + 0.5)
+      tower.bn_beta(key).copy_(torch.rand(w, generator=g) * 0.6 - 0.3)
+  nl = len(tower.dims) - 1
+  dbl = lambda t: t.detach().cpu().double().clone().requires_grad_()
+  params = {'dense_w': [dbl(tower.kernel(i)) for i in range(nl)],
+            'dense_b': [dbl(tower.bias(i)) for i in range(nl)],
+            'bn_gamma': [], 'bn_beta': [], 'in_bn_gamma': None, 'in_bn_beta': None}
+  if input_bn:
+    params['in_bn_gamma'] = dbl(tower.bn_gamma('input'))
+    params['in_bn_beta'] = dbl(tower.bn_beta('input'))
+  if use_bn:
+    params['bn_gamma'] = [dbl(tower.bn_gamma(i)) for i in range(len(hidden))]
+    params['bn_beta'] = [dbl(tower.bn_beta(i)) for i in range(len(hidden))]
+  return tower, params
+
+
+def _bn_flat_grad(params, zero=False):
+  parts = []
+  for w, b in zip(params['dense_w'], params['dense_b']):
+    parts += [w.grad.reshape(-1), b.grad.reshape(-1)]
+  if params['in_bn_gamma'] is not None:
+    parts += [params['in_bn_gamma'].grad, params['in_bn_beta'].grad]
+  for g_, b_ in zip(params['bn_gamma'], params['bn_beta']):
+    parts += [g_.grad, b_.grad]
+  return torch.cat(parts)
+
+
+@pytest.mark.parametrize('precision,tol', [('fp32', 2e-5), ('tf32x3', 5e-5)])
+@pytest.mark.parametrize('shape', [
+    # m, d, hidden, out, act, input_bn, use_bn
+    (700, 136, [256, 128, 64], 1, 'relu', True, True),     # reference defaults
+    (700, 136, [256, 128, 64], 1, 'relu', False, True),
+    (1300, 24, [48, 16], 1, None, True, False),
+    (515, 40, [], 1, None, True, False),                    # linear scorer + input BN
+    (4200, 64, [128], 2, None, True, True),
+])
+def test_tower_batch_norm_training(oracle_api, shape, precision, tol):
+  """create_tower with BatchNormalization in training mode
+  (keras/layers.py:67-72): batch statistics, parameter gradients of Dense and
+  BN layers, and the moving-average update."""
+  import ranking_b200 as tfr
+  m, d, hidden, out, act, input_bn, use_bn = shape
+  tower, params = _bn_tower_and_params(tfr, d, hidden, out, m, act, precision,
+                                       input_bn, use_bn)
+  g = torch.Generator().manual_seed(m)
+  x = torch.randn(m, d, generator=g) * 1.5 + 0.3
+  up = torch.randn(m, out, generator=g)
+  moving = oracle_api.scorer.init_bn_moving(d, hidden, input_bn, use_bn,
+                                            dtype=torch.float64)
+  tower.train()
+  y = tower(x.cuda())
+  (y * up.cuda()).sum().backward()
+  ref = oracle_api.scorer.tower_forward(
+      x.double(), params, activation=act, use_batch_norm=use_bn and bool(hidden),
+      input_batch_norm=input_bn, training=True, bn_moving=moving, momentum=0.9)
+  (ref * up.double()).sum().backward()
+  assert _rel_err(y, ref) <= tol, _rel_err(y, ref)
+  got, want = tower.flat.grad.detach().cpu().double(), _bn_flat_grad(params)
+  if act is None:
+    assert _rel_err(got, want) <= 10 * tol, _rel_err(got, want)
+  else:
+    # One ReLU input within rounding distance of 0 may take the other branch than in
+    # the fp64 oracle; through BN's batch coupling a single flip moves the whole
+    # gradient by O(1/sqrt(M)) of one column (measured 3e-3 at M = 700).  The
+    # identity-activation cases above pin the BN arithmetic to 1e-4.
+    l2 = float((got - want).norm() / want.norm())
+    assert l2 <= 1e-2, l2
+  for key, (mean, var) in moving.items():
+    gm, gv = tower.bn_moving(key)
+    assert _rel_err(gm, mean) <= 1e-5
+    assert _rel_err(gv, var) <= 1e-5
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+def test_tower_batch_norm_inference(oracle_api, precision):
+  """eval(): moving statistics normalise, nothing is updated; gradients flow
+  through the frozen statistics."""
+  import ranking_b200 as tfr
+  m, d, hidden = 600, 32, [64, 16]
+  tower, params = _bn_tower_and_params(tfr, d, hidden, 1, 3, None, precision,
+                                       True, True)
+  g = torch.Generator().manual_seed(5)
+  moving = oracle_api.scorer.init_bn_moving(d, hidden, True, True,
+                                            dtype=torch.float64)
+  with torch.no_grad():
+    for key, (mean, var) in moving.items():
+      mean.copy_(torch.randn(mean.shape, generator=g) * 0.3)
+      var.copy_(torch.rand(var.shape, generator=g) + 0.5)
+      gm, gv = tower.bn_moving(key)
+      gm.copy_(mean.float())
+      gv.copy_(var.float())
+  state_before = tower.bn_state.clone()
+  x = torch.randn(m, d, generator=g)
+  up = torch.randn(m, 1, generator=g)
+  tower.eval()
+  y = tower(x.cuda())
+  (y * up.cuda()).sum().backward()
+  ref = oracle_api.scorer.tower_forward(
+      x.double(), params, activation=None, use_batch_norm=True,
+      input_batch_norm=True, training=False, bn_moving=moving)
+  (ref * up.double()).sum().backward()
+  assert torch.equal(tower.bn_state, state_before)
+  assert _rel_err(y, ref) <= 5e-5
+  assert _rel_err(tower.flat.grad, _bn_flat_grad(params)) <= 5e-4
+
+
+def _dropout_keep_mask(seed, layer, m, n, rate):
+  """The mask tfr_mlp_fwd draws (include/tfr_b200.h, "dropout mask"): element i of
+  hidden layer `layer` is dropped iff u < rate, u = top 24 bits of
+  splitmix64(seed * 0x100000001B3 + layer + 1 + 0x9E3779B97F4A7C15 * (i + 1))."""
+  import numpy as np
+  with np.errstate(over='ignore'):
+    s = np.uint64(seed) * np.uint64(0x100000001B3) + np.uint64(layer + 1)
+    idx = np.arange(m * n, dtype=np.uint64)
+    z = s + np.uint64(0x9E3779B97F4A7C15) * (idx + np.uint64(1))
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    z = z ^ (z >> np.uint64(31))
+  u = (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+  keep = ~(u < np.float32(rate))
+  return torch.from_numpy(keep.reshape(m, n))
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32x3'])
+@pytest.mark.parametrize('act,use_bn', [('relu', False), (None, False), ('relu', True)])
+def test_tower_dropout(oracle_api, precision, act, use_bn):
+  """Dropout after every hidden activation (keras/layers.py:74-75).  The reference's
+  mask is random; ours is a documented counter hash of (seed, layer, element), so
+  the test replays exactly that mask through the oracle, and checks the drop rate,
+  the 1/(1-p) scale, determinism under a fixed seed, and eval()."""
+  import ranking_b200 as tfr
+  m, d, hidden, p = 2048, 32, [64, 32], 0.3
+  tower, params = _bn_tower_and_params(tfr, d, hidden, 1, 11, act, precision,
+                                       False, use_bn, dropout=p)
+  g = torch.Generator().manual_seed(9)
+  x = torch.randn(m, d, generator=g)
+  up = torch.randn(m, 1, generator=g)
+  tower.train()
+  tower._dropout_calls = 0
+  y = tower(x.cuda())
+  (y * up.cuda()).sum().backward()
+  seed = (tower._dropout_base << 32) | 1
+  keeps = [_dropout_keep_mask(seed, i, m, h, p) for i, h in enumerate(hidden)]
+  for k in keeps:
+    assert abs(1.0 - float(k.double().mean()) - p) < 0.02
+  ref = oracle_api.scorer.tower_forward(
+      x.double(), params, activation=act, use_batch_norm=use_bn,
+      keep_masks=[k.double() / (1 - p) for k in keeps])
+  (ref * up.double()).sum().backward()
+  assert _rel_err(y, ref) <= 1e-4, _rel_err(y, ref)
+  got, want = tower.flat.grad.detach().cpu().double(), _bn_flat_grad(params)
+  l2 = float((got - want).norm() / want.norm())
+  assert l2 <= 1e-3, l2
+  # same seed and call index -> same mask; next call -> another mask
+  tower._dropout_calls = 0
+  y2 = tower(x.cuda())
+  assert torch.equal(y2, y)
+  y3 = tower(x.cuda())
+  assert not torch.equal(y3, y)
+  # eval(): dropout is the identity
+  tower.eval()
+  ye = tower(x.cuda())
+  moving = None
+  if use_bn:
+    moving = {i: [t.detach().cpu().double() for t in tower.bn_moving(i)]
+              for i in range(len(hidden))}
+  refe = oracle_api.scorer.tower_forward(x.double(), params, activation=act,
+                                         use_batch_norm=use_bn, training=False,
+                                         bn_moving=moving)
+  assert _rel_err(ye, refe) <= 1e-4
+
+
+def test_fused_train_step_with_batch_norm(oracle_api):
+  """RankingTrainer over a BN tower: three Adagrad steps stay on the oracle's
+  trajectory (BN parameters are part of the flat buffer / single all-reduce)."""
+  import ranking_b200 as tfr
+  b, n, d, hidden = 16, 12, 24, [32, 16]
+  tower, params = _bn_tower_and_params(tfr, d, hidden, 1, 21, 'relu', 'fp32',
+                                       True, True)
+  loss = tfr.keras.losses.get('approx_ndcg_loss')
+  trainer = tfr.train.RankingTrainer(tower, loss, optimizer='adagrad',
+                                     learning_rate=0.05)
+  oloss = oracle_api.keras_losses.get('approx_ndcg_loss')
+  leaves = (params['dense_w'] + params['dense_b'] +
+            [params['in_bn_gamma'], params['in_bn_beta']] +
+            params['bn_gamma'] + params['bn_beta'])
+  accum = [torch.full_like(t, 0.1) for t in leaves]
+  g = torch.Generator().manual_seed(2)
+  for step in range(3):
+    x = torch.randn(b, n, d, generator=g)
+    y = torch.randint(0, 5, (b, n), generator=g).float()
+    y[:, -2:] = -1.0
+    got = float(trainer.train_step(x.cuda(), y.cuda()))
+    for t in leaves:
+      t.grad = None
+    mask = y >= 0
+    flat = oracle_api.scorer.tower_forward(
+        x.double().reshape(b * n, d), params, activation='relu',
+        use_batch_norm=True, input_batch_norm=True)
+    logits = oracle_api.scorer.restore_list(flat, mask)
+    ol = oloss(y.double(), logits)
+    ol.backward()
+    with torch.no_grad():
+      for t, a in zip(leaves, accum):
+        a.add_(t.grad * t.grad)
+        t.sub_(0.05 * t.grad / (a.sqrt() + 1e-7))
+    assert got == pytest.approx(float(ol.detach()), rel=2e-4, abs=1e-6)
+  want = torch.cat([torch.cat([w.reshape(-1), b_.reshape(-1)]) for w, b_ in
+                    zip(params['dense_w'], params['dense_b'])] +
+                   [params['in_bn_gamma'], params['in_bn_beta']] +
+                   [t for pair in zip(params['bn_gamma'], params['bn_beta'])
+                    for t in pair]).detach()
+  assert _rel_err(tower.flat.detach(), want) <= 2e-3
+
+
 def test_tower_tensor_core_rejects_unaligned_widths():
   import ranking_b200 as tfr
   tower, _ = _tower_and_params(tfr, 17, [33], 1, seed=1, precision='tf32x3')
