@@ -245,14 +245,17 @@ int tfr_mlp_bwd(const float* X, int M, const tfr_mlp_cfg* cfg,
  * uses (D[GM,GN] = A[GM,GK] * B[GK,GN]).  a_mn/b_mn select the operand storage
  * (0: K contiguous, i.e. A stored [GM,GK], B stored [GN,GK]; 1: M/N contiguous,
  * i.e. A stored [GK,GM], B stored [GK,GN]); passes 1 = TF32, 3 = 3xTF32 (fp32-
- * faithful); epi 0 store, 1 bias+act, 2 relu-mask by aux.  See csrc/tc_gemm.cuh. */
+ * faithful); epi 0 store, 1 bias+act (optionally writing ReLU sign bits to
+ * mask_bits_out, word [(col / 32) * GM + row]), 2 relu-mask by aux, 3 relu-mask by
+ * mask_bits_in.  See csrc/tc_gemm.cuh. */
 int tfr_tc_gemm(const float* A, int lda, const float* B, int ldb, const float* B_lo,
                 float* C, int ldc, int GM, int GN, int GK, int a_mn, int b_mn,
                 int passes, int split_b, int epi, const float* bias,
                 const float* aux, int act, int store_transposed, int splits,
-                size_t split_stride, void* stream);
+                size_t split_stride, uint32_t* mask_bits_out,
+                const uint32_t* mask_bits_in, void* stream);
 
-/* Profiling aid for the engine above: device buffer [num_SMs][8] of int64 that each
+/* Profiling aid for the engine above: device buffer [num_SMs][12] of int64 that each
  * GEMM launch fills with per-warp-role mbarrier wait cycles (NULL disables). */
 int tfr_tc_set_debug(long long* buf);
 

@@ -74,7 +74,7 @@ _SIGNATURES = {
     'tfr_mlp_fwd': (_I, [_P, _I, C.POINTER(MlpCfg), _P, _P, _P, _P, _I, _P]),
     'tfr_mlp_bwd': (_I, [_P, _I, C.POINTER(MlpCfg), _P, _P, _P, _P, _P, _I, _P]),
     'tfr_tc_gemm': (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I,
-                         _P, _P, _I, _I, _I, C.c_size_t, _P]),
+                         _P, _P, _I, _I, _I, C.c_size_t, _P, _P, _P]),
     'tfr_tc_set_debug': (_I, [_P]),
     'tfr_optimizer_step': (_I, [_P, _P, _P, C.c_size_t, _I, _F, _F, _F, _P]),
 }

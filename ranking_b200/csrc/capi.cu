@@ -85,6 +85,8 @@ int make_mlp_plan(const tfr_mlp_cfg* cfg, int M, MlpPlan* p) {
   for (int d = 0; d < L; ++d) {
     p->act_off[d] = w;
     w += align_up((size_t)M * p->dims[d + 1], 64);
+    p->bits_off[d] = w;
+    w += align_up((size_t)M * ((p->dims[d + 1] + 31) / 32), 64);
   }
   if (p->use_bn)
     for (int d = 0; d < L; ++d) {
@@ -141,7 +143,7 @@ int make_mlp_plan(const tfr_mlp_cfg* cfg, int M, MlpPlan* p) {
   p->out_rows = M > 0 ? ((M + 591) / 592 + 3) / 4 * 4 : 4;
   if (p->out_rows < 16) p->out_rows = 16;
   p->out_slots = (M + p->out_rows - 1) / p->out_rows;
-  p->oslot_stride = align_up((size_t)p->dims[L] * (p->dims[L + 1] + 1) + p->dims[L + 1], 64);
+  p->oslot_stride = align_up((size_t)p->dims[L] * (p->dims[L + 1] + 1) + p->dims[L + 1] + 4, 64);
   p->oslot_off = w;
   w += (size_t)p->out_slots * p->oslot_stride;
   p->ws_floats = w;

@@ -17,6 +17,7 @@ struct MlpPlan {
   size_t w_off[TFR_MLP_MAX_LAYERS], b_off[TFR_MLP_MAX_LAYERS], n_params;
   // workspace layout (floats)
   size_t act_off[TFR_MLP_MAX_LAYERS];  // post-activation output of hidden layer d
+  size_t bits_off[TFR_MLP_MAX_LAYERS]; // ReLU sign bits of hidden layer d: [ceil(h/32)][M] words
   size_t dz_off[2];                    // ping-pong dZ buffers
   size_t partial_off, partial_stride;  // split partials for dW / db
   int splits, rows_per_split;

@@ -219,14 +219,14 @@ reduce_partials_kernel(const float* __restrict__ partial, int splits, size_t str
 }
 
 // Output-layer backward, finer grain: one block per `rows_per` rows, RL row lanes x
-// K columns.  Per block b it writes slot[b] = { dW[K*O], db[O], csum[K] } where
+// K columns.  Per block b it writes slot[b] = { dW[K*O], db[O], pad to 4, csum[K] } where
 // csum[k] = sum_m dH[m, k] (the bias gradient of the last hidden layer).
 __global__ void __launch_bounds__(1024)
 out_layer_bwd2_kernel(const float* __restrict__ H, int M, int K, int O,
                       const float* __restrict__ W, const float* __restrict__ dS,
                       const uint8_t* __restrict__ mask, int act, int rows_per, int RL,
                       float* __restrict__ dH, float* __restrict__ slots, size_t slot_stride) {
-  extern __shared__ float sm[];   // [RL][K * (O + 1) + O]
+  extern __shared__ float sm[];   // [RL][round4(K * O + O) + K]
   const int KT = blockDim.x / RL;          // threads along k (>= K, multiple of 32)
   const int k = threadIdx.x % KT, rl = threadIdx.x / KT;
   const int mbeg = blockIdx.x * rows_per, mend = min(M, mbeg + rows_per);
@@ -261,14 +261,74 @@ out_layer_bwd2_kernel(const float* __restrict__ H, int M, int K, int O,
 #pragma unroll
     for (int o = 0; o < kMaxOut; ++o) db[o] += ds[o];
   }
-  const int per = K * (O + 1) + O;
+  const int co = (K * O + O + 3) & ~3;      // csum starts 16-byte aligned
+  const int per = co + K;
   float* mine = sm + (size_t)rl * per;
   if (k < K) {
     for (int o = 0; o < O; ++o) mine[k * O + o] = dw[o];
-    mine[K * O + O + k] = csum;
+    mine[co + k] = csum;
   }
   if (k == 0)
+    for (int i = K * O + O; i < co; ++i) mine[i] = 0.f;
+  if (k == 0)
     for (int o = 0; o < O; ++o) mine[K * O + o] = db[o];
+  __syncthreads();
+  float* out = slots + (size_t)blockIdx.x * slot_stride;
+  for (int i = threadIdx.x; i < per; i += blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < RL; ++r) acc += sm[(size_t)r * per + i];
+    out[i] = acc;
+  }
+}
+
+// Same contract for the common single-output scorer (O == 1, K % 4 == 0, K <= 1024):
+// a thread owns 4 consecutive k, so H is read and dH written as float4 and a block
+// keeps 4x more bytes in flight (the kernel is a pure HBM stream: read H, write dH).
+__global__ void __launch_bounds__(256)
+out_layer_bwd2_o1_kernel(const float4* __restrict__ H4, int M, int K4,
+                         const float4* __restrict__ W4, const float* __restrict__ dS,
+                         const uint8_t* __restrict__ mask, int act, int rows_per, int RL,
+                         float4* __restrict__ dH4, float* __restrict__ slots,
+                         size_t slot_stride) {
+  extern __shared__ float sm[];   // [RL][2K + 4]
+  const int k4 = threadIdx.x % K4, rl = threadIdx.x / K4;
+  const int K = K4 * 4;
+  const int mbeg = blockIdx.x * rows_per, mend = min(M, mbeg + rows_per);
+  const bool active = rl < RL;
+  const float4 w = active ? W4[k4] : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dw = make_float4(0.f, 0.f, 0.f, 0.f), cs = dw;
+  float db = 0.f;
+  if (active) {
+#pragma unroll 4
+    for (int m = mbeg + rl; m < mend; m += RL) {
+      const float ds = (mask && !mask[m]) ? 0.f : dS[m];
+      const float4 h = H4[(size_t)m * K4 + k4];
+      dw.x = fmaf(h.x, ds, dw.x); dw.y = fmaf(h.y, ds, dw.y);
+      dw.z = fmaf(h.z, ds, dw.z); dw.w = fmaf(h.w, ds, dw.w);
+      db += ds;
+      if (dH4) {
+        float4 dh = make_float4(ds * w.x, ds * w.y, ds * w.z, ds * w.w);
+        if (act == TFR_ACT_RELU) {
+          if (!(h.x > 0.f)) dh.x = 0.f;
+          if (!(h.y > 0.f)) dh.y = 0.f;
+          if (!(h.z > 0.f)) dh.z = 0.f;
+          if (!(h.w > 0.f)) dh.w = 0.f;
+        }
+        dH4[(size_t)m * K4 + k4] = dh;
+        cs.x += dh.x; cs.y += dh.y; cs.z += dh.z; cs.w += dh.w;
+      }
+    }
+  }
+  const int co = K + 4;                     // { dW[K], db, 3 x pad, csum[K] }
+  const int per = co + K;
+  if (active) {
+    float* mine = sm + (size_t)rl * per;
+    mine[4 * k4 + 0] = dw.x; mine[4 * k4 + 1] = dw.y;
+    mine[4 * k4 + 2] = dw.z; mine[4 * k4 + 3] = dw.w;
+    if (k4 == 0) { mine[K] = db; mine[K + 1] = 0.f; mine[K + 2] = 0.f; mine[K + 3] = 0.f; }
+    mine[co + 4 * k4 + 0] = cs.x; mine[co + 4 * k4 + 1] = cs.y;
+    mine[co + 4 * k4 + 2] = cs.z; mine[co + 4 * k4 + 3] = cs.w;
+  }
   __syncthreads();
   float* out = slots + (size_t)blockIdx.x * slot_stride;
   for (int i = threadIdx.x; i < per; i += blockDim.x) {
@@ -324,10 +384,57 @@ reduce2_kernel(const float* __restrict__ srcA, int slotsA, size_t strideA, size_
   }
 }
 
+// Vector variant: nA, nB, strides multiples of 4 and 16-byte aligned bases.  A thread
+// sums one float4 of outputs over its slot lane; 8 float4 outputs x 32 slot lanes.
+__global__ void __launch_bounds__(256)
+reduce2_vec_kernel(const float4* __restrict__ srcA, int slotsA, size_t strideA4, size_t nA4,
+                   const float4* __restrict__ srcB, int slotsB, size_t strideB4, size_t nB4,
+                   float4* __restrict__ out) {
+  __shared__ float4 part[32][9];
+  const int o = threadIdx.x & 7, sl = threadIdx.x >> 3;
+  const size_t i = (size_t)blockIdx.x * 8 + o;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < nA4) {
+#pragma unroll 4
+    for (int z = sl; z < slotsA; z += 32) {
+      const float4 v = srcA[(size_t)z * strideA4 + i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  } else if (i < nA4 + nB4) {
+    const size_t j = i - nA4;
+#pragma unroll 4
+    for (int z = sl; z < slotsB; z += 32) {
+      const float4 v = srcB[(size_t)z * strideB4 + j];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  part[sl][o] = acc;
+  __syncthreads();
+  if (sl == 0 && i < nA4 + nB4) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const float4 v = part[l][o];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    out[i] = t;
+  }
+}
+
 // ------------------------------------------------------------- host side ---
 int mlp_reduce2(const float* srcA, int slotsA, size_t strideA, size_t nA, const float* srcB,
                 int slotsB, size_t strideB, size_t nB, float* out, cudaStream_t st) {
   const size_t n = nA + nB;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (nA % 4 == 0 && nB % 4 == 0 && strideA % 4 == 0 && strideB % 4 == 0 && al16(srcA) &&
+      al16(srcB) && al16(out)) {
+    reduce2_vec_kernel<<<(unsigned)((n / 4 + 7) / 8), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(srcA), slotsA, strideA / 4, nA / 4,
+        reinterpret_cast<const float4*>(srcB), slotsB, strideB / 4, nB / 4,
+        reinterpret_cast<float4*>(out));
+    TFR_LAUNCH_OK();
+    return TFR_OK;
+  }
   reduce2_kernel<<<(unsigned)((n + 15) / 16), 256, 0, st>>>(srcA, slotsA, strideA, nA, srcB,
                                                           slotsB, strideB, nB, out);
   TFR_LAUNCH_OK();
@@ -337,11 +444,26 @@ int mlp_reduce2(const float* srcA, int slotsA, size_t strideA, size_t nA, const 
 int mlp_out_layer_bwd2(const float* H, int M, int K, int O, const float* W, const float* dS,
                        const uint8_t* mask, int act, int rows_per, float* dH, float* slots,
                        size_t slot_stride, cudaStream_t st) {
+  if (O == 1 && K % 4 == 0 && K <= 1024 && (reinterpret_cast<uintptr_t>(H) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (!dH || (reinterpret_cast<uintptr_t>(dH) & 15) == 0)) {
+    const int K4 = K / 4;
+    const int RL = 256 / K4;                       // >= 1 (K <= 1024)
+    const int blocks = (M + rows_per - 1) / rows_per;
+    const size_t smem = (size_t)RL * (2 * K + 4) * sizeof(float);
+    if (smem > 48 * 1024)
+      TFR_CUDA_OK(cudaFuncSetAttribute(out_layer_bwd2_o1_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    out_layer_bwd2_o1_kernel<<<blocks, 256, smem, st>>>(
+        reinterpret_cast<const float4*>(H), M, K4, reinterpret_cast<const float4*>(W), dS, mask,
+        act, rows_per, RL, reinterpret_cast<float4*>(dH), slots, slot_stride);
+    TFR_LAUNCH_OK();
+    return TFR_OK;
+  }
   const int K32 = ((K + 31) / 32) * 32;
   int RL = 1, threads = K32;
   if (K32 <= 256) { RL = 256 / K32; threads = RL * K32; }
   const int blocks = (M + rows_per - 1) / rows_per;
-  const size_t smem = (size_t)RL * (K * (O + 1) + O) * sizeof(float);
+  const size_t smem = (size_t)RL * (((K * O + O + 3) & ~3) + K) * sizeof(float);
   if (smem > 48 * 1024)
     TFR_CUDA_OK(cudaFuncSetAttribute(out_layer_bwd2_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -73,6 +73,9 @@ int mlp_tc_fwd(const float* X, int M, const MlpPlan& p, const float* params,
     g.epi = tc::EPI_BIAS_ACT; g.bias = params + p.b_off[d];
     g.act = p.use_bn ? TFR_ACT_NONE : p.activation;   // BN sits before the activation
     g.splits = 1; g.split_stride = 0;
+    // ReLU sign bits for the backward mask: 1 bit per activation instead of re-reading H
+    if (p.activation == TFR_ACT_RELU && !p.post())
+      g.mask_bits_out = reinterpret_cast<uint32_t*>(ws + p.bits_off[d]);
     rc = tc::gemm(g, st);
     if (rc) return rc;
     rc = mlp_hidden_post_fwd(d, M, p, params, ws, st);
@@ -119,7 +122,7 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
   }
   // Source of the bias partials of the layer being processed: per-slot column sums of
   // its dZ, produced by whichever kernel wrote that dZ.
-  const float* bsrc = oslots + (size_t)p.dims[L] * p.dims[L + 1] + p.dims[L + 1];
+  const float* bsrc = oslots + (((size_t)p.dims[L] * p.dims[L + 1] + p.dims[L + 1] + 3) & ~(size_t)3);
   int bslots = p.out_slots;
   size_t bstride = p.oslot_stride;
   for (int d = L - 1; d >= 0; --d) {
@@ -173,8 +176,9 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
       g.GM = M; g.GN = Kin; g.GK = Nout;
       g.a_mn = 0; g.b_mn = 0; g.passes = passes; g.split_b = 0;
       const bool masked = d > 0 && mact != TFR_ACT_NONE;
-      g.epi = masked ? tc::EPI_MASK_POS : tc::EPI_STORE;
-      g.aux = masked ? ws + p.act_off[d - 1] : nullptr; g.act = mact;
+      g.epi = masked ? tc::EPI_MASK_BITS : tc::EPI_STORE;
+      g.mask_bits_in = masked ? reinterpret_cast<const uint32_t*>(ws + p.bits_off[d - 1]) : nullptr;
+      g.act = mact;
       g.splits = 1; g.split_stride = 0;
       int cslots = 0;
       if (d > 0 && !p.post()) {

@@ -28,13 +28,14 @@ namespace tc {
 constexpr int kSplitWarps = 8;
 constexpr int kSplitThreads = kSplitWarps * 32;
 constexpr int kEpiWarp0 = 2 + kSplitWarps;          // first epilogue warp
-constexpr int kThreads = (kEpiWarp0 + 4) * 32;      // 448
-constexpr int kEpiSmemBytes = 4 * 32 * 37 * 4;   // per-epilogue-warp transpose buffers (>= [32][36])
+constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;   // 576
+constexpr int kEpiSmemBytes = 4 * 32 * 37 * 4;   // fallback stores (4 warps): transpose buffers
+constexpr int kEpiSmemBytes2 = kEpiWarps * 4096; // TMA-store path: one staging tile per warp
 constexpr int BM = 128;       // UMMA M (cta_group::1)
 constexpr int BK = 32;        // fp32 elements per 128-byte swizzle span
 constexpr int kATileBytes = BM * BK * 4;   // 16 KB
 constexpr int kMaxStages = 4;
-constexpr unsigned kSmemBudget = 227 * 1024 - 2048 - kEpiSmemBytes;
 
 // ------------------------------------------------------------------ PTX -------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -89,6 +90,26 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
       "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// smem -> global tile store through the async proxy (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0,
+                                             int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() {   // smem of all groups has been read
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read1() {   // ... of all but the newest group
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() {     // all groups fully complete
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -135,6 +156,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
         "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
         "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -191,14 +222,22 @@ struct KernelArgs {
   float* colsum;       // optional [4 * gridDim.x][colsum_stride]: column sums of everything
   int colsum_stride;   //   this CTA stored, per 32-row quarter (bias gradients)
   int colsum_cols;     // GN rounded up to 4 (0 when colsum is off): smem accumulators
-  long long* dbg;      // optional [gridDim.x][8] wait-cycle counters per warp role
+  long long* dbg;      // optional [gridDim.x][12] wait-cycle counters per warp role
   int vec_ok;          // C / aux / bias / colsum allow 16-byte vector access
+  int tma_store;       // row-major unsplit output: epilogue stores 32x32 blocks by TMA
+  int epi_bufs;        // staging tiles per epilogue warp in that mode (1 or 2)
+  int epi_smem_bytes;  // bytes of the epilogue staging region
+  int colsum_regs;     // column sums kept in registers (single n tile, tma_store)
+  int bias_cols;       // floats of the bias copy staged in smem (tma_store + EPI_BIAS_ACT)
+  uint32_t* bits_out;        // optional (tma_store): ReLU sign bits of the stored values,
+  const uint32_t* bits_in;   //   word [(col / 32) * GM + row]; EPI_MASK_BITS reads them
 };
 
 template <bool A_MN, bool B_MN, int PASSES, bool SPLIT_B>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmBlo, const KernelArgs args) {
+               const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
+               const KernelArgs args) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms.
   // (pointer arithmetic, not an integer round trip: keeps the shared address space so
@@ -210,9 +249,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stage_bytes = a_bytes + args.b_tile_bytes * kBCopies;
   const int S = args.stages;
   unsigned char* epi_smem = smem + static_cast<size_t>(S) * stage_bytes;   // 4 x [32][33] floats
-  float* cacc_base = reinterpret_cast<float*>(epi_smem + kEpiSmemBytes);   // [4][colsum_cols]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + kEpiSmemBytes +
-                                               4 * args.colsum_cols * sizeof(float));
+  float* cacc_base = reinterpret_cast<float*>(epi_smem + args.epi_smem_bytes);   // [4][colsum_cols]
+  float* sbias = cacc_base + kEpiWarps * args.colsum_cols;                       // [bias_cols]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(
+      epi_smem + args.epi_smem_bytes +
+      (kEpiWarps * args.colsum_cols + args.bias_cols) * sizeof(float));
   uint64_t* full = bars;                         // TMA landed
   uint64_t* split = bars + kMaxStages;           // hi/lo split done
   uint64_t* empty = bars + 2 * kMaxStages;       // MMAs that read the stage retired
@@ -231,6 +272,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     if (PASSES == 3 && !SPLIT_B) prefetch_tmap(&tmBlo);
+    if (args.tma_store) prefetch_tmap(&tmC);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&split[s], kSplitWarps);
@@ -238,7 +280,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 128);
+      mbar_init(&acc_empty[i], kEpiWarps * 32);
     }
     fence_barrier_init();
   }
@@ -303,8 +345,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       if (args.dbg) {
-        args.dbg[blockIdx.x * 8 + 0] = w_empty;
-        args.dbg[blockIdx.x * 8 + 1] = clock64() - t_start;
+        args.dbg[blockIdx.x * 12 + 0] = w_empty;
+        args.dbg[blockIdx.x * 12 + 1] = clock64() - t_start;
       }
     }
   } else if (warp == 1) {
@@ -357,9 +399,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else mbar_arrive(&acc_full[ab]);         // empty k range: epilogue stores zeros
       }
       if (args.dbg) {
-        args.dbg[blockIdx.x * 8 + 2] = w_acc;
-        args.dbg[blockIdx.x * 8 + 3] = w_full;
-        args.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
+        args.dbg[blockIdx.x * 12 + 2] = w_acc;
+        args.dbg[blockIdx.x * 12 + 3] = w_full;
+        args.dbg[blockIdx.x * 12 + 4] = clock64() - t_start;
       }
     }
   } else if (warp < kEpiWarp0) {
@@ -413,31 +455,177 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) mbar_arrive(&split[s]);   // one arrival per splitter warp
         }
       }
-      if (args.dbg && t == 0) args.dbg[blockIdx.x * 8 + 5] = w_tma;
+      if (args.dbg && t == 0) args.dbg[blockIdx.x * 12 + 5] = w_tma;
     }
   } else {
-    // ---------------------------------------------------- epilogue (warps 10..13)
-    // TMEM lane quarter is fixed by warp id % 4.  While these warps drain buffer
-    // `ab`, the MMA warp already fills the other buffer with the next tile.
+    // ---------------------------------------------------- epilogue (warps 10..17)
+    // TMEM lane quarter is fixed by warp id % 4; the two warps of a quarter take
+    // alternate 32-column chunks (TMA-store mode; the single-warp epilogue is
+    // instruction/latency-bound at ~2k cycles per chunk).  The fallback stores
+    // (transposed / split-K partials: one store per long k loop) use warps 0..3 only.
+    // While these warps drain buffer `ab`, the MMA warp already fills the other one.
     const int q = warp & 3;
-    float* tb = reinterpret_cast<float*>(epi_smem) + (warp - kEpiWarp0) * (32 * 37);
+    const int ew = warp - kEpiWarp0;          // 0..7
+    const int half = ew >> 2;                 // which of the two warps of the quarter
+    float* tb = reinterpret_cast<float*>(epi_smem) + (ew & 3) * (32 * 37);
     // per-warp running column sums over all tiles of this CTA (one slot per CTA and
     // quarter instead of one per tile: 592 slots to reduce instead of 6400)
-    float* cacc = cacc_base + (warp - kEpiWarp0) * args.colsum_cols;
+    float* cacc = cacc_base + ew * args.colsum_cols;
     for (int c = lane; c < args.colsum_cols; c += 32) cacc[c] = 0.f;
     __syncwarp();
+    if (args.bias_cols) {   // bias copy, zero past GN; named barrier over the epilogue warps
+      for (int c = ew * 32 + lane; c < args.bias_cols; c += kEpiWarps * 32)
+        sbias[c] = c < args.GN ? __ldg(args.bias + c) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+    }
     uint32_t tcount = 0;
-    long long w_accfull = 0;
+    float ccol[8];   // register column sums: lane = column of chunk k (colsum_regs mode)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ccol[k] = 0.f;
+    long long w_accfull = 0, w_ld = 0, w_smem = 0, w_st = 0, w_x = 0;
     const long long t_start = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       int m0, n0, z, kb_begin, nkb;
       decode(tile, m0, n0, z, kb_begin, nkb);
       const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+      // ReLU sign bits of this warp's 32 rows (one word per row and 32-column chunk);
+      // the first chunk's word is fetched before the accumulator is even complete, the
+      // following ones one chunk ahead.
+      auto load_bits = [&](int c0) -> uint32_t {
+        const int col = n0 + c0, row = m0 + q * 32 + lane;
+        return (c0 < args.n_umma && col < args.GN && row < args.GM)
+                   ? __ldg(args.bits_in + static_cast<size_t>(col >> 5) * args.GM + row)
+                   : 0u;
+      };
+      uint32_t mword = 0, mword_next = 0;
+      if (args.tma_store && args.epi == EPI_MASK_BITS) mword = load_bits(half * 32);
       w_accfull += mbar_wait(&acc_full[ab], aph);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + ab * args.tmem_cols +
                               (static_cast<uint32_t>(q * 32) << 16);
       float* C = args.C + static_cast<size_t>(z) * args.split_stride;
+      if (args.tma_store) {
+        // Row-major output through TMA: lane = row; each 32-column chunk is drained in two
+        // 16-column halves (register budget: 96/thread with 18 warps).  Bias / ReLU / mask
+        // run in registers, the block goes to a 128B-swizzled [32][32] staging tile
+        // (conflict-free STS.128) and one elected lane hands it to the async proxy, so
+        // the warp never waits on global stores.
+        unsigned char* stg = epi_smem + ew * 4096;
+        const int row = m0 + q * 32 + lane;
+        const bool warp_live = m0 + q * 32 < args.GM;
+        int last_c0 = 0;
+        for (int c = 0; c < args.n_umma && n0 + c < args.GN; c += 32) last_c0 = c;
+        if (half * 32 > last_c0) {      // nothing for this warp in a one-chunk tile
+          tc_fence_before();
+          mbar_arrive(&acc_empty[ab]);
+          continue;
+        }
+        const int my_last = last_c0 - (((last_c0 >> 5) & 1) != half ? 32 : 0);
+#pragma unroll 1
+        for (int c0 = half * 32; c0 <= last_c0; c0 += 64) {
+          const int colb = n0 + c0;
+          if (args.epi == EPI_MASK_BITS) mword_next = load_bits(c0 + 64);
+          uint32_t word_out = 0;
+#pragma unroll 1
+          for (int hf = 0; hf < 2; ++hf) {
+            const long long tp0 = args.dbg ? clock64() : 0;
+            uint32_t v[16];
+            tmem_ld16(tmem_d + c0 + hf * 16, v);
+            const int colh = colb + hf * 16;
+            tmem_ld_wait();
+            if (hf == 1 && c0 == my_last) {   // accumulator drained: the MMA warp may refill it
+              tc_fence_before();
+              mbar_arrive(&acc_empty[ab]);
+            }
+            const long long tp1 = args.dbg ? clock64() : 0;
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+            if (nkb == 0) {            // empty k range: the accumulator was never written
+#pragma unroll
+              for (int j = 0; j < 16; ++j) x[j] = 0.f;
+            }
+            if (args.epi == EPI_BIAS_ACT) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 b4 = *reinterpret_cast<const float4*>(sbias + colh + 4 * j);
+                x[4 * j + 0] += b4.x; x[4 * j + 1] += b4.y;
+                x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+              }
+              if (args.act == TFR_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
+              }
+              if (args.bits_out) {
+                uint32_t w16 = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w16 |= (x[j] > 0.f ? 1u : 0u) << j;
+                word_out |= w16 << (hf * 16);
+              }
+            } else if (args.epi == EPI_MASK_BITS) {
+              const uint32_t w16 = mword >> (hf * 16);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                // bfe.s32 of a 1-bit field: 0 or 0xffffffff
+                int m;
+                asm("bfe.s32 %0, %1, %2, 1;" : "=r"(m) : "r"(w16), "r"(j));
+                x[j] = __uint_as_float(__float_as_uint(x[j]) & static_cast<uint32_t>(m));
+              }
+            }
+            const long long tpa = args.dbg ? clock64() : 0;
+            if (hf == 0) {
+              // the previous TMA store of this warp must have finished reading the tile
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
+            }
+            const long long tpb = args.dbg ? clock64() : 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(stg + lane * 128 + (((hf * 4 + j) ^ (lane & 7)) << 4)) =
+                  make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            if (args.dbg) {
+              w_ld += tp1 - tp0;
+              w_smem += tpa - tp1;    // register math
+              w_st += tpb - tpa;      // wait for the staging tile
+            }
+          }
+          const long long tpc = args.dbg ? clock64() : 0;
+          if (args.epi == EPI_BIAS_ACT && args.bits_out) {
+            if (args.GN - colb < 32) word_out &= (1u << (args.GN - colb)) - 1u;   // columns >= GN
+            if (row < args.GM)
+              args.bits_out[static_cast<size_t>(colb >> 5) * args.GM + row] = word_out;
+          }
+          mword = mword_next;
+          fence_proxy_async();
+          __syncwarp();
+          if (warp_live && lane == 0) {
+            tma_store_2d(&tmC, stg, colb, m0 + q * 32);
+            bulk_commit();
+          }
+          if (args.colsum) {
+            // lane = column: sum the 32 rows of the staged block (rows past GM are zero)
+            const float* tbf = reinterpret_cast<const float*>(stg);
+            float cs = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              cs += tbf[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
+            if (args.colsum_regs) {
+              const int ci = c0 >> 5;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) ccol[k] += ci == k ? cs : 0.f;
+            } else if (colb + lane < args.colsum_cols) {
+              cacc[colb + lane] += cs;
+            }
+          }
+          if (args.dbg) w_x += clock64() - tpc;   // fence + store issue + column sums
+        }
+        continue;   // acc_empty already signalled
+      }
+      if (ew >= 4) {                   // fallback stores are done by warps 0..3
+        tc_fence_before();
+        mbar_arrive(&acc_empty[ab]);
+        continue;
+      }
       if (args.store_transposed) {
         // lane = row: consecutive lanes hit consecutive addresses of C^T.
         const int row = m0 + q * 32 + lane;
@@ -478,6 +666,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (masked) load_keep(0, keep);
         for (int c0 = 0; c0 < args.n_umma; c0 += 32) {
           uint32_t v[32];
+          const long long tp0 = args.dbg ? clock64() : 0;
           tmem_ld32(tmem_d + c0, v);
           // prefetch the next block's mask while this one is transposed and stored
           if (masked && c0 + 32 < args.n_umma) load_keep(c0 + 32, keep_next);
@@ -487,6 +676,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (args.epi == EPI_BIAS_ACT && col_ok)
             bv = __ldg(reinterpret_cast<const float4*>(args.bias + col));
           tmem_ld_wait();
+          const long long tp1 = args.dbg ? clock64() : 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 t4;
@@ -501,6 +691,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float4 xs[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) xs[i] = tb4[(i * 4 + r4) * 9 + c4];
+          const long long tp2 = args.dbg ? clock64() : 0;
           float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -542,6 +733,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 8; ++i) keep[i] = keep_next[i];
           }
           __syncwarp();
+          if (args.dbg) {
+            const long long tp3 = clock64();
+            w_ld += tp1 - tp0;
+            w_smem += tp2 - tp1;
+            w_st += tp3 - tp2;
+          }
         }
       } else {
         // Row-major store, scalar fallback (unaligned leading dimension / width).
@@ -576,16 +773,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[ab]);   // 128 arrivals free the accumulator buffer
+      mbar_arrive(&acc_empty[ab]);   // all epilogue threads arrive: buffer is free
     }
+    if (args.tma_store && lane == 0) bulk_wait_all();
     if (args.colsum) {
       __syncwarp();
-      float* dst = args.colsum + static_cast<size_t>(blockIdx.x * 4 + q) * args.colsum_stride;
-      for (int c = lane; c < args.GN; c += 32) dst[c] = cacc[c];
+      float* dst = args.colsum + static_cast<size_t>(blockIdx.x * kEpiWarps + ew) * args.colsum_stride;
+      if (args.colsum_regs) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k * 32 + lane < args.GN) dst[k * 32 + lane] = ccol[k];
+      } else {
+        for (int c = lane; c < args.GN; c += 32) dst[c] = cacc[c];
+      }
     }
     if (args.dbg && threadIdx.x == kEpiWarp0 * 32) {
-      args.dbg[blockIdx.x * 8 + 6] = w_accfull;
-      args.dbg[blockIdx.x * 8 + 7] = clock64() - t_start;
+      args.dbg[blockIdx.x * 12 + 6] = w_accfull;
+      args.dbg[blockIdx.x * 12 + 7] = clock64() - t_start;
+      args.dbg[blockIdx.x * 12 + 8] = w_ld;
+      args.dbg[blockIdx.x * 12 + 9] = w_smem;
+      args.dbg[blockIdx.x * 12 + 10] = w_st;
+      args.dbg[blockIdx.x * 12 + 11] = w_x;
     }
   }
   tc_fence_before();
@@ -643,10 +851,11 @@ static long long* g_dbg = nullptr;   // set by tfr_tc_set_debug (profiling aid)
 
 template <bool A_MN, bool B_MN, int PASSES, bool SPLIT_B>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo,
-                  const KernelArgs& ka, dim3 grid, size_t smem, cudaStream_t st) {
+                  const CUtensorMap& tmC, const KernelArgs& ka, dim3 grid, size_t smem,
+                  cudaStream_t st) {
   auto kern = tc_gemm_kernel<A_MN, B_MN, PASSES, SPLIT_B>;
   TFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, kThreads, smem, st>>>(tmA, tmB, tmBlo, ka);
+  kern<<<grid, kThreads, smem, st>>>(tmA, tmB, tmBlo, tmC, ka);
   TFR_LAUNCH_OK();
   return TFR_OK;
 }
@@ -674,13 +883,27 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   const int b_tile_bytes = g.b_mn ? ((n_umma + 31) / 32) * bk * 128 : n_umma * 128;
   const int copies = g.passes == 3 ? 2 : 1;
   const int stage_bytes = (a_tile_bytes + b_tile_bytes) * copies;
-  const int colsum_cols = g.colsum ? ((g.GN + 3) / 4) * 4 : 0;
+  int splits = g.splits < 1 ? 1 : g.splits;
+  // TMA-store epilogue: row-major, unsplit output with 16-byte aligned rows.
+  static const bool no_tma_store = getenv("TFR_TC_NO_TMA_STORE") != nullptr;
+  const bool tma_store =
+      !no_tma_store && g.epi != EPI_MASK_POS && !g.store_transposed && splits == 1 &&
+      g.ldc % 4 == 0 && g.GN % 4 == 0 && (reinterpret_cast<uintptr_t>(g.C) & 15) == 0 &&
+      (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) &&
+      (n_tiles == 1 || n_umma % 32 == 0);
+  const bool colsum_regs = tma_store && g.colsum && n_tiles == 1;
+  const int colsum_cols = (g.colsum && !colsum_regs) ? ((g.GN + 3) / 4) * 4 : 0;
   TFR_REQUIRE(colsum_cols <= 1024, "tc gemm: colsum output supports GN <= 1024");
-  int stages = (int)((kSmemBudget - 4 * colsum_cols * sizeof(float)) / stage_bytes);
+  // Two staging tiles per epilogue warp when that does not cost a pipeline stage.
+  const int bias_cols = (tma_store && g.epi == EPI_BIAS_ACT) ? ((n_tiles * n_umma + 31) / 32) * 32 : 0;
+  const size_t fixed1 = kEpiSmemBytes + kEpiWarps * colsum_cols * sizeof(float);
+  const size_t fixed2 = kEpiSmemBytes2 + (kEpiWarps * colsum_cols + bias_cols) * sizeof(float);
+  const size_t budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;
+  const int epi_smem_bytes = tma_store ? kEpiSmemBytes2 : kEpiSmemBytes;
+  int stages = (int)((budget - (tma_store ? fixed2 : fixed1)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   TFR_REQUIRE(stages >= 1, "tc gemm: tile does not fit shared memory");
   const int nkb_total = (g.GK + bk - 1) / bk;
-  int splits = g.splits < 1 ? 1 : g.splits;
   int kb_per_split = (nkb_total + splits - 1) / splits;
   // (a split whose k range is empty stores zeros, so any split count is legal)
 
@@ -728,6 +951,21 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
               "tc gemm: colsum output needs a row-major, unsplit store");
   TFR_REQUIRE(g.epi != EPI_BIAS_ACT || g.bias, "tc gemm: bias required");
   TFR_REQUIRE(g.epi != EPI_MASK_POS || g.aux, "tc gemm: aux required");
+  ka.tma_store = tma_store;
+  ka.epi_bufs = 1;
+  ka.epi_smem_bytes = epi_smem_bytes;
+  ka.colsum_regs = colsum_regs;
+  ka.bias_cols = bias_cols;
+  ka.bits_out = g.mask_bits_out;
+  ka.bits_in = g.mask_bits_in;
+  TFR_REQUIRE(!(g.mask_bits_out || g.epi == EPI_MASK_BITS) || ka.tma_store,
+              "tc gemm: ReLU sign bits need the row-major TMA-store epilogue");
+  TFR_REQUIRE(g.epi != EPI_MASK_BITS || g.mask_bits_in, "tc gemm: mask_bits_in required");
+  CUtensorMap tmC = tmA;
+  if (ka.tma_store) {
+    rc = encode_2d(&tmC, g.C, (uint64_t)g.GN, (uint64_t)g.GM, (uint64_t)g.ldc, 32, false);
+    if (rc) return rc;
+  }
 
   ka.m_tiles = (g.GM + BM - 1) / BM;
   ka.n_tiles = n_tiles;
@@ -740,12 +978,13 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
     TFR_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
-  const size_t smem = (size_t)stages * stage_bytes + kEpiSmemBytes +
-                      4 * colsum_cols * sizeof(float) + 1024 /*align*/ + 256 /*barriers*/;
-  if (g.colsum_slots_out) *g.colsum_slots_out = 4 * (int)grid.x;
+  const size_t smem = (size_t)stages * stage_bytes + epi_smem_bytes +
+                      (kEpiWarps * colsum_cols + bias_cols) * sizeof(float) + 1024 /*align*/ +
+                      256 /*barriers*/;
+  if (g.colsum_slots_out) *g.colsum_slots_out = kEpiWarps * (int)grid.x;
 
 #define TFR_TC_LAUNCH(AMN, BMN, P, SB) \
-  return launch<AMN, BMN, P, SB>(tmA, tmB, tmBlo, ka, grid, smem, st)
+  return launch<AMN, BMN, P, SB>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st)
   const int key = (g.a_mn ? 8 : 0) | (g.b_mn ? 4 : 0) | (g.passes == 3 ? 2 : 0) |
                   ((g.passes == 3 && g.split_b) ? 1 : 0);
   switch (key) {
@@ -783,8 +1022,10 @@ extern "C" int tfr_tc_gemm(const float* A, int lda, const float* B, int ldb, con
                            float* C, int ldc, int GM, int GN, int GK, int a_mn, int b_mn,
                            int passes, int split_b, int epi, const float* bias, const float* aux,
                            int act, int store_transposed, int splits, size_t split_stride,
+                           uint32_t* mask_bits_out, const uint32_t* mask_bits_in,
                            void* stream) {
   tfr::tc::GemmDesc g{};
+  g.mask_bits_out = mask_bits_out; g.mask_bits_in = mask_bits_in;
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.B_lo = B_lo; g.C = C; g.ldc = ldc;
   g.GM = GM; g.GN = GN; g.GK = GK; g.a_mn = a_mn; g.b_mn = b_mn; g.passes = passes;
   g.split_b = split_b; g.epi = epi; g.bias = bias; g.aux = aux; g.act = act;

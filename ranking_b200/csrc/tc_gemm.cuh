@@ -7,7 +7,7 @@
 namespace tfr {
 namespace tc {
 
-enum Epi { EPI_STORE = 0, EPI_BIAS_ACT = 1, EPI_MASK_POS = 2 };
+enum Epi { EPI_STORE = 0, EPI_BIAS_ACT = 1, EPI_MASK_POS = 2, EPI_MASK_BITS = 3 };
 
 // D[GM, GN] = A[GM, GK] * B[GK, GN]  (fp32 in / fp32 out, TF32 tensor cores)
 //
@@ -36,8 +36,11 @@ struct GemmDesc {
   int splits;                    // split the GK loop over blockIdx.z; split z writes to
   size_t split_stride;           //   C + z * split_stride (floats); k range rounded to 32
   float* colsum;                 // optional: column sums of everything each CTA stored, slot
-  int colsum_stride;             //   (cta * 4 + 32-row quarter), row pitch in floats;
-  int* colsum_slots_out;         //   receives the number of slots written (4 * CTAs)
+  int colsum_stride;             //   (cta * 8 + epilogue warp), row pitch in floats;
+  int* colsum_slots_out;         //   receives the number of slots written (8 * CTAs)
+  // ReLU sign bits, word [(col / 32) * GM + row] (bit j = column 32 * (col / 32) + j):
+  uint32_t* mask_bits_out;       //   EPI_BIAS_ACT: written next to C (stored value > 0)
+  const uint32_t* mask_bits_in;  //   EPI_MASK_BITS: C = bit ? C : 0  (replaces `aux`)
 };
 
 // Returns a tfr_status.  Requirements (checked): lda/ldb multiples of 4 floats,

@@ -18,8 +18,19 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _pack_bits(keep):
+  """[gm, gn] bool -> int32 words [(gn + 31) // 32, gm], bit j = column 32 * w + j."""
+  gm, gn = keep.shape
+  nw = (gn + 31) // 32
+  pad = torch.zeros(gm, nw * 32, dtype=torch.int64)
+  pad[:, :gn] = keep.long()
+  words = (pad.reshape(gm, nw, 32) << torch.arange(32)).sum(2)      # [gm, nw] in [0, 2^32)
+  words = torch.where(words >= 2 ** 31, words - 2 ** 32, words)
+  return words.t().contiguous().to(torch.int32)
+
+
 def run_gemm(gm, gn, gk, a_mn, b_mn, passes, split_b, epi=0, act=0, transposed=0,
-             splits=1, seed=0):
+             splits=1, seed=0, want_bits=False):
   import ranking_b200  # noqa: F401
   from ranking_b200 import _C
   g = torch.Generator().manual_seed(seed)
@@ -33,7 +44,7 @@ def run_gemm(gm, gn, gk, a_mn, b_mn, passes, split_b, epi=0, act=0, transposed=0
     ref = ref + bias.double()
     if act == 1:
       ref = torch.relu(ref)
-  elif epi == 2 and act == 1:
+  elif epi in (2, 3) and act == 1:
     ref = torch.where(aux.double() > 0, ref, torch.zeros_like(ref))
   a_store = (A.t().contiguous() if a_mn else A.contiguous()).cuda()
   if passes == 3 and not split_b:
@@ -53,14 +64,21 @@ def run_gemm(gm, gn, gk, a_mn, b_mn, passes, split_b, epi=0, act=0, transposed=0
     C = torch.full((gn, gm) if transposed else (gm, gn), float('nan'), device='cuda')
   ldc = gm if transposed else gn
   bias_d, aux_d = bias.cuda(), aux.cuda()    # keep alive until the sync below
+  bits_out = bits_in = None
+  if want_bits:
+    bits_out = torch.full(((gn + 31) // 32, gm), -1, dtype=torch.int32, device='cuda')
+  if epi == 3:
+    bits_in = _pack_bits(aux > 0).cuda()
   rc = _C.lib.tfr_tc_gemm(
       _C.ptr(a_store), a_store.shape[1], _C.ptr(b_store), b_store.shape[1],
       _C.ptr(b_lo_store), _C.ptr(C), ldc, gm, gn, gk, a_mn, b_mn, passes, split_b,
       epi, _C.ptr(bias_d), _C.ptr(aux_d), act, transposed, splits, stride,
-      _C.stream())
+      _C.ptr(bits_out), _C.ptr(bits_in), _C.stream())
   _C.check(rc)
   torch.cuda.synchronize()
   out = C.double().cpu()
+  if want_bits:
+    assert torch.equal(bits_out.cpu(), _pack_bits(C.cpu() > 0))
   if splits > 1:
     out = out.sum(0)
   if transposed:
@@ -92,6 +110,14 @@ def test_tc_gemm_epilogues_and_splits():
   assert err <= 2e-6, err
   err, _, _ = run_gemm(384, 128, 64, 0, 0, 3, 0, epi=2, act=1)
   assert err <= 2e-6, err
+  # ReLU sign bits written by the forward epilogue / consumed by the backward one
+  for shape in [(384, 256, 136), (1000, 128, 256), (300, 136, 64), (200, 64, 128)]:
+    err, _, _ = run_gemm(*shape, 0, 1, 3, 0, epi=1, act=1, want_bits=True)
+    assert err <= 2e-6, (shape, err)
+    err, _, _ = run_gemm(*shape, 0, 0, 3, 0, epi=3, act=1)
+    assert err <= 2e-6, (shape, err)
+    err, _, _ = run_gemm(*shape, 0, 0, 1, 0, epi=3, act=1)
+    assert err <= 2e-3, (shape, err)
   # dW-shaped: both operands MN-major, long K split over CTAs, transposed store
   err, _, _ = run_gemm(256, 136, 4096, 1, 1, 3, 1, transposed=1, splits=4)
   assert err <= 2e-6, err

@@ -10,10 +10,11 @@ import ranking_b200 as tfr
 from ranking_b200 import _C
 
 M = 204800
-dbg = torch.zeros(148, 8, dtype=torch.int64, device='cuda')
+dbg = torch.zeros(148, 12, dtype=torch.int64, device='cuda')
 _C.lib.tfr_tc_set_debug(ctypes.c_void_p(dbg.data_ptr()))
 NAMES = ['prod_wait_empty', 'prod_total', 'mma_wait_accempty', 'mma_wait_operands',
-         'mma_total', 'split_wait_tma', 'epi_wait_accfull', 'epi_total']
+         'mma_total', 'split_wait_tma', 'epi_wait_accfull', 'epi_total', 'epi_tmem_ld',
+         'epi_math', 'epi_wait_stage', 'epi_sts_fence']
 
 
 def run(name, gm, gn, gk, a_mn, b_mn, passes, split_b, epi, transposed=0, splits=1):
@@ -22,6 +23,8 @@ def run(name, gm, gn, gk, a_mn, b_mn, passes, split_b, epi, transposed=0, splits
   Blo = torch.randn_like(B) * 1e-4 if (passes == 3 and not split_b) else None
   bias = torch.randn(gn, device='cuda')
   aux = torch.randn(gm, gn, device='cuda')
+  bits = torch.randint(-2 ** 31, 2 ** 31 - 1, ((gn + 31) // 32, gm), dtype=torch.int32,
+                       device='cuda')
   stride = gm * gn if splits > 1 else 0
   C = torch.empty(max(splits, 1) * gm * gn, device='cuda')
   ldc = gm if transposed else gn
@@ -32,7 +35,8 @@ def run(name, gm, gn, gk, a_mn, b_mn, passes, split_b, epi, transposed=0, splits
     _C.check(_C.lib.tfr_tc_gemm(_C.ptr(A), A.shape[1], _C.ptr(B), B.shape[1], _C.ptr(Blo),
                                 _C.ptr(C), ldc, gm, gn, gk, a_mn, b_mn, passes, split_b, epi,
                                 _C.ptr(bias), _C.ptr(aux), 1, transposed, splits, stride,
-                                _C.stream()))
+                                _C.ptr(bits if epi == 1 else None),
+                                _C.ptr(bits if epi == 3 else None), _C.stream()))
     e1.record()
     torch.cuda.synchronize()
   d = dbg.double().mean(0).tolist()
@@ -40,13 +44,15 @@ def run(name, gm, gn, gk, a_mn, b_mn, passes, split_b, epi, transposed=0, splits
         '  '.join('%s=%.0fk' % (n, v / 1e3) for n, v in zip(NAMES, d)), flush=True)
 
 
-for passes in (3, 1):
+for passes in (3,):
   print('passes', passes)
   run('fwd L1 136->256', M, 256, 136, 0, 1, passes, 0, 1)
   run('fwd L2 256->128', M, 128, 256, 0, 1, passes, 0, 1)
   run('fwd L3 128->64', M, 64, 128, 0, 1, passes, 0, 1)
   run('dH1 128->256 mask', M, 256, 128, 0, 0, passes, 0, 2)
   run('dH2 64->128 mask', M, 128, 64, 0, 0, passes, 0, 2)
+  run('dH1 128->256 bits', M, 256, 128, 0, 0, passes, 0, 3)
+  run('dH2 64->128 bits', M, 128, 64, 0, 0, passes, 0, 3)
   run('dH1 store only', M, 256, 128, 0, 0, passes, 0, 0)
   run('dW1^T 256x136 (swapped)', 256, 136, M, 1, 1, passes, 1 if passes == 3 else 0, 0, 1, 100)
   run('dW2 256x128', 256, 128, M, 1, 1, passes, 1 if passes == 3 else 0, 0, 0, 100)
