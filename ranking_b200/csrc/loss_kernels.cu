@@ -91,23 +91,22 @@ __device__ inline ListView carve(unsigned char* base, int N) {
 // with the worst valid item are broken randomly.  Here invalid entries are
 // strictly last and ties are broken by index (shuffle_ties=False semantics).
 __device__ inline void compute_ranks(const ListView& v, int N, float /*zmin*/) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
-  for (int i = warp; i < N; i += nwarps) {
+  // One thread per item; the (validity, score) reads of the partners are smem broadcasts.
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const bool vi = v.mv[i];
     const float si = v.z[i];
     int cnt = 0;
-    for (int j = lane; j < N; j += 32) {
+#pragma unroll 4
+    for (int j = 0; j < N; ++j) {
       const bool vj = v.mv[j];
       const float sj = v.z[j];
-      bool before;
-      if (vi != vj) before = vj;
-      else if (!vi) before = j < i;
-      else before = (sj > si) || (sj == si && j < i);
+      const bool same = vi == vj;
+      // different validity: the valid one precedes; both invalid: by index
+      const bool by_score = (sj > si) || (sj == si && j < i);
+      const bool before = same ? (vi ? by_score : j < i) : vj;
       cnt += before;
     }
-    cnt = warp_sum_int(cnt);
-    if (lane == 0) v.rank[i] = cnt + 1;
+    v.rank[i] = cnt + 1;
   }
 }
 
@@ -117,18 +116,19 @@ __device__ inline void compute_ranks(const ListView& v, int N, float /*zmin*/) {
 template <typename DiscFn>
 __device__ inline float ideal_dcg(const float* cl, const float* gain, int N,
                                   int topn, float* red, DiscFn disc) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
+  // One thread per item: its rank among the labels by counting (label reads are smem
+  // broadcasts), then every lane evaluates its own discount.  (A warp-per-row count
+  // with a lane-0 discount serialises ~50 transcendental instructions per row.)
   float part = 0.f;
-  for (int i = warp; i < N; i += nwarps) {
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const float li = cl[i];
     int cnt = 0;
-    for (int j = lane; j < N; j += 32) {
+#pragma unroll 4
+    for (int j = 0; j < N; ++j) {
       const float lj = cl[j];
       cnt += (lj > li) || (lj == li && j < i);
     }
-    cnt = warp_sum_int(cnt);
-    if (lane == 0 && cnt + 1 <= topn) part += gain[i] * disc(cnt + 1);
+    if (cnt + 1 <= topn) part += gain[i] * disc(cnt + 1);
   }
   return block_sum(part, red);
 }
@@ -235,6 +235,11 @@ __device__ __forceinline__ float exp2f_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {   // one MUFU.RCP (~1 ulp), no fix-up
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float log2f_approx(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -250,7 +255,7 @@ __device__ __forceinline__ void phi_eval(float x, float& f, float& df) {
     // relu(-x) + log1p(exp(-|x|)); d/dx = -sigmoid(-x)   (losses_impl.py:936-940)
     // MUFU path: e = 2^(-|x| log2 e), log1p(e) = lg2(1 + e) ln 2, 1/(1+e) by rcp
     const float e = exp2f_approx(-fabsf(x) * kLog2e);
-    const float rc = __frcp_rn(1.f + e);
+    const float rc = rcp_approx(1.f + e);
     f = fmaxf(-x, 0.f) + log2f_approx(1.f + e) * kLn2;
     df = -(x >= 0.f ? e * rc : rc);
   } else if (PHI == TFR_PHI_HINGE) {
@@ -260,7 +265,7 @@ __device__ __forceinline__ void phi_eval(float x, float& f, float& df) {
   } else {
     // sigmoid(-x); d/dx = -sigmoid(x) sigmoid(-x)       (losses_impl.py:954-958)
     const float e = exp2f_approx(-fabsf(x) * kLog2e);
-    const float inv = __frcp_rn(1.f + e);
+    const float inv = rcp_approx(1.f + e);
     f = x > 0.f ? e * inv : inv;
     df = -e * inv * inv;
   }
@@ -394,7 +399,8 @@ sorted_ranks_kernel(const float* __restrict__ scores, const float* __restrict__ 
 // (lane l always sees the columns l + 32 t).  T = ceil(N / 32) column registers;
 // T == 0 selects the generic both-ends loop for N > 1024.
 template <int MODE, int T>
-__global__ void __launch_bounds__(kLossThreads, T <= 8 ? 7 : 2)   // 7 CTAs/SM: B=1024 in one wave
+// 7 warps x 7 CTAs/SM: B = 1024 lists in one wave (224 threads measured faster than 192 or 256)
+__global__ void __launch_bounds__(T > 0 && T <= 8 ? 224 : kLossThreads, T > 0 && T <= 8 ? 7 : 2)
 approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
                    const float* __restrict__ item_w, int w_per_item,
                    const uint8_t* __restrict__ mask, int N, float temperature,
@@ -448,26 +454,37 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
     for (int t = 0; t < T; ++t) {
       const int j = lane + 32 * t;
       col[t] = 0.f;
-      zc[t] = j < N ? v.z[j] * kLog2e : 0.f;
+      // columns past N sit at -huge: sigmoid(z_j - z_i) = 0 without a bounds test
+      zc[t] = j < N ? v.z[j] * kLog2e : -3.0e38f;
     }
-    for (int i = warp; i < N; i += nwarps) {
-      const float zi = v.z[i] * kLog2e;
-      float acc = 0.f;
-      const int t0 = i >> 5;
+    // Rows are walked tile by tile (t0 compile-time), so the column loop t = t0..T-1 has
+    // static bounds: no divergence bookkeeping, static register indexing, and only the
+    // diagonal tile pays for the j > i mask.  2 MUFU + 9 ALU per pair: MUFU-bound.
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        if (t < t0) continue;                       // warp-uniform: block left of the diagonal
-        const int j = lane + 32 * t;
-        const bool on = (t > t0 || j > i) && j < N;
-        const float d = zc[t] - zi;
-        const float e = exp2f_approx(-fabsf(d));
-        const float rc = __frcp_rn(1.f + e);
-        const float big = rc, small = e * rc;       // sigmoid(|d|), sigmoid(-|d|)
-        acc += on ? (d >= 0.f ? big : small) : 0.f;    // sigmoid(z_j - z_i) -> r_i
-        col[t] += on ? (d >= 0.f ? small : big) : 0.f; // sigmoid(z_i - z_j) -> r_j
+    for (int t0 = 0; t0 < T; ++t0) {
+      const int iend = min(N, 32 * t0 + 32);
+      for (int i = 32 * t0 + warp; i < iend; i += nwarps) {
+        const float zi = v.z[i] * kLog2e;
+        float acc = 0.f;
+#pragma unroll
+        for (int t = t0; t < T; ++t) {
+          const float d = zc[t] - zi;
+          const float e = exp2f_approx(-fabsf(d));
+          const float big = rcp_approx(1.f + e);      // sigmoid(|d|)
+          const float small = e * big;                // sigmoid(-|d|)
+          float sa = d >= 0.f ? big : small;          // sigmoid(z_j - z_i) -> r_i
+          float sb = d >= 0.f ? small : big;          // sigmoid(z_i - z_j) -> r_j
+          if (t == t0) {
+            const bool on = lane + 32 * t0 > i;
+            sa = on ? sa : 0.f;
+            sb = on ? sb : 0.f;
+          }
+          acc += sa;
+          col[t] += sb;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) r[i] = acc;
       }
-      acc = warp_sum(acc);
-      if (lane == 0) r[i] = acc;
     }
 #pragma unroll
     for (int t = 0; t < T; ++t) {
@@ -488,7 +505,7 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
       for (int j = lane; j < N; j += 32) {
         const float d = v.z[j] - zi;
         const float e = __expf(-fabsf(d));
-        const float rc = __frcp_rn(1.f + e);
+        const float rc = rcp_approx(1.f + e);
         acc += d >= 0.f ? rc : e * rc;
       }
       acc = warp_sum(acc);
@@ -541,26 +558,27 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
       for (int t = 0; t < T; ++t) {
         const int j = lane + 32 * t;
         col[t] = 0.f;
-        zc[t] = j < N ? v.z[j] * kLog2e : 0.f;
+        zc[t] = j < N ? v.z[j] * kLog2e : -3.0e38f;
         cc[t] = j < N ? c[j] : 0.f;
       }
-      for (int k = warp; k < N; k += nwarps) {
-        const float zk = v.z[k] * kLog2e, ck = c[k];
-        float acc = 0.f;
-        const int t0 = k >> 5;
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-          if (t < t0) continue;
-          const int i = lane + 32 * t;
-          const bool on = (t > t0 || i > k) && i < N;
-          const float e = exp2f_approx(-fabsf(zk - zc[t]));
-          const float rc = __frcp_rn(1.f + e);
-          const float term = on ? (cc[t] - ck) * (e * rc * rc) : 0.f;
-          acc += term;        // -> grad_k
-          col[t] -= term;     // -> grad_i (antisymmetric)
+      for (int t0 = 0; t0 < T; ++t0) {
+        const int kend = min(N, 32 * t0 + 32);
+        for (int k = 32 * t0 + warp; k < kend; k += nwarps) {
+          const float zk = v.z[k] * kLog2e, ck = c[k];
+          float acc = 0.f;
+#pragma unroll
+          for (int t = t0; t < T; ++t) {
+            const float e = exp2f_approx(-fabsf(zk - zc[t]));   // columns past N: e = 0
+            const float rc = rcp_approx(1.f + e);
+            float term = (cc[t] - ck) * (e * rc * rc);           // (c_i - c_k) sigmoid'
+            if (t == t0) term = lane + 32 * t0 > k ? term : 0.f;
+            acc += term;        // -> grad_k
+            col[t] -= term;     // -> grad_i (antisymmetric)
+          }
+          acc = warp_sum(acc);
+          if (lane == 0) gacc[k] = acc;
         }
-        acc = warp_sum(acc);
-        if (lane == 0) gacc[k] = acc;
       }
 #pragma unroll
       for (int t = 0; t < T; ++t) {
@@ -580,7 +598,7 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
           const float zk = v.z[k], ck = c[k];
           for (int i = lane; i < N; i += 32) {
             const float e = __expf(-fabsf(zk - v.z[i]));
-            const float rc = __frcp_rn(1.f + e);
+            const float rc = rcp_approx(1.f + e);
             acc += (c[i] - ck) * (e * rc * rc);
           }
         }
@@ -842,7 +860,7 @@ extern "C" int tfr_approx_loss_fwd_bwd(const float* scores, const float* labels,
   {                                                                                         \
     rc = prep_smem(approx_loss_kernel<MODE_, T_>, smem);                                    \
     if (rc) return rc;                                                                      \
-    approx_loss_kernel<MODE_, T_><<<B, kLossThreads, smem, st>>>(                           \
+    approx_loss_kernel<MODE_, T_><<<B, (T_ > 0 && T_ <= 8) ? 224 : kLossThreads, smem, st>>>(                           \
         scores, labels, item_w, w_per_item, mask, N, temperature, grad_scale,               \
         scale_by_weight, grad, loss, weight);                                               \
   }
