@@ -301,11 +301,15 @@ def run_gpu(args):
     achieved = step_fl * B / (gemm_ms * 1e-3) / 1e12
     peak = peaks['bf16_tflops_sustained']
     # HBM view of the same kernels: X read by fwd L1 and dW1; every hidden
-    # activation written once and read by the next layer, its dW and its mask;
-    # every dZ written once and read by its dW and the next dH.
+    # activation written once and read by the next layer and its dW (ReLU masks
+    # travel as 1 bit per activation: written by the forward, read by the dZ GEMM);
+    # every dZ written once and read by its dW and the next dZ GEMM, except dZ1
+    # which only feeds dW1.
     dims = [D] + HIDDEN
     act_bytes = sum(dims[1:]) * 4 * N           # per list, one pass over H1..H3
-    gemm_bytes_per_list = 2 * D * 4 * N + 4 * act_bytes + 3 * act_bytes
+    bit_bytes = 2 * sum(dims[1:-1]) * N // 8    # sign bits of H1, H2: write + read
+    gemm_bytes_per_list = (2 * D * 4 * N + 3 * act_bytes +
+                           3 * act_bytes - dims[1] * 4 * N + bit_bytes)
     hbm_achieved = gemm_bytes_per_list * B / (gemm_ms * 1e-3) / 1e9
     traffic = None      # dram__bytes_read + write of these kernels, from the committed ncu capture
     tpath = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
