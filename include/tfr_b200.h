@@ -149,6 +149,34 @@ int tfr_softmax_loss_fwd_bwd(const float* scores, const float* labels,
                              float* loss, float* weight, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * K3b  Pointwise and remaining listwise losses, fused forward + backward.
+ *   SIGMOID_CE     SigmoidCrossEntropyLoss  losses_impl.py:1425-1446
+ *   MEAN_SQUARED   MeanSquaredLoss          :1449-1469   (pass temperature = 1)
+ *     item weight w_i = (label_i >= 0 ? w : 0) * mask_i  (:1287-1293);
+ *     row[b,i] = loss_i * w_i (optional), loss[b] = sum_i row, weight[b] = sum_i w_i,
+ *     nonzero[b] = #{w_i != 0}; grad = grad_scale * d loss[b] / d scores.
+ *   UNIQUE_SOFTMAX UniqueSoftmaxLoss        :1250-1281
+ *   LIST_MLE       ListMLELoss              :1541-1576; rank_weight (optional, [N]) is
+ *     ListMLELambdaWeight's discount of ranks 1..N (:457-480).  Label ties are ordered
+ *     by index (the reference shuffles them randomly); invalid items are last.
+ *     loss[b] = list loss, weight[b] = label-weighted mean of the item weights
+ *     (:1004-1015, 1 without weights); grad = grad_scale * d loss[b] / d scores.
+ * ------------------------------------------------------------------------- */
+typedef enum {
+  TFR_MISC_SIGMOID_CE = 0,
+  TFR_MISC_MEAN_SQUARED = 1,
+  TFR_MISC_UNIQUE_SOFTMAX = 2,
+  TFR_MISC_LIST_MLE = 3
+} tfr_misc_loss;
+
+int tfr_misc_loss_fwd_bwd(const float* scores, const float* labels,
+                          const float* item_w, int w_per_item,
+                          const uint8_t* mask, int B, int N, float temperature,
+                          int kind, const float* rank_weight, float grad_scale,
+                          float* grad, float* row, float* loss, float* weight,
+                          float* nonzero, void* stream);
+
+/* ---------------------------------------------------------------------------
  * K4  NDCG@k and MRR@k for several cut-offs in one launch; per-list shared-memory
  * bitonic sort, ties by index, invalid entries last.  Replaces
  * metrics_impl.py:63-151, 228-266, 429-459, 631-670 and utils.py:115-164.

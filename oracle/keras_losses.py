@@ -173,7 +173,44 @@ class ApproxMRRLoss(_ListwiseLoss):
   _default_temperature = 0.1
 
 
+class UniqueSoftmaxLoss(_ListwiseLoss):
+  """keras/losses.py:946-1005."""
+  _impl = losses_impl.UniqueSoftmaxLoss
+
+
+class ListMLELoss(_ListwiseLoss):
+  """keras/losses.py:1008-1090."""
+  _impl = losses_impl.ListMLELoss
+
+
+class ListMLELambdaWeight(losses_impl.ListMLELambdaWeight):
+  """keras/losses.py:233-244."""
+
+  def __init__(self, rank_discount_fn=None, **kwargs):
+    super().__init__(rank_discount_fn)
+
+
+class SigmoidCrossEntropyLoss(_RankingLoss):
+  """keras/losses.py:1499-1546."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None):
+    super().__init__(reduction, name)
+    self._loss = losses_impl.SigmoidCrossEntropyLoss(name=name)
+
+
+class MeanSquaredLoss(_RankingLoss):
+  """keras/losses.py:1549-1600."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None):
+    super().__init__(reduction, name)
+    self._loss = losses_impl.MeanSquaredLoss(name=name)
+
+
 _KEY_TO_CLS = {
+    'unique_softmax_loss': UniqueSoftmaxLoss,
+    'list_mle_loss': ListMLELoss,
+    'sigmoid_cross_entropy_loss': SigmoidCrossEntropyLoss,
+    'mean_squared_loss': MeanSquaredLoss,
     'pairwise_hinge_loss': PairwiseHingeLoss,
     'pairwise_logistic_loss': PairwiseLogisticLoss,
     'pairwise_soft_zero_one_loss': PairwiseSoftZeroOneLoss,
@@ -189,6 +226,7 @@ def get(loss, reduction=Reduction.AUTO, lambda_weight=None, name=None, **kwargs)
   if loss not in _KEY_TO_CLS:
     raise ValueError('unsupported loss: {}'.format(loss))
   kw = dict(reduction=reduction, name=name, **kwargs)
-  if loss not in ('approx_ndcg_loss', 'approx_mrr_loss'):
+  if loss not in ('approx_ndcg_loss', 'approx_mrr_loss', 'sigmoid_cross_entropy_loss',
+                  'mean_squared_loss'):
     kw['lambda_weight'] = lambda_weight
   return _KEY_TO_CLS[loss](**kw)

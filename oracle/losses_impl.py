@@ -559,3 +559,129 @@ class ApproxMRRLoss(_ListwiseLoss):
     rr = (rr * labels).sum(-1, keepdim=True)
     mrr = rr / labels.sum(-1, keepdim=True)
     return -mrr, nonzero_mask.to(logits.dtype).reshape(-1, 1)
+
+
+# ----------------------------------------------------------------------------
+# Pointwise losses (losses_impl.py:1284-1469)
+# ----------------------------------------------------------------------------
+class _PointwiseLoss(_RankingLoss):
+  """losses_impl.py:1284-1321."""
+
+  def _normalize_weights_impl(self, labels, weights):
+    labels = torch.as_tensor(labels)
+    if weights is None:
+      weights = 1.
+    weights = torch.as_tensor(weights, dtype=labels.dtype)
+    return torch.where(utils.is_label_valid(labels),
+                       torch.ones_like(labels) * weights,
+                       torch.zeros_like(labels))
+
+  def compute_per_list(self, labels, logits, weights, mask=None):
+    labels, logits, weights, mask = self._prepare_and_validate_params(
+        labels, logits, weights, mask)
+    losses, loss_weights = self._compute_unreduced_loss_impl(
+        labels, logits, mask)
+    weights = self._normalize_weights_impl(labels, weights) * loss_weights
+    per_list_weights = weights.sum(1)
+    per_list_losses = (losses * weights).sum(1)
+    return _divide_no_nan(per_list_losses, per_list_weights), per_list_weights
+
+
+class SigmoidCrossEntropyLoss(_PointwiseLoss):
+  """losses_impl.py:1425-1446."""
+
+  def __init__(self, name=None, temperature=1.0):
+    super().__init__(name, None, temperature)
+
+  def _compute_unreduced_loss_impl(self, labels, logits, mask=None):
+    if mask is None:
+      mask = utils.is_label_valid(labels)
+    labels = torch.where(mask, labels, torch.zeros_like(labels))
+    logits = torch.where(mask, logits, torch.zeros_like(logits))
+    # tf.nn.sigmoid_cross_entropy_with_logits: max(x, 0) - x z + log(1 + exp(-|x|))
+    losses = torch.clamp(logits, min=0) - logits * labels + torch.log1p(
+        torch.exp(-logits.abs()))
+    return losses, mask.to(logits.dtype)
+
+
+class MeanSquaredLoss(_PointwiseLoss):
+  """losses_impl.py:1449-1469 (temperature is not used)."""
+
+  def __init__(self, name=None):
+    super().__init__(name, None, 1.0)
+
+  def _compute_unreduced_loss_impl(self, labels, logits, mask=None):
+    if mask is None:
+      mask = utils.is_label_valid(labels)
+    labels = torch.where(mask, labels, torch.zeros_like(labels))
+    logits = torch.where(mask, logits, torch.zeros_like(logits))
+    return (labels - logits) ** 2, mask.to(logits.dtype)
+
+
+# ----------------------------------------------------------------------------
+# UniqueSoftmaxLoss (losses_impl.py:1250-1281), ListMLELoss (:1541-1576)
+# ----------------------------------------------------------------------------
+class UniqueSoftmaxLoss(_ListwiseLoss):
+
+  def _compute_unreduced_loss_impl(self, labels, logits, mask=None):
+    if mask is None:
+      mask = utils.is_label_valid(labels)
+    labels = torch.where(mask, labels, torch.zeros_like(labels))
+    logits = torch.where(mask, logits,
+                         math.log(_EPSILON) * torch.ones_like(logits))
+    pairwise_labels, _ = _pairwise_comparison(labels, logits, mask)
+    denominator_logits = logits.unsqueeze(1) * pairwise_labels
+    denominator_logits = torch.cat([denominator_logits, logits.unsqueeze(2)], 2)
+    denominator_mask = torch.cat(
+        [pairwise_labels, torch.ones_like(logits).unsqueeze(2)], 2)
+    denominator_logits = torch.where(
+        denominator_mask > 0.0, denominator_logits,
+        -1e-3 + denominator_logits.min() * torch.ones_like(denominator_logits))
+    logits_max = denominator_logits.max(dim=-1, keepdim=True).values
+    denominator_logits = denominator_logits - logits_max
+    logits = logits - logits_max.squeeze(-1)
+    gains = torch.pow(2.0, labels) - 1
+    per_doc_softmax = -logits + torch.log(
+        (torch.exp(denominator_logits) * denominator_mask).sum(-1))
+    losses = (per_doc_softmax * gains).sum(1, keepdim=True)
+    return losses, torch.ones_like(losses)
+
+
+class ListMLELambdaWeight(_LambdaWeight):
+  """losses_impl.py:457-480."""
+
+  def __init__(self, rank_discount_fn):
+    self._rank_discount_fn = rank_discount_fn
+
+  def individual_weights(self, labels, ranks):
+    labels = torch.as_tensor(labels)
+    return torch.ones_like(labels) * self._rank_discount_fn(
+        torch.as_tensor(ranks).to(labels.dtype))
+
+
+class ListMLELoss(_ListwiseLoss):
+  """losses_impl.py:1541-1576.  The reference breaks label ties randomly
+  (`shuffle_ties=True, seed=37`); this restatement breaks them by index, which is
+  one of the orders the reference can draw."""
+
+  def _compute_unreduced_loss_impl(self, labels, logits, mask=None):
+    if mask is None:
+      mask = utils.is_label_valid(labels)
+    labels = torch.where(mask, labels, torch.zeros_like(labels))
+    logits = torch.where(mask, logits,
+                         math.log(_EPSILON) * torch.ones_like(logits))
+    scores = torch.where(
+        mask, labels,
+        labels.min(dim=1, keepdim=True).values - 1e-6 * torch.ones_like(labels))
+    sorted_labels, sorted_logits = utils.sort_by_scores(scores, [labels, logits])
+    raw_max = sorted_logits.max(dim=1, keepdim=True).values
+    sorted_logits = sorted_logits - raw_max
+    sums = torch.flip(torch.cumsum(torch.flip(torch.exp(sorted_logits), [1]), 1),
+                      [1])
+    sums = torch.log(sums) - sorted_logits
+    if isinstance(self._lambda_weight, ListMLELambdaWeight):
+      b, n = sorted_labels.shape
+      ranks = (torch.arange(n) + 1).unsqueeze(0).expand(b, n)
+      sums = sums * self._lambda_weight.individual_weights(sorted_labels, ranks)
+    nll = sums.sum(1, keepdim=True)
+    return nll, torch.ones_like(nll)

@@ -65,6 +65,8 @@ _SIGNATURES = {
     'tfr_softmax_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _P, _I, _I, _F,
                                       C.POINTER(LambdaCfg), _F, _I, _P, _P, _P,
                                       _P]),
+    'tfr_misc_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _P, _I, _I, _F, _I, _P, _F, _P, _P, _P, _P,
+                                   _P, _P]),
     'tfr_rank_metrics': (_I, [_P, _P, _P, _I, _P, _I, _I, C.POINTER(C.c_int32),
                               _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'tfr_weighted_sum': (_I, [_P, _P, _I, _F, _P, _P]),

@@ -703,6 +703,203 @@ weighted_sum_kernel(const float* __restrict__ v, const float* __restrict__ w, in
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// K3b  Remaining RankingLossKey members that share the one-CTA-per-list staging:
+//   pointwise  SigmoidCrossEntropyLoss / MeanSquaredLoss  (losses_impl.py:1284-1469)
+//   listwise   UniqueSoftmaxLoss (:1250-1281), ListMLELoss (:1541-1576)
+// ---------------------------------------------------------------------------
+
+// Exclusive prefix sums of a[0..N) in place (block-wide): every thread scans a
+// contiguous chunk, chunk totals are scanned through `red`-style shuffles.
+__device__ inline void block_exclusive_scan(float* a, int N, float* scratch /*[blockDim.x]*/) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int per = (N + nt - 1) / nt;
+  const int beg = min(N, tid * per), end = min(N, beg + per);
+  float s = 0.f;
+  for (int i = beg; i < end; ++i) s += a[i];
+  scratch[tid] = s;
+  __syncthreads();
+  if (tid == 0) {              // nt <= 256 chunk totals: serial scan is ~0.3 us
+    float run = 0.f;
+    for (int t = 0; t < nt; ++t) {
+      const float x = scratch[t];
+      scratch[t] = run;
+      run += x;
+    }
+  }
+  __syncthreads();
+  float run = scratch[tid];
+  for (int i = beg; i < end; ++i) {
+    const float x = a[i];
+    a[i] = run;
+    run += x;
+  }
+  __syncthreads();
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kLossThreads)
+misc_loss_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                 const float* __restrict__ item_w, int w_per_item,
+                 const uint8_t* __restrict__ mask, int N, float temperature,
+                 const float* __restrict__ rank_weight, float grad_scale,
+                 float* __restrict__ grad, float* __restrict__ row, float* __restrict__ loss,
+                 float* __restrict__ weight, float* __restrict__ nonzero) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ListView v = carve(smem_raw, N);
+  float* scratch = reinterpret_cast<float*>(smem_raw + ((list_smem_bytes(N) + 15) & ~(size_t)15));
+  const int b = blockIdx.x, tid = threadIdx.x;
+  load_list(v, scores, labels, item_w, w_per_item, mask, b, N, temperature);
+  const size_t off = (size_t)b * N;
+  const float gs = grad_scale / temperature;
+
+  if (KIND == TFR_MISC_SIGMOID_CE || KIND == TFR_MISC_MEAN_SQUARED) {
+    // item weight = (label valid ? w : 0) * mask   (:1287-1293, :1443 / :1469)
+    float sl = 0.f, sw = 0.f, nz = 0.f;
+    for (int i = tid; i < N; i += blockDim.x) {
+      const bool mvalid = v.mv[i];
+      const float z = mvalid ? v.z[i] : 0.f;
+      const float l = mvalid ? v.l[i] : 0.f;
+      const float w = mvalid ? v.w[i] : 0.f;
+      float f, df;
+      if (KIND == TFR_MISC_SIGMOID_CE) {
+        // max(z, 0) - z l + log1p(exp(-|z|));  d/dz = sigmoid(z) - l
+        const float e = expf(-fabsf(z));
+        f = fmaxf(z, 0.f) - z * l + log1pf(e);
+        df = (z >= 0.f ? 1.f / (1.f + e) : e / (1.f + e)) - l;
+      } else {
+        const float d = z - l;
+        f = d * d;
+        df = 2.f * d;
+      }
+      if (row) row[off + i] = f * w;
+      if (grad) grad[off + i] = mvalid ? df * w * gs : 0.f;
+      sl += f * w;
+      sw += w;
+      nz += w != 0.f ? 1.f : 0.f;
+    }
+    sl = block_sum(sl, v.red);
+    sw = block_sum(sw, v.red);
+    nz = block_sum(nz, v.red);
+    if (tid == 0) {
+      loss[b] = sl;
+      if (weight) weight[b] = sw;
+      if (nonzero) nonzero[b] = nz;
+    }
+    return;
+  }
+
+  // ---- listwise: cleaned labels / logits and the list weight (:1004-1015) ----
+  float wl = 0.f, lvsum = 0.f;
+  for (int i = tid; i < N; i += blockDim.x) {
+    const bool mvalid = v.mv[i];
+    const float lv = v.lv[i] ? v.l[i] : 0.f;
+    wl += v.w[i] * lv;              // v.w is already 0 for invalid labels
+    lvsum += lv;
+    if (!mvalid) {
+      v.z[i] = kLogEpsilon;
+      v.l[i] = 0.f;
+    }
+  }
+  wl = block_sum(wl, v.red);
+  lvsum = block_sum(lvsum, v.red);
+  const float list_w = item_w ? (lvsum != 0.f ? wl / lvsum : 0.f) : 1.f;
+  __syncthreads();
+
+  if (KIND == TFR_MISC_UNIQUE_SOFTMAX) {
+    // L = sum_i g_i [ -z_i + log( e^{z_i} + sum_{j: l_j < l_i, both valid} e^{z_j} ) ]
+    float* g = v.g;                                   // 2^l - 1
+    float* m = v.disc;                                // row maxima
+    float* q = reinterpret_cast<float*>(v.rank);      // g_i / S_i
+    float part = 0.f;
+    for (int i = tid; i < N; i += blockDim.x) {
+      const float li = v.l[i], zi = v.z[i];
+      const bool vi = v.mv[i];
+      float mi = zi;
+      for (int j = 0; j < N; ++j)
+        if (vi && v.mv[j] && li > v.l[j]) mi = fmaxf(mi, v.z[j]);
+      float S = expf(zi - mi);
+      for (int j = 0; j < N; ++j)
+        if (vi && v.mv[j] && li > v.l[j]) S += expf(v.z[j] - mi);
+      const float gi = exp2f(li) - 1.f;
+      part += gi * (-zi + mi + logf(S));
+      g[i] = gi;
+      m[i] = mi;
+      q[i] = gi / S;
+    }
+    part = block_sum(part, v.red);   // barrier publishes g / m / q
+    if (grad) {
+      for (int k = tid; k < N; k += blockDim.x) {
+        const float lk = v.l[k], zk = v.z[k];
+        const bool vk = v.mv[k];
+        float acc = -g[k] + expf(zk - m[k]) * q[k];
+        for (int i = 0; i < N; ++i)
+          if (vk && v.mv[i] && v.l[i] > lk) acc += expf(zk - m[i]) * q[i];
+        grad[off + k] = vk ? acc * gs : 0.f;
+      }
+    }
+    if (tid == 0) {
+      loss[b] = part;
+      if (weight) weight[b] = list_w;
+    }
+    return;
+  }
+
+  // ---- ListMLE: order by label (valid first, ties by index; the reference shuffles
+  // ties randomly and parks invalid items at min(label) - 1e-6), then
+  //   L = sum_p w_p [ log sum_{m >= p} e^{z_(m)} - z_(p) ]
+  float* zs = v.g;                                   // sorted logits (shifted by the max)
+  float* C = v.disc;                                 // suffix sums of exp
+  float* A = v.w;                                    // prefix sums of w_p / C_p
+  int* pos = v.rank;                                 // position of item i
+  float zmax = -CUDART_INF_F;
+  for (int i = tid; i < N; i += blockDim.x) {
+    const float li = v.l[i];
+    const bool vi = v.mv[i];
+    int cnt = 0;
+    for (int j = 0; j < N; ++j) {
+      const bool vj = v.mv[j];
+      const float lj = v.l[j];
+      const bool before = vi == vj ? ((vi && lj > li) || ((!vi || lj == li) && j < i)) : vj;
+      cnt += before;
+    }
+    pos[i] = cnt;
+    zmax = fmaxf(zmax, v.z[i]);
+  }
+  zmax = block_max(zmax, v.red);
+  for (int i = tid; i < N; i += blockDim.x) zs[pos[i]] = v.z[i] - zmax;
+  __syncthreads();
+  // suffix sums: exclusive prefix over the reversed order, plus the own term
+  for (int p = tid; p < N; p += blockDim.x) C[N - 1 - p] = expf(zs[p]);
+  __syncthreads();
+  block_exclusive_scan(C, N, scratch);               // C[r] = sum_{r' < r} e_rev[r']
+  float part = 0.f;
+  for (int p = tid; p < N; p += blockDim.x) {
+    const float suffix = C[N - 1 - p] + expf(zs[p]);  // sum_{m >= p}
+    const float wp = rank_weight ? rank_weight[p] : 1.f;
+    part += wp * (logf(suffix) - zs[p]);
+    A[p] = wp / suffix;
+  }
+  part = block_sum(part, v.red);
+  if (grad) {
+    __syncthreads();
+    block_exclusive_scan(A, N, scratch);             // A[p] = sum_{k < p} w_k / C_k
+    for (int i = tid; i < N; i += blockDim.x) {
+      const int p = pos[i];
+      const float wp = rank_weight ? rank_weight[p] : 1.f;
+      const float e = expf(zs[p]);
+      const float suffix = C[N - 1 - p] + e;
+      const float gsum = A[p] + wp / suffix;          // inclusive prefix
+      grad[off + i] = v.mv[i] ? (e * gsum - wp) * gs : 0.f;
+    }
+  }
+  if (tid == 0) {
+    loss[b] = part;
+    if (weight) weight[b] = list_w;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
@@ -903,6 +1100,40 @@ extern "C" int tfr_softmax_loss_fwd_bwd(const float* scores, const float* labels
   softmax_loss_kernel<<<B, kLossThreads, smem, (cudaStream_t)stream>>>(
       scores, labels, item_w, w_per_item, mask, N, temperature, lam, grad_scale,
       scale_by_weight, grad, loss, weight);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+extern "C" int tfr_misc_loss_fwd_bwd(const float* scores, const float* labels,
+                                     const float* item_w, int w_per_item, const uint8_t* mask,
+                                     int B, int N, float temperature, int kind,
+                                     const float* rank_weight, float grad_scale, float* grad,
+                                     float* row, float* loss, float* weight, float* nonzero,
+                                     void* stream) {
+  int rc = check_list_args(scores, labels, B, N, temperature);
+  if (rc) return rc;
+  TFR_REQUIRE(loss != nullptr, "loss must not be NULL");
+  TFR_REQUIRE(kind >= TFR_MISC_SIGMOID_CE && kind <= TFR_MISC_LIST_MLE,
+              "kind %d is not a tfr_misc_loss", kind);
+  if (B == 0) return TFR_OK;
+  const size_t smem = ((list_smem_bytes(N) + 15) & ~(size_t)15) + kLossThreads * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+#define TFR_MISC_CASE(K_)                                                                    \
+  case K_:                                                                                   \
+    rc = prep_smem(misc_loss_kernel<K_>, smem);                                              \
+    if (rc) return rc;                                                                       \
+    misc_loss_kernel<K_><<<B, kLossThreads, smem, st>>>(scores, labels, item_w, w_per_item,   \
+                                                        mask, N, temperature, rank_weight,   \
+                                                        grad_scale, grad, row, loss, weight, \
+                                                        nonzero);                            \
+    break;
+  switch (kind) {
+    TFR_MISC_CASE(TFR_MISC_SIGMOID_CE)
+    TFR_MISC_CASE(TFR_MISC_MEAN_SQUARED)
+    TFR_MISC_CASE(TFR_MISC_UNIQUE_SOFTMAX)
+    TFR_MISC_CASE(TFR_MISC_LIST_MLE)
+  }
+#undef TFR_MISC_CASE
   TFR_LAUNCH_OK();
   return TFR_OK;
 }

@@ -319,9 +319,98 @@ class ApproxMRRLoss(_ListwiseLoss):
   _default_temperature = 0.1
 
 
+class _MiscListwiseLoss(_ListwiseLoss):
+  """Listwise losses served by K3b (tfr_misc_loss_fwd_bwd)."""
+
+  def fused_fwd_bwd(self, y_true, y_pred, sample_weight, grad_out, per_list,
+                    total2):
+    labels, logits = losses_impl._prep_2d(y_true, y_pred)
+    w, wpi = losses_impl._prep_weights(sample_weight, logits)
+    b, n = logits.shape
+    scale = 1.0 if self.reduction == Reduction.SUM else 1.0 / float(b)
+    table = None
+    if isinstance(self._lambda_weight, losses_impl.ListMLELambdaWeight):
+      table = self._lambda_weight.rank_table(n, logits.device)
+    # grad_out = scale * d loss_b / d s; the list weight multiplies on the host side
+    # of the kernel only when weights are given (weight_b = 1 otherwise).
+    _C.check(_C.lib.tfr_misc_loss_fwd_bwd(
+        _C.ptr(logits), _C.ptr(labels), _C.ptr(w), wpi, None, b, n,
+        float(self._temperature), losses_impl._MISC[self._loss._kind],
+        _C.ptr(table), scale, _C.ptr(grad_out), None, _C.ptr(per_list[0]),
+        _C.ptr(per_list[1]), None, _C.stream()))
+    if w is not None:
+      grad_out.mul_(per_list[1].unsqueeze(1))
+    _C.check(_C.lib.tfr_weighted_sum(_C.ptr(per_list[0]), _C.ptr(per_list[1]), b,
+                                     scale, _C.ptr(total2), _C.stream()))
+
+
+class UniqueSoftmaxLoss(_MiscListwiseLoss):
+  """keras/losses.py:946-1005."""
+  _impl = losses_impl.UniqueSoftmaxLoss
+
+
+class ListMLELoss(_MiscListwiseLoss):
+  """keras/losses.py:1008-1090."""
+  _impl = losses_impl.ListMLELoss
+
+
+class ListMLELambdaWeight(losses_impl.ListMLELambdaWeight):
+  """keras/losses.py:233-244."""
+
+  def __init__(self, rank_discount_fn=None, **kwargs):
+    super().__init__(rank_discount_fn)
+
+  def get_config(self):
+    return {'rank_discount_fn': self._rank_discount_fn}
+
+
+class _PointwiseLoss(_RankingLoss):
+  """keras/losses.py:1499-1600: `call` returns loss_i * mask_i, `__call__` applies the
+  normalised sample weight and the Keras reduction; one kernel launch here."""
+  _impl = None
+
+  def __call__(self, y_true, y_pred, sample_weight=None):
+    rows = self._loss.compute_weighted_rows(y_true, y_pred, sample_weight)
+    return _keras_reduce(rows, None, self.reduction)
+
+  def fused_fwd_bwd(self, y_true, y_pred, sample_weight, grad_out, per_list,
+                    total2):
+    labels, logits = losses_impl._prep_2d(y_true, y_pred)
+    w, wpi = losses_impl._prep_weights(sample_weight, logits)
+    b, n = logits.shape
+    scale = 1.0 if self.reduction == Reduction.SUM else 1.0 / float(b * n)
+    _C.check(_C.lib.tfr_misc_loss_fwd_bwd(
+        _C.ptr(logits), _C.ptr(labels), _C.ptr(w), wpi, None, b, n,
+        float(self._loss._temperature), losses_impl._MISC[self._loss._kind], None,
+        scale, _C.ptr(grad_out), None, _C.ptr(per_list[0]), _C.ptr(per_list[1]),
+        None, _C.stream()))
+    _C.check(_C.lib.tfr_weighted_sum(_C.ptr(per_list[0]), None, b, scale,
+                                     _C.ptr(total2), _C.stream()))
+
+
+class SigmoidCrossEntropyLoss(_PointwiseLoss):
+  """keras/losses.py:1499-1546."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, ragged=False):
+    super().__init__(reduction, name, ragged)
+    self._loss = losses_impl.SigmoidCrossEntropyLoss(
+        name='{}_impl'.format(name) if name else None, ragged=ragged)
+
+
+class MeanSquaredLoss(_PointwiseLoss):
+  """keras/losses.py:1549-1600."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, ragged=False):
+    super().__init__(reduction, name, ragged)
+    self._loss = losses_impl.MeanSquaredLoss(
+        name='{}_impl'.format(name) if name else None, ragged=ragged)
+
+
 _KEY_TO_CLS = {
     RankingLossKey.APPROX_NDCG_LOSS: ApproxNDCGLoss,
     RankingLossKey.APPROX_MRR_LOSS: ApproxMRRLoss,
+    RankingLossKey.SIGMOID_CROSS_ENTROPY_LOSS: SigmoidCrossEntropyLoss,
+    RankingLossKey.MEAN_SQUARED_LOSS: MeanSquaredLoss,
 }
 _KEY_TO_CLS_WITH_LAMBDA = {
     RankingLossKey.PAIRWISE_HINGE_LOSS: PairwiseHingeLoss,
@@ -329,6 +418,8 @@ _KEY_TO_CLS_WITH_LAMBDA = {
     RankingLossKey.PAIRWISE_SOFT_ZERO_ONE_LOSS: PairwiseSoftZeroOneLoss,
     RankingLossKey.PAIRWISE_MSE_LOSS: PairwiseMSELoss,
     RankingLossKey.SOFTMAX_LOSS: SoftmaxLoss,
+    RankingLossKey.UNIQUE_SOFTMAX_LOSS: UniqueSoftmaxLoss,
+    RankingLossKey.LIST_MLE_LOSS: ListMLELoss,
 }
 
 

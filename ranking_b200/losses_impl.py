@@ -484,3 +484,147 @@ class ApproxMRRLoss(_ListwiseLoss):
   def __init__(self, name=None, lambda_weight=None, temperature=0.1,
                ragged=False):
     super().__init__(name, lambda_weight, temperature, ragged)
+
+
+# ----------------------------------------------------------------------------
+# Pointwise losses + UniqueSoftmax / ListMLE  (tfr_misc_loss_fwd_bwd, K3b)
+# ----------------------------------------------------------------------------
+_MISC = {'sigmoid_ce': 0, 'mean_squared': 1, 'unique_softmax': 2, 'list_mle': 3}
+
+
+class _MiscFn(torch.autograd.Function):
+  """(loss[B], weight[B], nonzero[B], row[B, N]) from one K3b launch.  Pointwise
+  kinds: loss = sum_i row, row_i = loss_i * w_i.  Listwise kinds: row is None."""
+
+  @staticmethod
+  def forward(ctx, logits, labels, w, w_per_item, mask, temperature, kind,
+              rank_weight):
+    b, n = logits.shape
+    dev = logits.device
+    grad = torch.empty_like(logits)
+    loss = torch.empty(b, dtype=torch.float32, device=dev)
+    weight = torch.empty_like(loss)
+    pointwise = kind in ('sigmoid_ce', 'mean_squared')
+    nonzero = torch.empty_like(loss) if pointwise else None
+    row = torch.empty_like(logits) if pointwise else None
+    _C.check(_C.lib.tfr_misc_loss_fwd_bwd(
+        _C.ptr(logits), _C.ptr(labels), _C.ptr(w), w_per_item, _C.ptr(mask), b, n,
+        float(temperature), _MISC[kind], _C.ptr(rank_weight), 1.0, _C.ptr(grad),
+        _C.ptr(row), _C.ptr(loss), _C.ptr(weight), _C.ptr(nonzero), _C.stream()))
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(grad)
+    ctx.mark_non_differentiable(weight)
+    if pointwise:
+      ctx.mark_non_differentiable(nonzero)
+      return loss, weight, nonzero, row
+    return loss, weight
+
+  @staticmethod
+  def backward(ctx, g_loss, _gw, *rest):
+    grad, = ctx.saved_tensors
+    out = None
+    if g_loss is not None:
+      out = grad * g_loss.reshape(-1, 1)
+    if len(rest) == 2 and rest[1] is not None:     # d row_i / d s_i = grad_i
+      out = grad * rest[1] if out is None else out + grad * rest[1]
+    return out, None, None, None, None, None, None, None
+
+
+class _PointwiseLoss(_RankingLoss):
+  """losses_impl.py:1284-1321."""
+  _kind = None
+
+  def _run(self, labels, logits, weights, mask, temperature):
+    labels, logits = _prep_2d(labels, logits)
+    w, wpi = _prep_weights(weights, logits)
+    m = _prep_mask(mask, logits)
+    return _MiscFn.apply(logits, labels, w, wpi, m, temperature, self._kind, None)
+
+  def compute(self, labels, logits, weights, reduction, mask=None):
+    loss, weight, nonzero, row = self._run(labels, logits, weights, mask,
+                                           self._temperature)
+    if reduction == Reduction.NONE:
+      return row
+    total = loss.sum()
+    if reduction == Reduction.SUM:
+      return total
+    if reduction == Reduction.MEAN:
+      return _safe_div(total, weight.sum())
+    if reduction == Reduction.SUM_BY_NONZERO_WEIGHTS:
+      return _safe_div(total, nonzero.sum())
+    if reduction == Reduction.SUM_OVER_BATCH_SIZE:
+      return total / float(row.numel())
+    raise ValueError('bad reduction %r' % (reduction,))
+
+  def compute_per_list(self, labels, logits, weights, mask=None):
+    """losses_impl.py:1295-1321 (no temperature, as in the reference)."""
+    loss, weight, _, _ = self._run(labels, logits, weights, mask, 1.0)
+    return _safe_div(loss, weight), weight
+
+  def compute_weighted_rows(self, labels, logits, weights):
+    """[B, N] loss_i * mask_i * normalised weight: the Keras `call` x sample_weight."""
+    return self._run(labels, logits, weights, None, self._temperature)[3]
+
+  def _normalize_weights_impl(self, labels, weights):
+    """losses_impl.py:1287-1293."""
+    w = 1.0 if weights is None else _as_f32(weights, labels.device, 'weights')
+    return torch.where(labels >= 0, torch.ones_like(labels) * w,
+                       torch.zeros_like(labels))
+
+
+class SigmoidCrossEntropyLoss(_PointwiseLoss):
+  """losses_impl.py:1425-1446."""
+  _kind = 'sigmoid_ce'
+
+  def __init__(self, name=None, temperature=1.0, ragged=False):
+    super().__init__(name, None, temperature, ragged)
+
+
+class MeanSquaredLoss(_PointwiseLoss):
+  """losses_impl.py:1449-1469 (temperature is not used)."""
+  _kind = 'mean_squared'
+
+  def __init__(self, name=None, ragged=False):
+    super().__init__(name, None, 1.0, ragged)
+
+
+class ListMLELambdaWeight(_LambdaWeight):
+  """losses_impl.py:457-480."""
+
+  def __init__(self, rank_discount_fn):
+    self._rank_discount_fn = rank_discount_fn
+
+  def individual_weights(self, labels, ranks):
+    labels = torch.as_tensor(labels)
+    return torch.ones_like(labels) * self._rank_discount_fn(
+        torch.as_tensor(ranks).to(labels.dtype))
+
+  def rank_table(self, n, device):
+    """Discount of ranks 1..n as the [n] table the kernel reads."""
+    r = torch.arange(1, n + 1, dtype=torch.float32, device=device)
+    return (torch.ones_like(r) * self._rank_discount_fn(r)).float().contiguous()
+
+
+class _MiscListwiseLoss(_ListwiseLoss):
+  """UniqueSoftmax / ListMLE share the listwise plumbing of K2/K3."""
+
+  def _run(self, labels, logits, weights, mask, temperature):
+    labels, logits = _prep_2d(labels, logits)
+    w, wpi = _prep_weights(weights, logits)
+    m = _prep_mask(mask, logits)
+    table = None
+    if self._kind == 'list_mle' and isinstance(self._lambda_weight,
+                                               ListMLELambdaWeight):
+      table = self._lambda_weight.rank_table(logits.shape[1], logits.device)
+    return _MiscFn.apply(logits, labels, w, wpi, m, temperature, self._kind, table)
+
+
+class UniqueSoftmaxLoss(_MiscListwiseLoss):
+  """losses_impl.py:1250-1281."""
+  _kind = 'unique_softmax'
+
+
+class ListMLELoss(_MiscListwiseLoss):
+  """losses_impl.py:1541-1576.  Label ties are ordered by index (the reference
+  shuffles them randomly with a fixed op seed); invalid items come last."""
+  _kind = 'list_mle'

@@ -386,3 +386,127 @@ def test_approx_mrr_loss(api):
       api.t([[True, False, True]], dtype=torch.bool))
   approxrank = 1. + 1. / (1. + math.exp(-(1. - 2.)))
   _close(result, -1. / approxrank)
+
+
+# ---------------------------------------------------------------------------
+# Pointwise losses, UniqueSoftmax, ListMLE: losses_impl_test.py:517-623, 1229-1418
+# ---------------------------------------------------------------------------
+def _sigmoid_cross_entropy(labels, logits):
+  return sum(max(x, 0.) - x * z + ln(1. + math.exp(-abs(x)))
+             for z, x in zip(labels, logits))
+
+
+def _mean_squared_error(labels, logits):
+  return sum((a - b) ** 2 for a, b in zip(labels, logits))
+
+
+def test_pointwise_compute_per_list(api):
+  """losses_impl_test.py:517-528."""
+  loss_fn = api.losses_impl.SigmoidCrossEntropyLoss(name=None)
+  losses, weights = loss_fn.compute_per_list(api.t(LABELS), api.t(SCORES),
+                                             api.t(ITEM_W))
+  _close(losses, [1.3644443, 0.16292572])
+  _close(weights, [2. + 3. + 4., 1. + 1. + 1.])
+
+
+@pytest.mark.parametrize('cls,expected_losses,expected_weights', [
+    ('SigmoidCrossEntropyLoss', [1.3644443, -0.8190755], [9., 2.]),
+    ('MeanSquaredLoss', [3.6666667, 1.], [9., 2.]),
+    # label tie (0, 0) resolved by index: the order the reference happens to draw in
+    # this test (seed 42); its unreduced-loss test draws the other order (1.534534)
+    ('ListMLELoss', [3.534534, 0.126928], [4., 1.]),
+    ('UniqueSoftmaxLoss', [1.407606, 0.380784], [4., 1.]),
+])
+def test_compute_per_list_padded_more(api, cls, expected_losses, expected_weights):
+  """losses_impl_test.py:556-578 with ragged rows padded the way ragged_to_dense does."""
+  loss_fn = getattr(api.losses_impl, cls)(name=None)
+  losses, weights = loss_fn.compute_per_list(
+      api.t(RAGGED_LABELS), api.t(RAGGED_SCORES), api.t(RAGGED_W))
+  _close(losses, expected_losses)
+  _close(weights, expected_weights)
+
+
+@pytest.mark.parametrize('cls,fn', [('SigmoidCrossEntropyLoss', _sigmoid_cross_entropy),
+                                    ('MeanSquaredLoss', _mean_squared_error)])
+def test_pointwise_losses(api, cls, fn):
+  """losses_impl_test.py:1333-1418."""
+  scores = [[0.2, 0.5, 0.3], [0.2, 0.3, 0.5], [0.2, 0.3, 0.5]]
+  labels = [[0., 0., 1.], [0., 0., 2.], [0., 0., 0.]]
+  weights = [[2.], [1.], [1.]]
+  red = api.Reduction.SUM_BY_NONZERO_WEIGHTS
+  loss_fn = getattr(api.losses_impl, cls)(name=None)
+  _close(loss_fn.compute(api.t(labels), api.t(scores), None, red),
+         (fn(labels[0], scores[0]) + fn(labels[1], scores[1]) +
+          fn(labels[2], scores[2])) / 9.)
+  _close(loss_fn.compute(api.t(labels), api.t(scores), api.t(weights), red),
+         (fn(labels[0], scores[0]) * 2. + fn(labels[1], scores[1]) +
+          fn(labels[2], scores[2])) / 9.)
+  # invalid labels, explicit mask
+  expect = {'SigmoidCrossEntropyLoss': (ln(1. + math.exp(-2.)) + ln(1. + math.exp(1.))) / 2,
+            'MeanSquaredLoss': (1. + 1.) / 2}[cls]
+  _close(loss_fn.compute(api.t([[0., -1., 1.]]), api.t([[1., 3., 2.]]), None, red), expect)
+  mask = torch.tensor([[True, False, True]], device=api.device)
+  _close(loss_fn.compute(api.t([[0., 1., 1.]]), api.t([[1., 3., 2.]]), None, red,
+                         mask), expect)
+
+
+def test_pointwise_unreduced_rows(api):
+  """losses_impl_test.py:583-586: weighted per-item losses of the padded rows
+  (Reduction.NONE of `compute` = losses * weights)."""
+  red = api.Reduction.NONE
+  got = api.losses_impl.SigmoidCrossEntropyLoss(name=None).compute(
+      api.t(RAGGED_LABELS), api.t(RAGGED_SCORES), None, red)
+  _close(got, [[1.313262, 3.048587, 0.126928], [1.313262, -2.951413, 0.]])
+  got = api.losses_impl.MeanSquaredLoss(name=None).compute(
+      api.t(RAGGED_LABELS), api.t(RAGGED_SCORES), None, red)
+  _close(got, [[1., 9., 1.], [1., 1., 0.]])
+
+
+def test_unique_softmax_loss(api):
+  """losses_impl_test.py:1231-1272."""
+  scores = [[1., 3., 2.], [1., 2., 3.], [1., 2., 3.]]
+  labels = [[0., 0., 1.], [0., 1., 2.], [0., 0., 0.]]
+  weights = [[2.], [1.], [1.]]
+  red = api.Reduction.SUM_BY_NONZERO_WEIGHTS
+  loss_fn = api.losses_impl.UniqueSoftmaxLoss(name=None)
+  _close(loss_fn.compute(api.t(labels), api.t(scores), None, red),
+         -(ln(_softmax(scores[0])[2]) + ln(_softmax(scores[1][:2])[1]) +
+           ln(_softmax(scores[1])[2]) * 3.) / 3.)
+  _close(loss_fn.compute(api.t(labels), api.t(scores), api.t(weights), red),
+         -(ln(_softmax(scores[0])[2]) * 2. + ln(_softmax(scores[1][:2])[1]) * 1. +
+           ln(_softmax(scores[1])[2]) * 3. * 1.) / 2.)
+  losses, w = loss_fn.compute_per_list(api.t(LABELS), api.t(SCORES), api.t(ITEM_W))
+  _close(losses, [1.407606, 1.222818])
+  _close(w, [4., 1.])
+  mask = torch.tensor([[True, False, True, True]], device=api.device)
+  _close(loss_fn.compute(api.t([[0., 1., 1., 0.]]), api.t([[1., 2., 3., 2.]]), None, red,
+                         mask), -ln(_softmax([1, 3, 2])[1]))
+
+
+def test_list_mle_loss(api):
+  """losses_impl_test.py:1276-1328 (the tie test depends on the random tie order and
+  is replaced by the by-index order)."""
+  scores = [[0., ln(3), ln(2)], [0., ln(2), ln(3)]]
+  labels = [[0., 2., 1.], [1., 0., 2.]]
+  weights = [[2.], [1.]]
+  red = api.Reduction.SUM_BY_NONZERO_WEIGHTS
+  L = api.losses_impl
+  loss_fn = L.ListMLELoss(name=None)
+  a = ln(3. / (3 + 2 + 1)) + ln(2. / (2 + 1)) + ln(1. / 1)
+  b = ln(3. / (3 + 2 + 1)) + ln(1. / (1 + 2)) + ln(2. / 2)
+  _close(loss_fn.compute(api.t(labels), api.t(scores), None, red), -(a + b) / 2)
+  _close(loss_fn.compute(api.t(labels), api.t(scores), api.t(weights), red),
+         -(2 * a + 1 * b) / 2)
+  lw = L.ListMLELambdaWeight(rank_discount_fn=lambda rank: torch.pow(
+      torch.as_tensor(2., device=rank.device), 3 - rank) - 1.)
+  loss_fn = L.ListMLELoss(name=None, lambda_weight=lw)
+  _close(loss_fn.compute(api.t(labels), api.t(scores), None, red),
+         -((3 * ln(3. / (3 + 2 + 1)) + 1 * ln(2. / (2 + 1)) + 0 * ln(1. / 1)) +
+           (3 * ln(3. / (3 + 2 + 1)) + 1 * ln(1. / (1 + 2)) + 0 * ln(2. / 2))) / 2)
+  # ties by index: order (item 2, item 0, item 1)
+  loss_fn = L.ListMLELoss(name=None)
+  _close(loss_fn.compute(api.t([[0., 0., 1.]]), api.t([[0., ln(2), ln(3)]]), None, red),
+         -(ln(3. / (3 + 2 + 1)) + ln(1. / (1 + 2)) + ln(2. / 2)))
+  mask = torch.tensor([[True, False, True]], device=api.device)
+  _close(loss_fn.compute(api.t([[0., 0., 1.]]), api.t([[0., ln(2), ln(3)]]), None, red,
+                         mask), -(ln(3. / (3 + 1)) + ln(1. / 1)))

@@ -92,6 +92,60 @@ def test_listwise_loss_and_grad(cuda_api, oracle_api, cls, wkind, n):
   _check_loss_and_grad(loss_c, loss_o, scores, labels, weights)
 
 
+@pytest.mark.parametrize('cls', ['UniqueSoftmaxLoss', 'ListMLELoss',
+                                 'SigmoidCrossEntropyLoss', 'MeanSquaredLoss'])
+@pytest.mark.parametrize('wkind', ['none', 'list', 'item'])
+@pytest.mark.parametrize('n', [1, 5, 64, 200, 700])
+def test_more_losses_and_grad(cuda_api, oracle_api, cls, wkind, n):
+  """K3b: the remaining RankingLossKey members against the oracle (values and
+  gradients, Keras SUM_OVER_BATCH_SIZE reduction)."""
+  scores, labels, item_w, list_w = _batch(6, n, seed=17 + n)
+  weights = {'none': None, 'list': list_w, 'item': item_w}[wkind]
+  loss_c = getattr(cuda_api.keras_losses, cls)()
+  loss_o = getattr(oracle_api.keras_losses, cls)()
+  _check_loss_and_grad(loss_c, loss_o, scores, labels, weights)
+
+
+def test_list_mle_lambda_weight_and_temperature(cuda_api, oracle_api):
+  scores, labels, item_w, _ = _batch(5, 40, seed=23)
+  KC, KO = cuda_api.keras_losses, oracle_api.keras_losses
+  disc = lambda r: 1. / torch.log1p(r)
+  _check_loss_and_grad(
+      KC.ListMLELoss(lambda_weight=KC.ListMLELambdaWeight(rank_discount_fn=disc),
+                     temperature=0.5),
+      KO.ListMLELoss(lambda_weight=KO.ListMLELambdaWeight(rank_discount_fn=disc),
+                     temperature=0.5), scores, labels, item_w)
+  _check_loss_and_grad(KC.UniqueSoftmaxLoss(temperature=2.0),
+                       KO.UniqueSoftmaxLoss(temperature=2.0), scores, labels, None)
+
+
+@pytest.mark.parametrize('key', ['unique_softmax_loss', 'list_mle_loss',
+                                 'sigmoid_cross_entropy_loss', 'mean_squared_loss'])
+def test_fused_train_step_more_losses(oracle_api, key):
+  """RankingTrainer with the K3b losses: one Adagrad step equals the oracle's."""
+  import ranking_b200 as tfr
+  b, n, d, hidden = 8, 10, 16, [24]
+  tower, params = _tower_and_params(tfr, d, hidden, 1, seed=5)
+  trainer = tfr.train.RankingTrainer(tower, tfr.keras.losses.get(key),
+                                     optimizer='sgd', learning_rate=0.1)
+  g = torch.Generator().manual_seed(4)
+  x = torch.randn(b, n, d, generator=g)
+  y = torch.randint(0, 4, (b, n), generator=g).float()
+  y[:, -3:] = -1.0
+  w = torch.rand(b, 1, generator=g) + 0.5
+  got = float(trainer.train_step(x.cuda(), y.cuda(), sample_weight=w.cuda()))
+  flat = oracle_api.scorer.tower_forward(x.double().reshape(b * n, d), params,
+                                         activation='relu')
+  logits = oracle_api.scorer.restore_list(flat, y >= 0)
+  ol = oracle_api.keras_losses.get(key)(y.double(), logits, w.double())
+  ol.backward()
+  assert got == pytest.approx(float(ol.detach()), rel=2e-5, abs=1e-6)
+  want = torch.cat([torch.cat([(wt - 0.1 * wt.grad).reshape(-1),
+                               (bs - 0.1 * bs.grad).reshape(-1)])
+                    for wt, bs in zip(params['dense_w'], params['dense_b'])])
+  assert _rel_err(tower.flat.detach(), want.detach()) <= 1e-5
+
+
 def test_softmax_with_dcg_lambda(cuda_api, oracle_api):
   scores, labels, item_w, _ = _batch(8, 50, seed=3)
   KC, KO = cuda_api.keras_losses, oracle_api.keras_losses
