@@ -196,6 +196,37 @@ int tfr_rank_metrics(const float* scores, const float* labels,
                      const float* disc_table, float* ndcg, float* ndcg_w,
                      float* mrr, float* mrr_w, float* raw, void* stream);
 
+/* The same launch can also emit the other metrics of `default_keras_metrics()`
+ * (keras/metrics.py:131-153) from the one score sort; every pointer is optional.
+ *   dcg        [B, T]  sum_{k < cut} w gain(l) disc(k)       DCGMetric  :673-705
+ *                      (divide by ndcg_w for the reference's per-list value)
+ *   precision  [B, T]  #rel in top cut / min(cut, #valid)    PrecisionMetric :180-207, 564
+ *   recall     [B, T]  #rel in top cut / #rel                RecallMetric :154-177, 539
+ *   map        [B, T]  MeanAveragePrecisionMetric :589-628
+ *   hits       [B, T]  HitsMetric :462-506
+ *   arp        [B, 2]  {value, per-list weight = sum w l}    ARPMetric :509-536
+ *   opa        [B, 2]  {value, per-list weight}              OPAMetric :708-743
+ * precision / recall / map / hits use mrr_w as their per-list weight (relevance =
+ * [label >= 1]); dcg uses ndcg_w. */
+typedef struct {
+  float* dcg;
+  float* precision;
+  float* recall;
+  float* map;
+  float* hits;
+  float* arp;
+  float* opa;
+} tfr_metric_ext;
+
+int tfr_rank_metrics_ext(const float* scores, const float* labels,
+                         const float* item_w, int w_per_item,
+                         const uint8_t* mask, int B, int N,
+                         const int32_t* topns_host, int n_topn, int gain_fn,
+                         int disc_fn, const float* gain_table,
+                         const float* disc_table, float* ndcg, float* ndcg_w,
+                         float* mrr, float* mrr_w, float* raw,
+                         const tfr_metric_ext* ext, void* stream);
+
 /* out2[0] = scale * sum_i v[i] * (w ? w[i] : 1); out2[1] = sum_i (w ? w[i] : 1).
  * Deterministic single-CTA reduction (Keras Mean state / loss reduction). */
 int tfr_weighted_sum(const float* v, const float* w, int n, float scale,

@@ -115,6 +115,152 @@ class NDCGMetric(_RankingMetric):
     return per_list_ndcg, per_list_weights
 
 
+def _per_list_recall(labels, predictions, topn, mask):
+  """metrics_impl.py:154-177."""
+  sorted_labels = utils.sort_by_scores(predictions, [labels], topn=topn,
+                                       mask=mask)[0]
+  topn_positives = (sorted_labels >= 1.0).to(predictions.dtype)
+  labels = (labels >= 1.0).to(predictions.dtype)
+  return L._divide_no_nan(topn_positives.sum(1, keepdim=True),
+                          labels.sum(1, keepdim=True))
+
+
+def _per_list_precision(labels, predictions, topn, mask):
+  """metrics_impl.py:180-207."""
+  sorted_labels = utils.sort_by_scores(predictions, [labels], topn=topn,
+                                       mask=mask)[0]
+  relevance = (sorted_labels >= 1.0).to(predictions.dtype)
+  if topn is None:
+    topn = relevance.shape[1]
+  valid_topn = torch.clamp(mask.to(torch.int64).sum(1, keepdim=True), max=topn)
+  return L._divide_no_nan(relevance.sum(1, keepdim=True),
+                          valid_topn.to(predictions.dtype))
+
+
+def _binary(labels):
+  return (labels >= 1.0).to(labels.dtype)
+
+
+class HitsMetric(_RankingMetric):
+  """metrics_impl.py:462-506."""
+
+  def __init__(self, name=None, topn=None):
+    self._topn = topn
+
+  def _compute_impl(self, labels, predictions, weights, mask):
+    topn = predictions.shape[1] if self._topn is None else self._topn
+    sorted_labels, = utils.sort_by_scores(predictions, [labels], topn=topn,
+                                          mask=mask)
+    relevance = (sorted_labels >= 1.0).to(predictions.dtype)
+    hits = relevance.max(dim=1, keepdim=True).values
+    return hits, _per_example_weights_to_per_list_weights(weights, _binary(labels))
+
+
+class ARPMetric(_RankingMetric):
+  """metrics_impl.py:509-536."""
+
+  def __init__(self, name=None):
+    pass
+
+  def _compute_impl(self, labels, predictions, weights, mask):
+    topn = predictions.shape[1]
+    sorted_labels, sorted_weights = utils.sort_by_scores(
+        predictions, [labels, weights], topn=topn, mask=mask)
+    weighted_labels = sorted_labels * sorted_weights
+    position = torch.arange(1, topn + 1).to(predictions.dtype) * torch.ones_like(
+        weighted_labels)
+    per_list_weights = weighted_labels.sum(1, keepdim=True)
+    per_list_arp = L._divide_no_nan(
+        (position * weighted_labels).sum(1, keepdim=True), per_list_weights)
+    return per_list_arp, per_list_weights
+
+
+class RecallMetric(_RankingMetric):
+  """metrics_impl.py:539-561."""
+
+  def __init__(self, name=None, topn=None):
+    self._topn = topn
+
+  def _compute_impl(self, labels, predictions, weights, mask):
+    topn = predictions.shape[1] if self._topn is None else self._topn
+    return (_per_list_recall(labels, predictions, topn, mask),
+            _per_example_weights_to_per_list_weights(weights, _binary(labels)))
+
+
+class PrecisionMetric(_RankingMetric):
+  """metrics_impl.py:564-586."""
+
+  def __init__(self, name=None, topn=None):
+    self._topn = topn
+
+  def _compute_impl(self, labels, predictions, weights, mask):
+    topn = predictions.shape[1] if self._topn is None else self._topn
+    return (_per_list_precision(labels, predictions, topn, mask),
+            _per_example_weights_to_per_list_weights(weights, _binary(labels)))
+
+
+class MeanAveragePrecisionMetric(_RankingMetric):
+  """metrics_impl.py:589-628."""
+
+  def __init__(self, name=None, topn=None):
+    self._topn = topn
+
+  def _compute_impl(self, labels, predictions, weights, mask):
+    topn = predictions.shape[1] if self._topn is None else self._topn
+    relevance = _binary(labels)
+    sorted_relevance, sorted_weights = utils.sort_by_scores(
+        predictions, [relevance, weights], topn=topn, mask=mask)
+    per_list_relevant_counts = torch.cumsum(sorted_relevance, 1)
+    per_list_cutoffs = torch.cumsum(torch.ones_like(sorted_relevance), 1)
+    per_list_precisions = L._divide_no_nan(per_list_relevant_counts,
+                                           per_list_cutoffs)
+    total_precision = (per_list_precisions * sorted_weights *
+                       sorted_relevance).sum(1, keepdim=True)
+    total_relevance = (weights * relevance).sum(1, keepdim=True)
+    per_list_map = L._divide_no_nan(total_precision, total_relevance)
+    return per_list_map, _per_example_weights_to_per_list_weights(weights,
+                                                                  relevance)
+
+
+class DCGMetric(_RankingMetric):
+  """metrics_impl.py:673-705."""
+
+  def __init__(self, name=None, topn=None, gain_fn=_DEFAULT_GAIN_FN,
+               rank_discount_fn=_DEFAULT_RANK_DISCOUNT_FN):
+    self._topn = topn
+    self._gain_fn = gain_fn
+    self._rank_discount_fn = rank_discount_fn
+
+  def _compute_impl(self, labels, predictions, weights, mask):
+    topn = predictions.shape[1] if self._topn is None else self._topn
+    sorted_labels, sorted_weights = utils.sort_by_scores(
+        predictions, [labels, weights], topn=topn, mask=mask)
+    dcg = _discounted_cumulative_gain(sorted_labels, sorted_weights,
+                                      self._gain_fn, self._rank_discount_fn)
+    per_list_weights = _per_example_weights_to_per_list_weights(
+        weights=weights, relevance=self._gain_fn(labels))
+    return L._divide_no_nan(dcg, per_list_weights), per_list_weights
+
+
+class OPAMetric(_RankingMetric):
+  """metrics_impl.py:708-743."""
+
+  def __init__(self, name=None):
+    pass
+
+  def _compute_impl(self, labels, predictions, weights, mask):
+    dt = predictions.dtype
+    valid_pair = torch.logical_and(mask.unsqueeze(2), mask.unsqueeze(1))
+    pair_label_diff = labels.unsqueeze(2) - labels.unsqueeze(1)
+    pair_pred_diff = predictions.unsqueeze(2) - predictions.unsqueeze(1)
+    correct_pairs = (pair_label_diff > 0).to(dt) * (pair_pred_diff > 0).to(dt)
+    pair_weights = (pair_label_diff > 0).to(dt) * weights.unsqueeze(2) * valid_pair.to(dt)
+    per_list_weights = pair_weights.sum((1, 2)).unsqueeze(1)
+    per_list_opa = L._divide_no_nan(
+        (correct_pairs * pair_weights).sum((1, 2)).unsqueeze(1), per_list_weights)
+    return per_list_opa, per_list_weights
+
+
 class KerasMean(object):
   """tf.keras.metrics.Mean over (values, sample_weight): keras/metrics.py:171-193."""
 

@@ -37,6 +37,11 @@ class LambdaCfg(C.Structure):
               ('disc_table', C.c_void_p)]
 
 
+class MetricExt(C.Structure):
+  _fields_ = [(k, C.c_void_p) for k in ('dcg', 'precision', 'recall', 'map', 'hits',
+                                        'arp', 'opa')]
+
+
 class MlpCfg(C.Structure):
   _fields_ = [('n_dense', C.c_int32), ('dims', C.c_int32 * (MLP_MAX_LAYERS + 1)),
               ('activation', C.c_int32),
@@ -69,6 +74,9 @@ _SIGNATURES = {
                                    _P, _P]),
     'tfr_rank_metrics': (_I, [_P, _P, _P, _I, _P, _I, _I, C.POINTER(C.c_int32),
                               _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    'tfr_rank_metrics_ext': (_I, [_P, _P, _P, _I, _P, _I, _I, C.POINTER(C.c_int32),
+                                  _I, _I, _I, _P, _P, _P, _P, _P, _P, _P,
+                                  C.POINTER(MetricExt), _P]),
     'tfr_weighted_sum': (_I, [_P, _P, _I, _F, _P, _P]),
     'tfr_mlp_param_count': (C.c_size_t, [C.POINTER(MlpCfg)]),
     'tfr_mlp_bn_state_count': (C.c_size_t, [C.POINTER(MlpCfg)]),

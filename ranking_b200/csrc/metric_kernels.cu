@@ -27,6 +27,10 @@ __device__ __forceinline__ uint32_t desc_bits(float x) {
   return ~u;                                        // descending
 }
 
+__device__ __forceinline__ float sc_clean(bool ok, float s, float pmin) {
+  return ok ? s : (-1e-6f + pmin);   // metrics_impl.py:262-265
+}
+
 __device__ inline void bitonic_sort(unsigned long long* keys, int P) {
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -46,6 +50,39 @@ __device__ inline void bitonic_sort(unsigned long long* keys, int P) {
   }
 }
 
+struct MetricExt {   // device copy of tfr_metric_ext (all optional)
+  float *dcg, *precision, *recall, *map, *hits, *arp, *opa;
+  __host__ __device__ bool any() const {
+    return dcg || precision || recall || map || hits || arp || opa;
+  }
+};
+
+// Inclusive prefix sums of a[0..N) in place (chunk per thread + serial chunk totals).
+__device__ inline void block_inclusive_scan(float* a, int N, float* scratch /*[blockDim.x]*/) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int per = (N + nt - 1) / nt;
+  const int beg = min(N, tid * per), end = min(N, beg + per);
+  float s = 0.f;
+  for (int i = beg; i < end; ++i) s += a[i];
+  scratch[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    float run = 0.f;
+    for (int t = 0; t < nt; ++t) {
+      const float x = scratch[t];
+      scratch[t] = run;
+      run += x;
+    }
+  }
+  __syncthreads();
+  float run = scratch[tid];
+  for (int i = beg; i < end; ++i) {
+    run += a[i];
+    a[i] = run;
+  }
+  __syncthreads();
+}
+
 // raw[b, 0..4] = {sum w, sum w*gain, sum gain, sum w*rel, sum rel}, rel = [label >= 1]
 __global__ void __launch_bounds__(kMetricThreads)
 rank_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
@@ -53,7 +90,7 @@ rank_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ 
                     const uint8_t* __restrict__ mask, int N, int P, TopnList topns,
                     int gain_fn, int disc_fn, const float* __restrict__ gain_table,
                     const float* __restrict__ disc_table, float* __restrict__ ndcg,
-                    float* __restrict__ mrr, float* __restrict__ raw) {
+                    float* __restrict__ mrr, float* __restrict__ raw, MetricExt ext) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
   float* cl = reinterpret_cast<float*>(keys + P);  // cleaned labels
@@ -62,6 +99,13 @@ rank_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ 
   float* term = wg + N;                             // per-position DCG terms
   float* red = term + N;                            // [32]
   unsigned char* valid = reinterpret_cast<unsigned char*>(red + 32);
+  // extended metrics only: cleaned scores, sorted relevance / weights, scan scratch
+  float* sc = reinterpret_cast<float*>(smem_raw + (((size_t)P * 8 + (size_t)(4 * N + 32) * 4 +
+                                                    N + 15) & ~(size_t)15));
+  float* relk = sc + N;
+  float* wk = relk + N;
+  float* scratch = wk + N;                          // [blockDim.x]
+  const bool want_ext = ext.any();
 
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t off = (size_t)b * N;
@@ -79,13 +123,14 @@ rank_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ 
     ok = ok && (wv > 0.f);
     const float c = ok ? lab : 0.f;
     const float g = gain_fn == TFR_GAIN_TABLE ? gain_table[off + i] : gain_of(gain_fn, c);
-    const float sc = ok ? scores[off + i] : (-1e-6f + pmin);
+    const float sc_i = sc_clean(ok, scores[off + i], pmin);
     cl[i] = c;
     w[i] = wv;
     wg[i] = wv * g;
     valid[i] = ok;
+    if (want_ext) sc[i] = sc_i;
     keys[i] = ((unsigned long long)(ok ? 0 : 1) << 45) |
-              ((unsigned long long)desc_bits(sc) << 13) | (unsigned long long)i;
+              ((unsigned long long)desc_bits(sc_i) << 13) | (unsigned long long)i;
     const float rel = c >= 1.f ? 1.f : 0.f;
     s_w += wv;
     s_wg += wv * g;
@@ -129,6 +174,70 @@ rank_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ 
     dcg[t] = block_sum(acc, red);
     if (tid == 0 && mrr)
       mrr[(size_t)b * topns.n + t] = first_rel < cut ? 1.f / (float)(first_rel + 1) : 0.f;
+  }
+  if (want_ext) {
+    // ---- metrics that share the score order (metrics_impl.py:154-207, 462-744) ----
+    __syncthreads();
+    float nv = 0.f, a_num = 0.f, a_den = 0.f;
+    for (int k = tid; k < N; k += blockDim.x) {
+      const int idx = (int)(keys[k] & 0x1fffull);
+      const float c = cl[idx];
+      relk[k] = c >= 1.f ? 1.f : 0.f;
+      wk[k] = w[idx];
+      term[k] = relk[k];                 // -> cumulative relevant count
+      nv += valid[k] ? 1.f : 0.f;
+      a_num += (float)(k + 1) * w[idx] * c;      // ARP (:524-536)
+      a_den += w[idx] * c;
+    }
+    nv = block_sum(nv, red);
+    a_num = block_sum(a_num, red);
+    a_den = block_sum(a_den, red);
+    if (tid == 0 && ext.arp) {
+      ext.arp[b * 2 + 0] = a_den != 0.f ? a_num / a_den : 0.f;
+      ext.arp[b * 2 + 1] = a_den;
+    }
+    block_inclusive_scan(term, N, scratch);
+    for (int t = 0; t < topns.n; ++t) {
+      const int cut = topns.v[t] > 0 ? min(topns.v[t], N) : N;
+      float rsum = 0.f, msum = 0.f;
+      for (int k = tid; k < cut; k += blockDim.x) {
+        rsum += relk[k];
+        msum += term[k] / (float)(k + 1) * wk[k] * relk[k];   // precision@k at relevant k
+      }
+      rsum = block_sum(rsum, red);
+      msum = block_sum(msum, red);
+      if (tid == 0) {
+        const size_t o = (size_t)b * topns.n + t;
+        const float vt = fminf((float)cut, nv);
+        if (ext.dcg) ext.dcg[o] = dcg[t];
+        if (ext.precision) ext.precision[o] = vt > 0.f ? rsum / vt : 0.f;
+        if (ext.recall) ext.recall[o] = s_r != 0.f ? rsum / s_r : 0.f;
+        if (ext.hits) ext.hits[o] = rsum > 0.f ? 1.f : 0.f;
+        if (ext.map) ext.map[o] = s_wr != 0.f ? msum / s_wr : 0.f;
+      }
+    }
+    if (ext.opa) {
+      // ordered pair accuracy (:721-743): pairs (i, j) with l_i > l_j, weight w_i
+      float num = 0.f, den = 0.f;
+      for (int i = tid; i < N; i += blockDim.x) {
+        if (!valid[i]) continue;
+        const float li = cl[i], si = sc[i], wi = w[i];
+        float n_i = 0.f, d_i = 0.f;
+        for (int j = 0; j < N; ++j) {
+          const bool pair = valid[j] && li > cl[j];
+          d_i += pair ? 1.f : 0.f;
+          n_i += (pair && si > sc[j]) ? 1.f : 0.f;
+        }
+        num += wi * n_i;
+        den += wi * d_i;
+      }
+      num = block_sum(num, red);
+      den = block_sum(den, red);
+      if (tid == 0) {
+        ext.opa[b * 2 + 0] = den != 0.f ? num / den : 0.f;
+        ext.opa[b * 2 + 1] = den;
+      }
+    }
   }
   if (ndcg == nullptr) return;
   __syncthreads();
@@ -187,12 +296,13 @@ metric_list_weights_kernel(const float* __restrict__ raw, int B, float* __restri
 
 using namespace tfr;
 
-extern "C" int tfr_rank_metrics(const float* scores, const float* labels,
+extern "C" int tfr_rank_metrics_ext(const float* scores, const float* labels,
                                 const float* item_w, int w_per_item, const uint8_t* mask,
                                 int B, int N, const int32_t* topns_host, int n_topn,
                                 int gain_fn, int disc_fn, const float* gain_table,
                                 const float* disc_table, float* ndcg, float* ndcg_w,
-                                float* mrr, float* mrr_w, float* raw, void* stream) {
+                                    float* mrr, float* mrr_w, float* raw,
+                                    const tfr_metric_ext* ext_host, void* stream) {
   TFR_REQUIRE(scores && labels, "scores/labels must not be NULL");
   TFR_REQUIRE(B >= 0 && N >= 1 && N <= kMaxMetricListSize,
               "need 1 <= list_size <= %d (got %d)", kMaxMetricListSize, N);
@@ -208,18 +318,34 @@ extern "C" int tfr_rank_metrics(const float* scores, const float* labels,
   for (int i = 0; i < n_topn; ++i) t.v[i] = topns_host[i];
   int P = 1;
   while (P < N) P <<= 1;
-  const size_t smem = (size_t)P * 8 + (size_t)(4 * N + 32) * 4 + N + 16;
+  MetricExt ext{};
+  if (ext_host)
+    ext = MetricExt{ext_host->dcg, ext_host->precision, ext_host->recall, ext_host->map,
+                    ext_host->hits, ext_host->arp, ext_host->opa};
+  const size_t smem = (((size_t)P * 8 + (size_t)(4 * N + 32) * 4 + N + 15) & ~(size_t)15) +
+                      (ext.any() ? (size_t)(3 * N + kMetricThreads) * 4 : 0) + 16;
   if (smem > 48 * 1024)
     TFR_CUDA_OK(cudaFuncSetAttribute(rank_metrics_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaStream_t st = (cudaStream_t)stream;
   rank_metrics_kernel<<<B, kMetricThreads, smem, st>>>(scores, labels, item_w, w_per_item, mask,
                                                       N, P, t, gain_fn, disc_fn, gain_table,
-                                                      disc_table, ndcg, mrr, raw);
+                                                      disc_table, ndcg, mrr, raw, ext);
   TFR_LAUNCH_OK();
   if (ndcg_w || mrr_w) {
     metric_list_weights_kernel<<<1, 1024, 0, st>>>(raw, B, ndcg_w, mrr_w);
     TFR_LAUNCH_OK();
   }
   return TFR_OK;
+}
+
+extern "C" int tfr_rank_metrics(const float* scores, const float* labels,
+                                const float* item_w, int w_per_item, const uint8_t* mask,
+                                int B, int N, const int32_t* topns_host, int n_topn,
+                                int gain_fn, int disc_fn, const float* gain_table,
+                                const float* disc_table, float* ndcg, float* ndcg_w,
+                                float* mrr, float* mrr_w, float* raw, void* stream) {
+  return tfr_rank_metrics_ext(scores, labels, item_w, w_per_item, mask, B, N, topns_host,
+                              n_topn, gain_fn, disc_fn, gain_table, disc_table, ndcg, ndcg_w,
+                              mrr, mrr_w, raw, nullptr, stream);
 }

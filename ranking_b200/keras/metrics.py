@@ -103,7 +103,84 @@ class NDCGMetric(_RankingMetric):
     return config
 
 
-_KEY_TO_CLS = {RankingMetricKey.MRR: MRRMetric, RankingMetricKey.NDCG: NDCGMetric}
+class _TopnMetric(_RankingMetric):
+  _impl = None
+
+  def __init__(self, name=None, topn=None, dtype=None, ragged=False, **kwargs):
+    super().__init__(name=name, dtype=dtype, ragged=ragged, **kwargs)
+    self._topn = topn
+    self._metric = self._impl(name=name, topn=topn, ragged=ragged)
+
+  def get_config(self):
+    config = super().get_config()
+    config.update({'topn': self._topn})
+    return config
+
+
+class HitsMetric(_TopnMetric):
+  """keras/metrics.py:269-331."""
+  _impl = metrics_impl.HitsMetric
+
+
+class RecallMetric(_TopnMetric):
+  """keras/metrics.py:417-482."""
+  _impl = metrics_impl.RecallMetric
+
+
+class PrecisionMetric(_TopnMetric):
+  """keras/metrics.py:485-551."""
+  _impl = metrics_impl.PrecisionMetric
+
+
+class MeanAveragePrecisionMetric(_TopnMetric):
+  """keras/metrics.py:554-640."""
+  _impl = metrics_impl.MeanAveragePrecisionMetric
+
+
+class ARPMetric(_RankingMetric):
+  """keras/metrics.py:334-414."""
+
+  def __init__(self, name=None, dtype=None, ragged=False, **kwargs):
+    super().__init__(name=name, dtype=dtype, ragged=ragged, **kwargs)
+    self._metric = metrics_impl.ARPMetric(name=name, ragged=ragged)
+
+
+class OPAMetric(_RankingMetric):
+  """keras/metrics.py:948-1010."""
+
+  def __init__(self, name=None, dtype=None, ragged=False, **kwargs):
+    super().__init__(name=name, dtype=dtype, ragged=ragged, **kwargs)
+    self._metric = metrics_impl.OPAMetric(name=name, ragged=ragged)
+
+
+class DCGMetric(_RankingMetric):
+  """keras/metrics.py:799-877."""
+
+  def __init__(self, name=None, topn=None, gain_fn=None, rank_discount_fn=None,
+               dtype=None, ragged=False, **kwargs):
+    super().__init__(name=name, dtype=dtype, ragged=ragged, **kwargs)
+    self._topn = topn
+    self._gain_fn = gain_fn or utils.pow_minus_1
+    self._rank_discount_fn = rank_discount_fn or utils.log2_inverse
+    self._metric = metrics_impl.DCGMetric(
+        name=name, topn=topn, gain_fn=self._gain_fn,
+        rank_discount_fn=self._rank_discount_fn, ragged=ragged)
+
+  def get_config(self):
+    config = super().get_config()
+    config.update({'topn': self._topn, 'gain_fn': self._gain_fn,
+                   'rank_discount_fn': self._rank_discount_fn})
+    return config
+
+
+_KEY_TO_CLS = {
+    RankingMetricKey.MRR: MRRMetric, RankingMetricKey.NDCG: NDCGMetric,
+    RankingMetricKey.ARP: ARPMetric, RankingMetricKey.DCG: DCGMetric,
+    RankingMetricKey.PRECISION: PrecisionMetric,
+    RankingMetricKey.MAP: MeanAveragePrecisionMetric,
+    RankingMetricKey.ORDERED_PAIR_ACCURACY: OPAMetric,
+    RankingMetricKey.HITS: HitsMetric,
+}
 _ALL_KEYS = [v for k, v in vars(RankingMetricKey).items() if k.isupper()]
 
 
@@ -124,13 +201,20 @@ def get(key, name=None, dtype=None, topn=None, **kwargs):
 
 
 def default_keras_metrics(**kwargs):
-  """keras/metrics.py:131-153, restricted to the metrics on the hot path:
-  NDCG@{1,3,5,10}, MRR, NDCG."""
+  """keras/metrics.py:131-153: the same eleven metrics as the reference.  For
+  evaluation loops prefer `MetricGroup.default()`, which gets all of them from one
+  kernel launch per batch (one sort instead of eleven)."""
   list_kwargs = [
       dict(key='ndcg', topn=topn, name='metric/ndcg_{}'.format(topn), **kwargs)
       for topn in [1, 3, 5, 10]
   ] + [
+      dict(key='arp', name='metric/arp', **kwargs),
+      dict(key='ordered_pair_accuracy', name='metric/ordered_pair_accuracy',
+           **kwargs),
       dict(key='mrr', name='metric/mrr', **kwargs),
+      dict(key='precision', name='metric/precision', **kwargs),
+      dict(key='map', name='metric/map', **kwargs),
+      dict(key='dcg', name='metric/dcg', **kwargs),
       dict(key='ndcg', name='metric/ndcg', **kwargs),
   ]
   return [get(**kw) for kw in list_kwargs]
@@ -144,19 +228,41 @@ class MetricGroup(object):
   """
 
   def __init__(self, topns=(1, 3, 5, 10, None), gain_fn=None,
-               rank_discount_fn=None):
+               rank_discount_fn=None, ext=()):
     self.topns = tuple(topns)
     self._gain_fn = gain_fn
     self._rank_discount_fn = rank_discount_fn
+    self._ext = tuple(ext)   # extra metrics from the same launch (see `default`)
+    self._ext_state = None   # per ext metric: (sum v*w [T or 1], sum w)
     self._state = None    # [2T + 2]: sum ndcg_t*w (T), sum mrr_t*w (T), sum w_ndcg, sum w_mrr
+
+  @classmethod
+  def default(cls, **kwargs):
+    """All of `default_keras_metrics()` (keras/metrics.py:131-153) from one launch."""
+    return cls(topns=(1, 3, 5, 10, None),
+               ext=('arp', 'opa', 'precision', 'map', 'dcg'), **kwargs)
 
   def reset_state(self):
     self._state = None
+    self._ext_state = None
 
   def update_state(self, y_true, y_pred, sample_weight=None):
     o = metrics_impl.rank_metrics(y_true, y_pred, sample_weight, None,
                                   self.topns, self._gain_fn,
-                                  self._rank_discount_fn)
+                                  self._rank_discount_fn, ext=self._ext)
+    if self._ext:
+      parts = []
+      for key in self._ext:
+        if key in ('arp', 'opa'):
+          v, w = o[key][:, 0:1], o[key][:, 1]
+        elif key == 'dcg':
+          w = o['ndcg_w']
+          v = metrics_impl._safe_div(o['dcg'], w.unsqueeze(1))
+        else:
+          v, w = o[key], o['mrr_w']
+        parts.append(torch.cat([(v * w.unsqueeze(1)).sum(0), w.sum().reshape(1)]))
+      upd_ext = torch.cat(parts)
+      self._ext_state = upd_ext if self._ext_state is None else self._ext_state + upd_ext
     upd = torch.cat([
         (o['ndcg'] * o['ndcg_w'].unsqueeze(1)).sum(0),
         (o['mrr'] * o['mrr_w'].unsqueeze(1)).sum(0),
@@ -166,11 +272,26 @@ class MetricGroup(object):
   def all_reduce(self, group=None):
     if self._state is not None:
       dp.all_reduce_sum_(self._state, group)
+    if self._ext_state is not None:
+      dp.all_reduce_sum_(self._ext_state, group)
 
   def result(self):
     t = len(self.topns)
     s = self._state.double().cpu()
     out = {}
+    if self._ext_state is not None:
+      e = self._ext_state.double().cpu()
+      names = {'arp': 'arp', 'opa': 'ordered_pair_accuracy', 'precision': 'precision',
+               'map': 'map', 'dcg': 'dcg', 'recall': 'recall', 'hits': 'hits'}
+      pos = 0
+      for key in self._ext:
+        width = 1 if key in ('arp', 'opa') else t
+        den = e[pos + width]
+        for i in range(width):
+          k = self.topns[i] if width > 1 else None
+          suffix = '' if not k else '_{}'.format(k)
+          out['metric/' + names[key] + suffix] = float(e[pos + i] / den) if den else 0.0
+        pos += width + 1
     for i, k in enumerate(self.topns):
       suffix = '' if not k else '_{}'.format(k)
       out['metric/ndcg' + suffix] = float(s[i] / s[2 * t]) if s[2 * t] else 0.0

@@ -19,11 +19,15 @@ _DEFAULT_GAIN_FN = keras_utils.pow_minus_1            # metrics_impl.py:31
 _DEFAULT_RANK_DISCOUNT_FN = keras_utils.log2_inverse  # metrics_impl.py:33
 
 
+_EXT_KEYS = ('dcg', 'precision', 'recall', 'map', 'hits', 'arp', 'opa')
+
+
 def rank_metrics(labels, predictions, weights=None, mask=None, topns=(None,),
                  gain_fn=None, rank_discount_fn=None, want_ndcg=True,
-                 want_mrr=True):
+                 want_mrr=True, ext=()):
   """One launch of K4.  Returns dict(ndcg [B, T], ndcg_w [B], mrr [B, T],
-  mrr_w [B], raw [B, 5])."""
+  mrr_w [B], raw [B, 5]) plus, for every name in `ext` (subset of dcg, precision,
+  recall, map, hits [B, T] and arp, opa [B, 2] = value, weight), that tensor."""
   labels, predictions = _prep_2d(labels, predictions)
   w, wpi = _prep_weights(weights, predictions)
   m = _prep_mask(mask, predictions)
@@ -66,12 +70,19 @@ def rank_metrics(labels, predictions, weights=None, mask=None, topns=(None,),
                if want_mrr else None,
       'raw': torch.empty(b, 5, dtype=torch.float32, device=dev),
   }
-  _C.check(_C.lib.tfr_rank_metrics(
+  ext_struct = _C.MetricExt()
+  for key in ext:
+    if key not in _EXT_KEYS:
+      raise ValueError('unknown extended metric %r' % (key,))
+    out[key] = torch.empty(b, 2 if key in ('arp', 'opa') else t,
+                           dtype=torch.float32, device=dev)
+    setattr(ext_struct, key, out[key].data_ptr())
+  _C.check(_C.lib.tfr_rank_metrics_ext(
       _C.ptr(predictions), _C.ptr(labels), _C.ptr(w), wpi, _C.ptr(m), b, n,
       topn_arr, t, gain_enum, disc_enum, _C.ptr(gain_table),
       _C.ptr(disc_table), _C.ptr(out['ndcg']), _C.ptr(out['ndcg_w']),
       _C.ptr(out['mrr']), _C.ptr(out['mrr_w']), _C.ptr(out['raw']),
-      _C.stream()))
+      ctypes.byref(ext_struct) if ext else None, _C.stream()))
   del keep
   return out
 
@@ -125,3 +136,105 @@ class NDCGMetric(_RankingMetric):
     o = rank_metrics(labels, predictions, weights, mask, (self._topn,),
                      self._gain_fn, self._rank_discount_fn, want_mrr=False)
     return o['ndcg'], o['ndcg_w'].unsqueeze(1)
+
+
+def _safe_div(num, den):
+  return torch.where(den != 0, num / torch.where(den != 0, den, torch.ones_like(den)),
+                     torch.zeros_like(num))
+
+
+class _ExtMetric(_RankingMetric):
+  """Metrics served by the extended outputs of K4 (one sort for all of them)."""
+  _key = None
+  _weight = 'mrr_w'     # per-list weight rule with relevance = [label >= 1]
+
+  def __init__(self, name=None, topn=None, ragged=False):
+    super().__init__(ragged)
+    self._name = name
+    self._topn = topn
+
+  @property
+  def name(self):
+    return self._name
+
+  def compute(self, labels, predictions, weights=None, mask=None):
+    o = rank_metrics(labels, predictions, weights, mask, (self._topn,),
+                     want_ndcg=False, want_mrr=True, ext=(self._key,))
+    return o[self._key], o[self._weight].unsqueeze(1)
+
+
+class HitsMetric(_ExtMetric):
+  """metrics_impl.py:462-506."""
+  _key = 'hits'
+
+
+class RecallMetric(_ExtMetric):
+  """metrics_impl.py:539-561."""
+  _key = 'recall'
+
+
+class PrecisionMetric(_ExtMetric):
+  """metrics_impl.py:564-586."""
+  _key = 'precision'
+
+
+class MeanAveragePrecisionMetric(_ExtMetric):
+  """metrics_impl.py:589-628."""
+  _key = 'map'
+
+
+class ARPMetric(_RankingMetric):
+  """metrics_impl.py:509-536."""
+
+  def __init__(self, name=None, ragged=False):
+    super().__init__(ragged)
+    self._name = name
+
+  @property
+  def name(self):
+    return self._name
+
+  def compute(self, labels, predictions, weights=None, mask=None):
+    o = rank_metrics(labels, predictions, weights, mask, (None,), want_ndcg=False,
+                     want_mrr=False, ext=('arp',))
+    return o['arp'][:, 0:1], o['arp'][:, 1:2]
+
+
+class OPAMetric(_RankingMetric):
+  """metrics_impl.py:708-743."""
+
+  def __init__(self, name=None, ragged=False):
+    super().__init__(ragged)
+    self._name = name
+
+  @property
+  def name(self):
+    return self._name
+
+  def compute(self, labels, predictions, weights=None, mask=None):
+    o = rank_metrics(labels, predictions, weights, mask, (None,), want_ndcg=False,
+                     want_mrr=False, ext=('opa',))
+    return o['opa'][:, 0:1], o['opa'][:, 1:2]
+
+
+class DCGMetric(_RankingMetric):
+  """metrics_impl.py:673-705."""
+
+  def __init__(self, name=None, topn=None, gain_fn=_DEFAULT_GAIN_FN,
+               rank_discount_fn=_DEFAULT_RANK_DISCOUNT_FN, ragged=False):
+    super().__init__(ragged)
+    self._name = name
+    self._topn = topn
+    self._gain_fn = gain_fn
+    self._rank_discount_fn = rank_discount_fn
+
+  @property
+  def name(self):
+    return self._name
+
+  def compute(self, labels, predictions, weights=None, mask=None):
+    o = rank_metrics(labels, predictions, weights, mask, (self._topn,),
+                     self._gain_fn, self._rank_discount_fn, want_mrr=False,
+                     ext=('dcg',))
+    w = o['ndcg_w'].unsqueeze(1)
+    return _safe_div(o['dcg'], w), w

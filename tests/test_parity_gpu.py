@@ -253,6 +253,56 @@ def test_rank_metrics(cuda_api, oracle_api, n):
                                  rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize('n', [1, 7, 64, 200, 1000])
+def test_rank_metrics_extended(cuda_api, oracle_api, n):
+  """K4's extended outputs (Hits, ARP, Recall, Precision, MAP, DCG, OPA) on random
+  batches with padding, ties, item weights (some zero) and an explicit mask."""
+  scores, labels, item_w, _ = _batch(12, n, seed=100 + n)
+  g = torch.Generator().manual_seed(n)
+  item_w = torch.where(torch.rand(item_w.shape, generator=g) < 0.1,
+                       torch.zeros_like(item_w), item_w)
+  mask = (labels >= 0) & (torch.rand(labels.shape, generator=g) < 0.9)
+  MO, MC = oracle_api.metrics_impl, cuda_api.metrics_impl
+  for weights, m in ((None, None), (item_w, None), (item_w, mask)):
+    w64 = None if weights is None else weights.double()
+    wc = None if weights is None else weights.cuda()
+    mc = None if m is None else m.cuda()
+    for topn in (1, 5, None):
+      for cls in ('HitsMetric', 'RecallMetric', 'PrecisionMetric',
+                  'MeanAveragePrecisionMetric', 'DCGMetric'):
+        v, w = getattr(MC, cls)(topn=topn).compute(labels.cuda(), scores.cuda(), wc, mc)
+        rv, rw = getattr(MO, cls)(topn=topn).compute(labels.double(), scores.double(),
+                                                     w64, m)
+        torch.testing.assert_close(v.cpu().double(), rv, rtol=2e-5, atol=1e-6)
+        torch.testing.assert_close(w.cpu().double(), rw, rtol=2e-5, atol=1e-6)
+    for cls in ('ARPMetric', 'OPAMetric'):
+      v, w = getattr(MC, cls)().compute(labels.cuda(), scores.cuda(), wc, mc)
+      rv, rw = getattr(MO, cls)().compute(labels.double(), scores.double(), w64, m)
+      torch.testing.assert_close(v.cpu().double(), rv, rtol=2e-5, atol=1e-6)
+      torch.testing.assert_close(w.cpu().double(), rw, rtol=2e-5, atol=1e-5)
+
+
+def test_default_keras_metrics_one_launch(cuda_api, oracle_api):
+  """`MetricGroup.default()` (one launch per batch) equals the eleven separate
+  `default_keras_metrics()` objects (keras/metrics.py:131-153)."""
+  MC = __import__('ranking_b200').keras.metrics
+  scores, labels, item_w, _ = _batch(24, 50, seed=8)
+  objs = MC.default_keras_metrics()
+  assert [o.name for o in objs] == [
+      'metric/ndcg_1', 'metric/ndcg_3', 'metric/ndcg_5', 'metric/ndcg_10', 'metric/arp',
+      'metric/ordered_pair_accuracy', 'metric/mrr', 'metric/precision', 'metric/map',
+      'metric/dcg', 'metric/ndcg']
+  grp = MC.MetricGroup.default()
+  for lo in (0, 12):
+    y, s_, w = labels[lo:lo + 12].cuda(), scores[lo:lo + 12].cuda(), item_w[lo:lo + 12].cuda()
+    for o in objs:
+      o.update_state(y, s_, w)
+    grp.update_state(y, s_, w)
+  res = grp.result()
+  for o in objs:
+    assert abs(res[o.name] - float(o.result())) <= 1e-5 * max(1.0, abs(float(o.result()))), o.name
+
+
 def test_keras_metric_objects(cuda_api, oracle_api):
   scores, labels, _, _ = _batch(32, 40, seed=77)
   MC = __import__('ranking_b200').keras.metrics
