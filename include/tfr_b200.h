@@ -177,6 +177,22 @@ int tfr_misc_loss_fwd_bwd(const float* scores, const float* labels,
                           float* nonzero, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * GumbelSampler.sample (losses_impl.py:540-649): `sample_size` perturbed copies of
+ * every list; row b * sample_size + s of out_logits [B * sample_size, N] is
+ *   log(softmax((scores[b] + G) / temperature) + 1e-20),
+ *   G = -log(-log(u + 1e-20) + 1e-20),  items with label < 0 at log(1e-20).
+ * u in [0, 1) is a counter hash: top 24 bits of splitmix64_mix(seed +
+ * 0x9E3779B97F4A7C15 * (e + 1)) * 2^-24 for element e = (b * sample_size + s) * N + i
+ * (the reference draws tf.random.uniform).  Labels / weights are tiled by the caller.
+ * Forward: pass out_logits.  Backward: pass grad_out [B * sample_size, N] and
+ * grad_scores [B, N] with the same seed (the noise is regenerated, not stored).
+ * ------------------------------------------------------------------------- */
+int tfr_gumbel_sample(const float* scores, const float* labels, int B, int N,
+                      int sample_size, float temperature, uint64_t seed,
+                      float* out_logits, const float* grad_out,
+                      float* grad_scores, void* stream);
+
+/* ---------------------------------------------------------------------------
  * K4  NDCG@k and MRR@k for several cut-offs in one launch; per-list shared-memory
  * bitonic sort, ties by index, invalid entries last.  Replaces
  * metrics_impl.py:63-151, 228-266, 429-459, 631-670 and utils.py:115-164.

@@ -206,7 +206,39 @@ class MeanSquaredLoss(_RankingLoss):
     self._loss = losses_impl.MeanSquaredLoss(name=name)
 
 
+class _GumbelMixin(object):
+  """keras/losses.py:609-718, 1241-1341; `uniforms` must be supplied per call."""
+
+  def _init_gumbel(self, sample_size, gumbel_temperature):
+    self._gumbel_sampler = losses_impl.GumbelSampler(
+        sample_size=sample_size, temperature=gumbel_temperature)
+
+  def __call__(self, y_true, y_pred, sample_weight=None, uniforms=None):
+    gl, gs, gw = self._gumbel_sampler.sample(y_true, y_pred, sample_weight,
+                                             uniforms=uniforms)
+    return super().__call__(gl, gs, gw)
+
+
+class YetiLogisticLoss(_GumbelMixin, PairwiseLogisticLoss):
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, lambda_weight=None,
+               temperature=1.0, sample_size=8, gumbel_temperature=1.0, seed=None):
+    PairwiseLogisticLoss.__init__(
+        self, reduction, name, lambda_weight or YetiDCGLambdaWeight(), temperature)
+    self._init_gumbel(sample_size, gumbel_temperature)
+
+
+class GumbelApproxNDCGLoss(_GumbelMixin, ApproxNDCGLoss):
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, lambda_weight=None,
+               temperature=0.1, sample_size=8, gumbel_temperature=1.0, seed=None):
+    ApproxNDCGLoss.__init__(self, reduction, name, lambda_weight, temperature)
+    self._init_gumbel(sample_size, gumbel_temperature)
+
+
 _KEY_TO_CLS = {
+    'yeti_logistic_loss': YetiLogisticLoss,
+    'gumbel_approx_ndcg_loss': GumbelApproxNDCGLoss,
     'unique_softmax_loss': UniqueSoftmaxLoss,
     'list_mle_loss': ListMLELoss,
     'sigmoid_cross_entropy_loss': SigmoidCrossEntropyLoss,
@@ -227,6 +259,6 @@ def get(loss, reduction=Reduction.AUTO, lambda_weight=None, name=None, **kwargs)
     raise ValueError('unsupported loss: {}'.format(loss))
   kw = dict(reduction=reduction, name=name, **kwargs)
   if loss not in ('approx_ndcg_loss', 'approx_mrr_loss', 'sigmoid_cross_entropy_loss',
-                  'mean_squared_loss'):
+                  'mean_squared_loss', 'gumbel_approx_ndcg_loss'):
     kw['lambda_weight'] = lambda_weight
   return _KEY_TO_CLS[loss](**kw)

@@ -685,3 +685,37 @@ class ListMLELoss(_ListwiseLoss):
       sums = sums * self._lambda_weight.individual_weights(sorted_labels, ranks)
     nll = sums.sum(1, keepdim=True)
     return nll, torch.ones_like(nll)
+
+
+# ----------------------------------------------------------------------------
+# GumbelSampler (losses_impl.py:540-649) with the uniforms passed in explicitly
+# ----------------------------------------------------------------------------
+class GumbelSampler(object):
+
+  def __init__(self, name=None, sample_size=8, temperature=1.0, seed=None):
+    self._sample_size = sample_size
+    self._temperature = temperature
+
+  def sample(self, labels, logits, weights=None, uniforms=None):
+    """`uniforms` [B, S, N] in [0, 1): what `tf.random.uniform` returns in the
+    reference (:647-649); the caller supplies them so that the restatement is
+    deterministic."""
+    logits = torch.as_tensor(logits)
+    labels = torch.as_tensor(labels, dtype=logits.dtype)
+    b, n = labels.shape
+    s = self._sample_size
+    expanded_labels = labels.unsqueeze(1).repeat(1, s, 1).reshape(b * s, n)
+    u = torch.as_tensor(uniforms, dtype=logits.dtype).reshape(b, s, n)
+    eps = 1e-20
+    gumbel = -torch.log(-torch.log(u + eps) + eps)
+    sampled = (logits.unsqueeze(1).repeat(1, s, 1) + gumbel).reshape(b * s, n)
+    is_label_valid = utils.is_label_valid(expanded_labels)
+    sampled = torch.where(is_label_valid, sampled / self._temperature,
+                          math.log(1e-20) * torch.ones_like(sampled))
+    sampled = torch.log(torch.softmax(sampled, dim=1) + 1e-20)
+    expanded_weights = weights
+    if expanded_weights is not None:
+      w = torch.as_tensor(expanded_weights, dtype=logits.dtype)
+      w = w.reshape(b, 1, 1) if w.dim() == 1 else w.unsqueeze(1)
+      expanded_weights = w.repeat(1, s, 1).reshape(b * s, -1)
+    return expanded_labels, sampled, expanded_weights

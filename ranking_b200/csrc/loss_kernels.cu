@@ -901,6 +901,94 @@ misc_loss_kernel(const float* __restrict__ scores, const float* __restrict__ lab
 }
 
 // ---------------------------------------------------------------------------
+// Gumbel sampler (losses_impl.py:540-649): S perturbed copies of every list,
+//   out = log(softmax((s + G) / T) + 1e-20),  G = -log(-log(u + 1e-20) + 1e-20),
+// invalid labels (< 0) sit at log(1e-20) before the softmax.  u is a counter hash of
+// (seed, element) — see the header — so the backward pass regenerates it.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float hash_uniform01(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+__device__ __forceinline__ float gumbel_logit(float score, float label, float inv_t,
+                                              unsigned long long seed, unsigned long long idx) {
+  if (!(label >= 0.f)) return logf(1e-20f);
+  const float u = hash_uniform01(seed, idx);
+  const float g = -logf(-logf(u + 1e-20f) + 1e-20f);
+  return (score + g) * inv_t;
+}
+
+// grid (S, B): list (b, s) -> row b * S + s of out.
+__global__ void __launch_bounds__(kLossThreads)
+gumbel_sample_fwd_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                         int N, int S, float inv_t, unsigned long long seed,
+                         float* __restrict__ out) {
+  extern __shared__ float zs[];          // [N] + red[32]
+  float* red = zs + N;
+  const int s = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const size_t in_off = (size_t)b * N, row = (size_t)b * S + s;
+  float zmax = -CUDART_INF_F;
+  for (int i = tid; i < N; i += blockDim.x) {
+    const float z = gumbel_logit(scores[in_off + i], labels[in_off + i], inv_t, seed,
+                                 row * N + i);
+    zs[i] = z;
+    zmax = fmaxf(zmax, z);
+  }
+  zmax = block_max(zmax, red);
+  float se = 0.f;
+  for (int i = tid; i < N; i += blockDim.x) se += expf(zs[i] - zmax);
+  se = block_sum(se, red);
+  const float inv = 1.f / se;
+  for (int i = tid; i < N; i += blockDim.x)
+    out[row * N + i] = logf(expf(zs[i] - zmax) * inv + 1e-20f);
+}
+
+// grid (B): d scores[b, i] = sum_s (1/T) (a_i - p_i sum_j a_j), a_j = gout_j p_j / (p_j + 1e-20)
+__global__ void __launch_bounds__(kLossThreads)
+gumbel_sample_bwd_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                         int N, int S, float inv_t, unsigned long long seed,
+                         const float* __restrict__ gout, float* __restrict__ gin) {
+  extern __shared__ float zs[];          // z [N], acc [N], red[32]
+  float* acc = zs + N;
+  float* red = acc + N;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const size_t in_off = (size_t)b * N;
+  for (int i = tid; i < N; i += blockDim.x) acc[i] = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const size_t row = (size_t)b * S + s;
+    float zmax = -CUDART_INF_F;
+    for (int i = tid; i < N; i += blockDim.x) {
+      const float z = gumbel_logit(scores[in_off + i], labels[in_off + i], inv_t, seed,
+                                   row * N + i);
+      zs[i] = z;
+      zmax = fmaxf(zmax, z);
+    }
+    zmax = block_max(zmax, red);
+    float se = 0.f;
+    for (int i = tid; i < N; i += blockDim.x) se += expf(zs[i] - zmax);
+    se = block_sum(se, red);
+    const float inv = 1.f / se;
+    float sa = 0.f;
+    for (int i = tid; i < N; i += blockDim.x) {
+      const float p = expf(zs[i] - zmax) * inv;
+      const float a = gout[row * N + i] * (p / (p + 1e-20f));
+      zs[i] = p;                 // own element only: safe without a barrier
+      sa += a;
+      acc[i] += a;               // a_i part
+    }
+    sa = block_sum(sa, red);
+    for (int i = tid; i < N; i += blockDim.x) acc[i] -= zs[i] * sa;
+    __syncthreads();
+  }
+  for (int i = tid; i < N; i += blockDim.x)
+    gin[in_off + i] = labels[in_off + i] >= 0.f ? acc[i] * inv_t : 0.f;
+}
+
+// ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
 template <typename K>
@@ -1135,6 +1223,37 @@ extern "C" int tfr_misc_loss_fwd_bwd(const float* scores, const float* labels,
   }
 #undef TFR_MISC_CASE
   TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+extern "C" int tfr_gumbel_sample(const float* scores, const float* labels, int B, int N,
+                                 int sample_size, float temperature, uint64_t seed,
+                                 float* out_logits, const float* grad_out, float* grad_scores,
+                                 void* stream) {
+  int rc = check_list_args(scores, labels, B, N, temperature);
+  if (rc) return rc;
+  TFR_REQUIRE(sample_size >= 1 && sample_size <= 65535, "sample_size %d out of range", sample_size);
+  TFR_REQUIRE(out_logits || (grad_out && grad_scores),
+              "need out_logits (forward) or grad_out + grad_scores (backward)");
+  if (B == 0) return TFR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv_t = 1.f / temperature;
+  if (out_logits) {
+    const size_t smem = (size_t)(N + 32) * 4;
+    rc = prep_smem(gumbel_sample_fwd_kernel, smem);
+    if (rc) return rc;
+    gumbel_sample_fwd_kernel<<<dim3(sample_size, B), kLossThreads, smem, st>>>(
+        scores, labels, N, sample_size, inv_t, seed, out_logits);
+    TFR_LAUNCH_OK();
+  }
+  if (grad_out && grad_scores) {
+    const size_t smem = (size_t)(2 * N + 32) * 4;
+    rc = prep_smem(gumbel_sample_bwd_kernel, smem);
+    if (rc) return rc;
+    gumbel_sample_bwd_kernel<<<B, kLossThreads, smem, st>>>(scores, labels, N, sample_size, inv_t,
+                                                            seed, grad_out, grad_scores);
+    TFR_LAUNCH_OK();
+  }
   return TFR_OK;
 }
 

@@ -319,6 +319,80 @@ class ApproxMRRLoss(_ListwiseLoss):
   _default_temperature = 0.1
 
 
+class _GumbelMixin(object):
+  """Losses evaluated on `sample_size` Gumbel-perturbed copies of every list
+  (keras/losses.py:609-718, 1241-1341)."""
+
+  def _init_gumbel(self, name, sample_size, gumbel_temperature, seed, ragged):
+    self._sample_size = sample_size
+    self._gumbel_temperature = gumbel_temperature
+    self._seed = seed
+    self._gumbel_sampler = losses_impl.GumbelSampler(
+        name=name, sample_size=sample_size, temperature=gumbel_temperature, seed=seed,
+        ragged=ragged)
+    self._bufs = None
+
+  def __call__(self, y_true, y_pred, sample_weight=None):
+    gbl_labels, gbl_logits, gbl_weights = self._gumbel_sampler.sample(
+        y_true, y_pred, weights=sample_weight)
+    return super().__call__(gbl_labels, gbl_logits, gbl_weights)
+
+  def fused_fwd_bwd(self, y_true, y_pred, sample_weight, grad_out, per_list,
+                    total2):
+    """sample -> base loss on [B * S, N] -> sampler backward; `per_list` (sized for
+    B lists) receives the per-list means over the S samples."""
+    labels, logits = losses_impl._prep_2d(y_true, y_pred)
+    smp = self._gumbel_sampler
+    s_ = smp._sample_size
+    b, n = logits.shape
+    ex_labels, ex_w = smp.expand(labels, sample_weight)
+    if self._bufs is None or self._bufs[0].shape != (b * s_, n):
+      dev = logits.device
+      self._bufs = (torch.empty(b * s_, n, device=dev), torch.empty(b * s_, n, device=dev),
+                    torch.zeros(2, b * s_, device=dev))
+    sampled, g_ex, pl_ex = self._bufs
+    seed = smp.next_seed()
+    _C.check(_C.lib.tfr_gumbel_sample(
+        _C.ptr(logits), _C.ptr(labels), b, n, s_, float(smp._temperature), seed,
+        _C.ptr(sampled), None, None, _C.stream()))
+    super().fused_fwd_bwd(ex_labels, sampled, ex_w, g_ex, pl_ex, total2)
+    _C.check(_C.lib.tfr_gumbel_sample(
+        _C.ptr(logits), _C.ptr(labels), b, n, s_, float(smp._temperature), seed, None,
+        _C.ptr(g_ex), _C.ptr(grad_out), _C.stream()))
+    per_list.copy_(pl_ex.reshape(2, b, s_).mean(2))
+
+  def get_config(self):
+    config = super().get_config()
+    config.update({'sample_size': self._sample_size,
+                   'gumbel_temperature': self._gumbel_temperature,
+                   'seed': self._seed})
+    return config
+
+
+class YetiLogisticLoss(_GumbelMixin, PairwiseLogisticLoss):
+  """keras/losses.py:609-718: pairwise logistic loss with YetiDCGLambdaWeight on
+  Gumbel-sampled scores."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, lambda_weight=None,
+               temperature=1.0, sample_size=8, gumbel_temperature=1.0, seed=None,
+               ragged=False):
+    lambda_weight = lambda_weight or YetiDCGLambdaWeight()
+    PairwiseLogisticLoss.__init__(self, reduction, name, lambda_weight,
+                                  temperature=temperature, ragged=ragged)
+    self._init_gumbel(name, sample_size, gumbel_temperature, seed, ragged)
+
+
+class GumbelApproxNDCGLoss(_GumbelMixin, ApproxNDCGLoss):
+  """keras/losses.py:1241-1341."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, lambda_weight=None,
+               temperature=0.1, sample_size=8, gumbel_temperature=1.0, seed=None,
+               ragged=False):
+    ApproxNDCGLoss.__init__(self, reduction, name, lambda_weight,
+                            temperature=temperature, ragged=ragged)
+    self._init_gumbel(name, sample_size, gumbel_temperature, seed, ragged)
+
+
 class _MiscListwiseLoss(_ListwiseLoss):
   """Listwise losses served by K3b (tfr_misc_loss_fwd_bwd)."""
 
@@ -411,6 +485,7 @@ _KEY_TO_CLS = {
     RankingLossKey.APPROX_MRR_LOSS: ApproxMRRLoss,
     RankingLossKey.SIGMOID_CROSS_ENTROPY_LOSS: SigmoidCrossEntropyLoss,
     RankingLossKey.MEAN_SQUARED_LOSS: MeanSquaredLoss,
+    RankingLossKey.GUMBEL_APPROX_NDCG_LOSS: GumbelApproxNDCGLoss,
 }
 _KEY_TO_CLS_WITH_LAMBDA = {
     RankingLossKey.PAIRWISE_HINGE_LOSS: PairwiseHingeLoss,
@@ -420,6 +495,7 @@ _KEY_TO_CLS_WITH_LAMBDA = {
     RankingLossKey.SOFTMAX_LOSS: SoftmaxLoss,
     RankingLossKey.UNIQUE_SOFTMAX_LOSS: UniqueSoftmaxLoss,
     RankingLossKey.LIST_MLE_LOSS: ListMLELoss,
+    RankingLossKey.YETI_LOGISTIC_LOSS: YetiLogisticLoss,
 }
 
 

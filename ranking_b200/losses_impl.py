@@ -628,3 +628,76 @@ class ListMLELoss(_MiscListwiseLoss):
   """losses_impl.py:1541-1576.  Label ties are ordered by index (the reference
   shuffles them randomly with a fixed op seed); invalid items come last."""
   _kind = 'list_mle'
+
+
+# ----------------------------------------------------------------------------
+# GumbelSampler (losses_impl.py:540-649)
+# ----------------------------------------------------------------------------
+class _GumbelFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, logits, labels, sample_size, temperature, seed):
+    b, n = logits.shape
+    out = torch.empty(b * sample_size, n, dtype=torch.float32, device=logits.device)
+    _C.check(_C.lib.tfr_gumbel_sample(
+        _C.ptr(logits), _C.ptr(labels), b, n, sample_size, float(temperature), seed,
+        _C.ptr(out), None, None, _C.stream()))
+    ctx.save_for_backward(logits, labels)
+    ctx.cfg = (sample_size, float(temperature), seed)
+    return out
+
+  @staticmethod
+  def backward(ctx, g_out):
+    logits, labels = ctx.saved_tensors
+    sample_size, temperature, seed = ctx.cfg
+    b, n = logits.shape
+    gin = torch.empty_like(logits)
+    g_out = g_out.contiguous()
+    _C.check(_C.lib.tfr_gumbel_sample(
+        _C.ptr(logits), _C.ptr(labels), b, n, sample_size, temperature, seed, None,
+        _C.ptr(g_out), _C.ptr(gin), _C.stream()))
+    return gin, None, None, None, None
+
+
+class GumbelSampler(object):
+  """losses_impl.py:540-645.  The uniforms are a counter hash of (seed, element)
+  (include/tfr_b200.h, tfr_gumbel_sample); `seed=None` draws a fresh base seed and
+  every `sample` call advances a counter, so consecutive calls differ like the
+  reference's stateful `tf.random.uniform`."""
+
+  def __init__(self, name=None, sample_size=8, temperature=1.0, seed=None,
+               ragged=False):
+    if ragged:
+      raise NotImplementedError('ragged=True: pass dense padded tensors.')
+    self._name = name
+    self._sample_size = int(sample_size)
+    self._temperature = temperature
+    self._seed = seed
+    self._base = int(seed if seed is not None else torch.seed()) & 0xFFFFFFFF
+    self._calls = 0
+
+  def next_seed(self):
+    self._calls += 1
+    return (self._base << 32) | (self._calls & 0xFFFFFFFF)
+
+  def expand(self, labels, weights):
+    """Tiled labels [B*S, N] and weights ([B*S, 1] or [B*S, N])."""
+    s = self._sample_size
+    b, n = labels.shape
+    ex_labels = labels.unsqueeze(1).expand(b, s, n).reshape(b * s, n).contiguous()
+    ex_w = None
+    if weights is not None:
+      w = _as_f32(weights, labels.device, 'weights')
+      if w.dim() == 0:
+        w = w.expand(b)
+      if w.dim() == 1:
+        w = w.reshape(b, 1)
+      ex_w = w.unsqueeze(1).expand(b, s, w.shape[1]).reshape(b * s, -1).contiguous()
+    return ex_labels, ex_w
+
+  def sample(self, labels, logits, weights=None):
+    labels, logits = _prep_2d(labels, logits)
+    ex_labels, ex_w = self.expand(labels, weights)
+    sampled = _GumbelFn.apply(logits, labels, self._sample_size, self._temperature,
+                              self.next_seed())
+    return ex_labels, sampled, ex_w

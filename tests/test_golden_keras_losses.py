@@ -217,3 +217,49 @@ def test_get_factory(api):
   assert isinstance(K.get('softmax_loss'), K.SoftmaxLoss)
   with pytest.raises(ValueError):
     K.get('no_such_loss')
+
+
+# ---------------------------------------------------------------------------
+# Gumbel-sampled losses (keras/losses_test.py:604-645; losses_impl.py:540-649)
+# ---------------------------------------------------------------------------
+def test_gumbel_sampler_transform(oracle_api):
+  """log(softmax((s + G) / T) + 1e-20) with G = -log(-log(u + eps) + eps); labels and
+  weights tiled sample-major per list."""
+  L = oracle_api.losses_impl
+  scores = [[1.0, 2.0, 0.5]]
+  labels = [[1.0, 0.0, -1.0]]
+  u = [[[0.5, 0.25, 0.9], [0.1, 0.7, 0.3]]]
+  smp = L.GumbelSampler(sample_size=2, temperature=2.0)
+  el, sl, ew = smp.sample(oracle_api.t(labels), oracle_api.t(scores),
+                          oracle_api.t([[3.0]]), uniforms=oracle_api.t(u))
+  rows = []
+  for srow in u[0]:
+    z = [(s + -math.log(-math.log(x + 1e-20) + 1e-20)) / 2.0 for s, x in zip(scores[0], srow)]
+    z[2] = math.log(1e-20)
+    m = max(z)
+    den = sum(math.exp(v - m) for v in z)
+    rows.append([math.log(math.exp(v - m) / den + 1e-20) for v in z])
+  torch.testing.assert_close(sl.double(), torch.tensor(rows, dtype=torch.float64),
+                             rtol=1e-5, atol=1e-5)
+  assert el.tolist() == [labels[0], labels[0]]
+  assert ew.tolist() == [[3.0], [3.0]]
+
+
+def test_gumbel_approx_ndcg_reference_case(api):
+  """keras/losses_test.py:604-645: the reference lists the scores its sampler drew
+  (seed 1); ApproxNDCG on those expanded lists must give its expected value."""
+  sampled = [[-.291, -1.643, -2.826], [-.0866, -2.924, -3.530],
+             [-12.42, -9.492, -7.939e-5], [-8.859, -6.830, -1.223e-3],
+             [-.8930, -.5266, -45.80183], [-.6650, -.7220, -45.94149]]
+  ex_labels = [[0., 2., 1.], [0., 2., 1.], [1., 0., 3.], [1., 0., 3.],
+               [0., 0., 0.], [0., 0., 0.]]
+  loss = api.keras_losses.ApproxNDCGLoss()
+  got = float(loss(api.t(ex_labels), api.t(sampled)))
+  want = -(2 * (1 / (3 / ln(2) + 1 / ln(3))) * (3 / ln(3) + 1 / ln(4)) + 2 *
+           (1 / (7 / ln(2) + 1 / ln(3))) * (7 / ln(2) + 1 / ln(4))) / 6
+  assert abs(got - want) < 5e-4
+  ex_w = [[2.], [2.], [1.], [1.], [1.], [1.]]
+  got = float(loss(api.t(ex_labels), api.t(sampled), api.t(ex_w)))
+  want = -(2 * 2 * (1 / (3 / ln(2) + 1 / ln(3))) * (3 / ln(3) + 1 / ln(4)) + 1 * 2 *
+           (1 / (7 / ln(2) + 1 / ln(3))) * (7 / ln(2) + 1 / ln(4))) / 6
+  assert abs(got - want) < 5e-4

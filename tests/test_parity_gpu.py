@@ -146,6 +146,72 @@ def test_fused_train_step_more_losses(oracle_api, key):
   assert _rel_err(tower.flat.detach(), want.detach()) <= 1e-5
 
 
+def _hash_uniforms(seed, numel):
+  """The uniforms of tfr_gumbel_sample / dropout (include/tfr_b200.h)."""
+  import numpy as np
+  with np.errstate(over='ignore'):
+    idx = np.arange(numel, dtype=np.uint64)
+    z = np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * (idx + np.uint64(1))
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    z = z ^ (z >> np.uint64(31))
+  return torch.from_numpy((z >> np.uint64(40)).astype(np.float32) *
+                          np.float32(1.0 / 16777216.0))
+
+
+@pytest.mark.parametrize('n', [1, 9, 200])
+def test_gumbel_sampler(cuda_api, oracle_api, n):
+  b, s_ = 5, 3
+  scores, labels, item_w, _ = _batch(b, n, seed=40 + n)
+  smp = cuda_api.losses_impl.GumbelSampler(sample_size=s_, temperature=0.7, seed=123)
+  sc = scores.cuda().requires_grad_()
+  el, sl, ew = smp.sample(labels.cuda(), sc, item_w.cuda())
+  seed = (123 << 32) | 1
+  u = _hash_uniforms(seed, b * s_ * n).reshape(b, s_, n)
+  so = scores.double().requires_grad_()
+  rl, rs, rw = oracle_api.losses_impl.GumbelSampler(sample_size=s_, temperature=0.7).sample(
+      labels.double(), so, item_w.double(), uniforms=u.double())
+  assert torch.equal(el.cpu().double(), rl)
+  torch.testing.assert_close(ew.cpu().double(), rw)
+  valid = rl >= 0
+  torch.testing.assert_close(sl.detach().cpu().double()[valid], rs.detach()[valid],
+                             rtol=1e-5, atol=2e-5)
+  up = torch.randn(b * s_, n, generator=torch.Generator().manual_seed(n)).double() * valid
+  (sl * up.float().cuda()).sum().backward()
+  (rs * up).sum().backward()
+  assert _rel_err(sc.grad, so.grad) <= 2e-5 or float(so.grad.abs().max()) < 1e-12
+
+
+@pytest.mark.parametrize('key', ['yeti_logistic_loss', 'gumbel_approx_ndcg_loss'])
+@pytest.mark.parametrize('wkind', ['none', 'list', 'item'])
+def test_gumbel_losses(cuda_api, oracle_api, key, wkind):
+  """YetiLogisticLoss / GumbelApproxNDCGLoss (keras/losses.py:609-718, 1241-1341) with
+  the oracle fed the same uniforms; autograd path and fused training path."""
+  b, n, s_ = 6, 30, 4
+  scores, labels, item_w, list_w = _batch(b, n, seed=61)
+  weights = {'none': None, 'list': list_w, 'item': item_w}[wkind]
+  lc = cuda_api.keras_losses.get(key, sample_size=s_, seed=7)
+  lo = oracle_api.keras_losses.get(key, sample_size=s_, seed=7)
+  u = _hash_uniforms((7 << 32) | 1, b * s_ * n).reshape(b, s_, n).double()
+  sc = scores.cuda().requires_grad_()
+  wc = None if weights is None else weights.cuda()
+  got = lc(labels.cuda(), sc, wc)
+  got.backward()
+  so = scores.double().requires_grad_()
+  ref = lo(labels.double(), so, None if weights is None else weights.double(), uniforms=u)
+  ref.backward()
+  assert abs(float(got.detach()) - float(ref.detach())) <= 2e-5 * max(1., abs(float(ref.detach())))
+  assert _rel_err(sc.grad, so.grad) <= 5e-5
+  # fused path: same seed -> same numbers without autograd
+  lc._gumbel_sampler._calls = 0
+  grad = torch.empty(b, n, device='cuda')
+  per_list = torch.empty(2, b, device='cuda')
+  total2 = torch.zeros(2, device='cuda')
+  lc.fused_fwd_bwd(labels.cuda(), scores.cuda(), wc, grad, per_list, total2)
+  assert abs(float(total2[0]) - float(ref.detach())) <= 2e-5 * max(1., abs(float(ref.detach())))
+  assert _rel_err(grad, so.grad) <= 5e-5
+
+
 def test_softmax_with_dcg_lambda(cuda_api, oracle_api):
   scores, labels, item_w, _ = _batch(8, 50, seed=3)
   KC, KO = cuda_api.keras_losses, oracle_api.keras_losses
