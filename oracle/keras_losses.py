@@ -162,6 +162,29 @@ class SoftmaxLoss(_ListwiseLoss):
     return _keras_compute_weighted_loss(losses, sw, self.reduction)
 
 
+class CalibratedSoftmaxLoss(SoftmaxLoss):
+  """keras/losses.py:836-943."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, lambda_weight=None,
+               temperature=1.0, virtual_label=0.0):
+    super().__init__(reduction, name, lambda_weight, temperature)
+    self._virtual_label = virtual_label
+
+  def __call__(self, y_true, y_pred, sample_weight=None):
+    y_pred = torch.as_tensor(y_pred)
+    y_true = torch.as_tensor(y_true, dtype=y_pred.dtype)
+    b = y_true.shape[0]
+    y_true = torch.cat([y_true, torch.ones(b, 1, dtype=y_true.dtype) *
+                        self._virtual_label], 1)
+    y_pred = torch.cat([y_pred, torch.zeros(b, 1, dtype=y_pred.dtype)], 1)
+    if sample_weight is not None:
+      sample_weight = torch.as_tensor(sample_weight, dtype=y_pred.dtype)
+      if sample_weight.dim() == 2 and sample_weight.shape[1] > 1:
+        sample_weight = torch.cat(
+            [sample_weight, torch.ones(b, 1, dtype=sample_weight.dtype)], 1)
+    return super().__call__(y_true, y_pred, sample_weight)
+
+
 class ApproxNDCGLoss(_ListwiseLoss):
   """keras/losses.py:1164-1237."""
   _impl = losses_impl.ApproxNDCGLoss
@@ -248,6 +271,7 @@ _KEY_TO_CLS = {
     'pairwise_soft_zero_one_loss': PairwiseSoftZeroOneLoss,
     'pairwise_mse_loss': PairwiseMSELoss,
     'softmax_loss': SoftmaxLoss,
+    'calibrated_softmax_loss': CalibratedSoftmaxLoss,
     'approx_ndcg_loss': ApproxNDCGLoss,
     'approx_mrr_loss': ApproxMRRLoss,
 }

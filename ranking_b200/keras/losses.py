@@ -307,6 +307,42 @@ class SoftmaxLoss(_ListwiseLoss):
     return _keras_reduce(losses * weights, None, self.reduction)
 
 
+class CalibratedSoftmaxLoss(SoftmaxLoss):
+  """keras/losses.py:836-943: softmax loss over the list plus one virtual item with
+  score 0, label `virtual_label` and weight 1 (anchors the scores to zero)."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, lambda_weight=None,
+               temperature=1.0, virtual_label=0.0, **kwargs):
+    super().__init__(reduction, name, lambda_weight, temperature, False)
+    assert virtual_label >= 0, 'Virtual label must be non-negative.'
+    self._virtual_label = virtual_label
+
+  def _augment(self, y_true, y_pred, sample_weight):
+    labels, logits = losses_impl._prep_2d(y_true, y_pred)
+    b = labels.shape[0]
+    labels = torch.cat([labels, labels.new_full((b, 1), float(self._virtual_label))], 1)
+    logits = torch.cat([logits, logits.new_zeros((b, 1))], 1)
+    if sample_weight is not None and torch.is_tensor(sample_weight) and \
+        sample_weight.dim() == 2 and sample_weight.shape[1] > 1:
+      sample_weight = torch.cat([sample_weight, sample_weight.new_ones((b, 1))], 1)
+    return labels, logits, sample_weight
+
+  def __call__(self, y_true, y_pred, sample_weight=None):
+    return super().__call__(*self._augment(y_true, y_pred, sample_weight))
+
+  def fused_fwd_bwd(self, y_true, y_pred, sample_weight, grad_out, per_list,
+                    total2):
+    labels, logits, w = self._augment(y_true, y_pred, sample_weight)
+    g = torch.empty_like(logits)
+    super().fused_fwd_bwd(labels, logits, w, g, per_list, total2)
+    grad_out.copy_(g[:, :-1])
+
+  def get_config(self):
+    config = super().get_config()
+    config.update({'virtual_label': self._virtual_label})
+    return config
+
+
 class ApproxNDCGLoss(_ListwiseLoss):
   """keras/losses.py:1164-1237."""
   _impl = losses_impl.ApproxNDCGLoss
@@ -493,6 +529,7 @@ _KEY_TO_CLS_WITH_LAMBDA = {
     RankingLossKey.PAIRWISE_SOFT_ZERO_ONE_LOSS: PairwiseSoftZeroOneLoss,
     RankingLossKey.PAIRWISE_MSE_LOSS: PairwiseMSELoss,
     RankingLossKey.SOFTMAX_LOSS: SoftmaxLoss,
+    RankingLossKey.CALIBRATED_SOFTMAX_LOSS: CalibratedSoftmaxLoss,
     RankingLossKey.UNIQUE_SOFTMAX_LOSS: UniqueSoftmaxLoss,
     RankingLossKey.LIST_MLE_LOSS: ListMLELoss,
     RankingLossKey.YETI_LOGISTIC_LOSS: YetiLogisticLoss,

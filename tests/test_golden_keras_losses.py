@@ -263,3 +263,22 @@ def test_gumbel_approx_ndcg_reference_case(api):
   want = -(2 * 2 * (1 / (3 / ln(2) + 1 / ln(3))) * (3 / ln(3) + 1 / ln(4)) + 1 * 2 *
            (1 / (7 / ln(2) + 1 / ln(3))) * (7 / ln(2) + 1 / ln(4))) / 6
   assert abs(got - want) < 5e-4
+
+
+def test_calibrated_softmax_loss(api):
+  """keras/losses_test.py:936-972."""
+  scores = [[1.0, 3.0, 2.0], [1.0, 2.0, 3.0], [1.0, 2.0, 3.0]]
+  labels = [[0.0, 0.0, 1.0], [0.0, 0.0, 2.0], [0.0, 0.0, 0.0]]
+  weights = [[2.0], [1.0], [1.0]]
+  vl = 0.5
+  den = lambda values: sum(math.exp(v) for v in values)
+  sm = lambda values: [math.exp(v) / (den(values) + 1.0) for v in values]
+  loss = api.keras_losses.get('calibrated_softmax_loss', virtual_label=vl)
+  _close(loss(api.t(labels), api.t(scores)),
+         -(ln(sm(scores[0])[2]) + ln(sm(scores[1])[2]) * 2.0 -
+           vl * ln(1.0 + den(scores[0])) - vl * ln(1.0 + den(scores[1])) -
+           vl * ln(1.0 + den(scores[2]))) / 3.0)
+  _close(loss(api.t(labels), api.t(scores), api.t(weights)),
+         -(ln(sm(scores[0])[2]) * 2.0 + ln(sm(scores[1])[2]) * 2.0 * 1.0 -
+           vl * ln(1.0 + den(scores[0])) * 2.0 - vl * ln(1.0 + den(scores[1])) -
+           vl * ln(1.0 + den(scores[2]))) / 3.0)

@@ -117,6 +117,9 @@ def test_list_mle_lambda_weight_and_temperature(cuda_api, oracle_api):
                      temperature=0.5), scores, labels, item_w)
   _check_loss_and_grad(KC.UniqueSoftmaxLoss(temperature=2.0),
                        KO.UniqueSoftmaxLoss(temperature=2.0), scores, labels, None)
+  for w in (None, item_w, item_w[:, :1]):
+    _check_loss_and_grad(KC.CalibratedSoftmaxLoss(virtual_label=0.7),
+                         KO.CalibratedSoftmaxLoss(virtual_label=0.7), scores, labels, w)
 
 
 @pytest.mark.parametrize('key', ['unique_softmax_loss', 'list_mle_loss',
