@@ -189,7 +189,7 @@ def run_reference(args):
               'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
   }
-  print(json.dumps(line), flush=True)
+  emit(line)
 
 
 def workload_config(n_gpus, extra=None):
@@ -371,7 +371,7 @@ def run_gpu(args):
           'sample': '%d lists/step x %d steps of the same workload (oracle: '
                     'torch-CPU restatement of the reference algorithm)' %
                     (sample, args.cpu_steps)}
-    print(json.dumps(line), flush=True)
+    emit(line)
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
@@ -416,6 +416,19 @@ def phase_times(trainer, resident, steps, stream):
   return {k: v / steps for k, v in acc.items()}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+  """Writes the JSON line to the process's real stdout (see main)."""
+  data = (json.dumps(line) + '\n').encode()
+  if _REAL_STDOUT is None:
+    sys.stdout.write(data.decode())
+    sys.stdout.flush()
+  else:
+    os.write(_REAL_STDOUT, data)
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -432,6 +445,13 @@ def main():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3)
+  # The contract is ONE JSON line on stdout.  Libraries print banners there (e.g.
+  # "NCCL version ..." at communicator creation), so everything but the final line is
+  # routed to stderr: fd 1 is parked and only `emit` writes to it.
+  global _REAL_STDOUT
+  sys.stdout.flush()
+  _REAL_STDOUT = os.dup(1)
+  os.dup2(2, 1)
   if args.impl == 'reference':
     run_reference(args)
   else:
