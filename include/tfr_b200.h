@@ -176,6 +176,18 @@ int tfr_misc_loss_fwd_bwd(const float* scores, const float* labels,
                           float* grad, float* row, float* loss, float* weight,
                           float* nonzero, void* stream);
 
+/* OrdinalLoss (losses_impl.py:1850-1918): scores [B, N, K] (K = ordinal_size heads per
+ * item), head k against [label >= k + 1] (+ the fractional part with
+ * use_fraction_label); grad [B, N, K]; row / loss / weight / nonzero as for the
+ * pointwise kinds of tfr_misc_loss_fwd_bwd. */
+int tfr_ordinal_loss_fwd_bwd(const float* scores, const float* labels,
+                             const float* item_w, int w_per_item,
+                             const uint8_t* mask, int B, int N, int K,
+                             float temperature, int use_fraction_label,
+                             float grad_scale, float* grad, float* row,
+                             float* loss, float* weight, float* nonzero,
+                             void* stream);
+
 /* ---------------------------------------------------------------------------
  * GumbelSampler.sample (losses_impl.py:540-649): `sample_size` perturbed copies of
  * every list; row b * sample_size + s of out_logits [B * sample_size, N] is

@@ -259,7 +259,18 @@ class GumbelApproxNDCGLoss(_GumbelMixin, ApproxNDCGLoss):
     self._init_gumbel(sample_size, gumbel_temperature)
 
 
+class OrdinalLoss(_RankingLoss):
+  """keras/losses.py:1603-1656."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, ordinal_size=1,
+               use_fraction_label=False):
+    super().__init__(reduction, name)
+    self._loss = losses_impl.OrdinalLoss(name=name, ordinal_size=ordinal_size,
+                                         use_fraction_label=use_fraction_label)
+
+
 _KEY_TO_CLS = {
+    'ordinal_loss': OrdinalLoss,
     'yeti_logistic_loss': YetiLogisticLoss,
     'gumbel_approx_ndcg_loss': GumbelApproxNDCGLoss,
     'unique_softmax_loss': UniqueSoftmaxLoss,
@@ -283,6 +294,6 @@ def get(loss, reduction=Reduction.AUTO, lambda_weight=None, name=None, **kwargs)
     raise ValueError('unsupported loss: {}'.format(loss))
   kw = dict(reduction=reduction, name=name, **kwargs)
   if loss not in ('approx_ndcg_loss', 'approx_mrr_loss', 'sigmoid_cross_entropy_loss',
-                  'mean_squared_loss', 'gumbel_approx_ndcg_loss'):
+                  'mean_squared_loss', 'gumbel_approx_ndcg_loss', 'ordinal_loss'):
     kw['lambda_weight'] = lambda_weight
   return _KEY_TO_CLS[loss](**kw)

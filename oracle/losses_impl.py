@@ -719,3 +719,47 @@ class GumbelSampler(object):
       w = w.reshape(b, 1, 1) if w.dim() == 1 else w.unsqueeze(1)
       expanded_weights = w.repeat(1, s, 1).reshape(b * s, -1)
     return expanded_labels, sampled, expanded_weights
+
+
+class OrdinalLoss(_PointwiseLoss):
+  """losses_impl.py:1850-1918."""
+
+  def __init__(self, name=None, ordinal_size=1, temperature=1.0,
+               use_fraction_label=False):
+    super().__init__(name, None, temperature)
+    self._ordinal_size = ordinal_size
+    self._use_fraction_label = use_fraction_label
+
+  def _labels_to_ordinals(self, labels, mask):
+    one_to_n = torch.arange(1, self._ordinal_size + 1).to(labels.dtype)
+    unsqueezed = labels.unsqueeze(2).repeat(1, 1, self._ordinal_size)
+    ordinals = torch.where(unsqueezed >= one_to_n, torch.ones_like(unsqueezed),
+                           torch.zeros_like(unsqueezed))
+    if self._use_fraction_label:
+      fractions = unsqueezed - one_to_n + 1.0
+      fractions = torch.where((fractions > 0.0) & (fractions < 1.0), fractions,
+                              torch.zeros_like(fractions))
+      ordinals = ordinals + fractions
+    return torch.where(mask.unsqueeze(-1), ordinals, torch.zeros_like(ordinals))
+
+  def _prepare_and_validate_params(self, labels, logits, weights, mask):
+    logits = torch.as_tensor(logits)
+    labels = torch.as_tensor(labels, dtype=logits.dtype)
+    if mask is None:
+      mask = utils.is_label_valid(labels)
+    if weights is None:
+      weights = 1.0
+    return labels, logits, torch.as_tensor(weights, dtype=logits.dtype), torch.as_tensor(mask)
+
+  def _compute_unreduced_loss_impl(self, labels, logits, mask=None):
+    if mask is None:
+      mask = utils.is_label_valid(labels)
+    if logits.dim() != 3:
+      raise ValueError('Predictions for ordinal loss must have rank 3.')
+    labels = torch.where(mask, labels, torch.zeros_like(labels))
+    logits = torch.where(mask.unsqueeze(-1), logits, torch.zeros_like(logits))
+    ordinals = self._labels_to_ordinals(labels, mask)
+    ce = torch.clamp(logits, min=0) - logits * ordinals + torch.log1p(
+        torch.exp(-logits.abs()))
+    losses = torch.where(mask.unsqueeze(-1), ce, torch.zeros_like(ce))
+    return losses.sum(-1), mask.to(logits.dtype)

@@ -989,6 +989,63 @@ gumbel_sample_bwd_kernel(const float* __restrict__ scores, const float* __restri
 }
 
 // ---------------------------------------------------------------------------
+// OrdinalLoss (losses_impl.py:1850-1918): K ordinal heads per item, head k trained
+// with sigmoid cross entropy against [label >= k + 1] (plus the fraction when asked).
+// Pointwise weights / outputs as in K3b.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossThreads)
+ordinal_loss_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                    const float* __restrict__ item_w, int w_per_item,
+                    const uint8_t* __restrict__ mask, int N, int K, float temperature,
+                    int use_fraction, float grad_scale, float* __restrict__ grad,
+                    float* __restrict__ row, float* __restrict__ loss,
+                    float* __restrict__ weight, float* __restrict__ nonzero) {
+  __shared__ float red[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const size_t off = (size_t)b * N;
+  const float gs = grad_scale / temperature;
+  float sl = 0.f, sw = 0.f, nz = 0.f;
+  for (int i = tid; i < N; i += blockDim.x) {
+    const float lab = labels[off + i];
+    const bool lvalid = lab >= 0.f;
+    const bool mvalid = mask ? (mask[off + i] != 0) : lvalid;
+    float wv = 1.f;
+    if (item_w) wv = w_per_item ? item_w[off + i] : item_w[b];
+    const float w = (lvalid && mvalid) ? wv : 0.f;
+    const float l = mvalid ? lab : 0.f;
+    float f = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float z = mvalid ? scores[(off + i) * K + k] / temperature : 0.f;
+      float o = l >= (float)(k + 1) ? 1.f : 0.f;
+      if (use_fraction) {
+        const float fr = l - (float)k;            // labels - one_to_n + 1
+        if (fr > 0.f && fr < 1.f) o += fr;
+      }
+      if (!mvalid) o = 0.f;
+      const float e = expf(-fabsf(z));
+      const float ce = fmaxf(z, 0.f) - z * o + log1pf(e);
+      f += mvalid ? ce : 0.f;
+      if (grad) {
+        const float sg = z >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+        grad[(off + i) * K + k] = mvalid ? (sg - o) * w * gs : 0.f;
+      }
+    }
+    if (row) row[off + i] = f * w;
+    sl += f * w;
+    sw += w;
+    nz += w != 0.f ? 1.f : 0.f;
+  }
+  sl = block_sum(sl, red);
+  sw = block_sum(sw, red);
+  nz = block_sum(nz, red);
+  if (tid == 0) {
+    loss[b] = sl;
+    if (weight) weight[b] = sw;
+    if (nonzero) nonzero[b] = nz;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------
 template <typename K>
@@ -1254,6 +1311,24 @@ extern "C" int tfr_gumbel_sample(const float* scores, const float* labels, int B
                                                             seed, grad_out, grad_scores);
     TFR_LAUNCH_OK();
   }
+  return TFR_OK;
+}
+
+extern "C" int tfr_ordinal_loss_fwd_bwd(const float* scores, const float* labels,
+                                        const float* item_w, int w_per_item,
+                                        const uint8_t* mask, int B, int N, int K,
+                                        float temperature, int use_fraction_label,
+                                        float grad_scale, float* grad, float* row, float* loss,
+                                        float* weight, float* nonzero, void* stream) {
+  int rc = check_list_args(scores, labels, B, N, temperature);
+  if (rc) return rc;
+  TFR_REQUIRE(K >= 1, "ordinal_size %d must be >= 1", K);
+  TFR_REQUIRE(loss != nullptr, "loss must not be NULL");
+  if (B == 0) return TFR_OK;
+  ordinal_loss_kernel<<<B, kLossThreads, 0, (cudaStream_t)stream>>>(
+      scores, labels, item_w, w_per_item, mask, N, K, temperature, use_fraction_label,
+      grad_scale, grad, row, loss, weight, nonzero);
+  TFR_LAUNCH_OK();
   return TFR_OK;
 }
 

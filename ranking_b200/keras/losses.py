@@ -516,7 +516,22 @@ class MeanSquaredLoss(_PointwiseLoss):
         name='{}_impl'.format(name) if name else None, ragged=ragged)
 
 
+class OrdinalLoss(_PointwiseLoss):
+  """keras/losses.py:1603-1656: y_pred [B, N, ordinal_size]."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, ragged=False,
+               ordinal_size=1, use_fraction_label=False):
+    super().__init__(reduction, name, ragged)
+    self._loss = losses_impl.OrdinalLoss(
+        name='{}_impl'.format(name) if name else None, ordinal_size=ordinal_size,
+        ragged=ragged, use_fraction_label=use_fraction_label)
+
+  def fused_fwd_bwd(self, *args, **kwargs):
+    raise NotImplementedError('OrdinalLoss needs a multi-head scorer; use autograd')
+
+
 _KEY_TO_CLS = {
+    RankingLossKey.ORDINAL_LOSS: OrdinalLoss,
     RankingLossKey.APPROX_NDCG_LOSS: ApproxNDCGLoss,
     RankingLossKey.APPROX_MRR_LOSS: ApproxMRRLoss,
     RankingLossKey.SIGMOID_CROSS_ENTROPY_LOSS: SigmoidCrossEntropyLoss,

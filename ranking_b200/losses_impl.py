@@ -701,3 +701,64 @@ class GumbelSampler(object):
     sampled = _GumbelFn.apply(logits, labels, self._sample_size, self._temperature,
                               self.next_seed())
     return ex_labels, sampled, ex_w
+
+
+# ----------------------------------------------------------------------------
+# OrdinalLoss (losses_impl.py:1850-1918)
+# ----------------------------------------------------------------------------
+class _OrdinalFn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, logits, labels, w, w_per_item, mask, temperature, use_fraction):
+    b, n, k = logits.shape
+    dev = logits.device
+    grad = torch.empty_like(logits)
+    loss = torch.empty(b, dtype=torch.float32, device=dev)
+    weight = torch.empty_like(loss)
+    nonzero = torch.empty_like(loss)
+    row = torch.empty(b, n, dtype=torch.float32, device=dev)
+    _C.check(_C.lib.tfr_ordinal_loss_fwd_bwd(
+        _C.ptr(logits), _C.ptr(labels), _C.ptr(w), w_per_item, _C.ptr(mask), b, n, k,
+        float(temperature), int(bool(use_fraction)), 1.0, _C.ptr(grad), _C.ptr(row),
+        _C.ptr(loss), _C.ptr(weight), _C.ptr(nonzero), _C.stream()))
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(grad)
+    ctx.mark_non_differentiable(weight, nonzero)
+    return loss, weight, nonzero, row
+
+  @staticmethod
+  def backward(ctx, g_loss, _gw, _gn, g_row):
+    grad, = ctx.saved_tensors
+    out = None
+    if g_loss is not None:
+      out = grad * g_loss.reshape(-1, 1, 1)
+    if g_row is not None:
+      out = grad * g_row.unsqueeze(2) if out is None else out + grad * g_row.unsqueeze(2)
+    return out, None, None, None, None, None, None
+
+
+class OrdinalLoss(_PointwiseLoss):
+  """losses_impl.py:1850-1918: logits [B, N, ordinal_size]."""
+
+  def __init__(self, name=None, ordinal_size=1, temperature=1.0, ragged=False,
+               use_fraction_label=False):
+    super().__init__(name, None, temperature, ragged)
+    self._ordinal_size = ordinal_size
+    self._use_fraction_label = use_fraction_label
+
+  def _run(self, labels, logits, weights, mask, temperature):
+    logits = _as_f32(logits, what='logits')
+    if logits.dim() != 3:
+      raise ValueError('Predictions for ordinal loss must have rank 3.')
+    if logits.shape[-1] != self._ordinal_size:
+      raise ValueError(
+          'The last dimension of logits must be the number of ordinal levels '
+          '{}, the actual dimension is {}.'.format(self._ordinal_size,
+                                                   logits.shape[-1]))
+    labels = _as_f32(labels, logits.device, 'labels')
+    if labels.shape != logits.shape[:2]:
+      raise ValueError('labels must have shape [batch_size, list_size]')
+    w, wpi = _prep_weights(weights, labels)
+    m = _prep_mask(mask, labels)
+    return _OrdinalFn.apply(logits, labels, w, wpi, m, temperature,
+                            self._use_fraction_label)

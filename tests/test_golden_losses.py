@@ -510,3 +510,36 @@ def test_list_mle_loss(api):
   mask = torch.tensor([[True, False, True]], device=api.device)
   _close(loss_fn.compute(api.t([[0., 0., 1.]]), api.t([[0., ln(2), ln(3)]]), None, red,
                          mask), -(ln(3. / (3 + 1)) + ln(1. / 1)))
+
+
+def test_ordinal_loss(api):
+  """losses_impl_test.py:1419-1475."""
+  scores = [[[1., 2.], [3., 2.], [2., 3.]], [[1., 3.], [2., 2.], [3., 2.]],
+            [[1., 1.], [2., 1.], [3., 3.]]]
+  labels = [[0., 0., 1.], [0., 1., 2.], [0., 0., 0.]]
+  weights = [[2.], [1.], [1.]]
+  red = api.Reduction.SUM_BY_NONZERO_WEIGHTS
+  ce = _sigmoid_cross_entropy
+  loss_fn = api.losses_impl.OrdinalLoss(name=None, ordinal_size=2)
+  _close(loss_fn.compute(api.t(labels), api.t(scores), None, red),
+         (ce([0., 0., 1.], [1., 3., 2.]) + ce([0., 0., 0.], [2., 2., 3.]) +
+          ce([0., 1., 1.], [1., 2., 3.]) + ce([0., 0., 1.], [3., 2., 2.]) +
+          ce([0., 0., 0.], [1., 2., 3.]) + ce([0., 0., 0.], [1., 1., 3.])) / 9.)
+  _close(loss_fn.compute(api.t(labels), api.t(scores), api.t(weights), red),
+         (ce([0., 0., 1.], [1., 3., 2.]) * 2. + ce([0., 0., 0.], [2., 2., 3.]) * 2. +
+          ce([0., 1., 1.], [1., 2., 3.]) + ce([0., 0., 1.], [3., 2., 2.]) +
+          ce([0., 0., 0.], [1., 2., 3.]) + ce([0., 0., 0.], [1., 1., 3.])) / 9.)
+  _close(loss_fn.compute(api.t([[0., -1., 1.]]),
+                         api.t([[[1., 1.], [3., 3.], [2., 2.]]]), None, red),
+         (ce([0., 1.], [1., 2.]) + ce([0., 0.], [1., 2.])) / 2.)
+  mask = torch.tensor([[True, False, True, True]], device=api.device)
+  _close(loss_fn.compute(api.t([[0., 1., 1., 0.]]),
+                         api.t([[[1., 1.], [2., 2.], [3., 3.], [2., 2.]]]), None, red,
+                         mask),
+         (ce([0., 1., 0.], [1., 3., 2.]) + ce([0., 0., 0.], [1., 3., 2.])) / 3.)
+
+
+def test_ordinal_loss_keras_docstring(api):
+  """keras/losses.py:1609-1613."""
+  loss = api.keras_losses.get('ordinal_loss', ordinal_size=2)
+  _close(loss(api.t([[1., 0.]]), api.t([[[0.6, 0.2], [0.8, 0.3]]])), 1.6305413)

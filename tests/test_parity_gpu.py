@@ -149,6 +149,20 @@ def test_fused_train_step_more_losses(oracle_api, key):
   assert _rel_err(tower.flat.detach(), want.detach()) <= 1e-5
 
 
+@pytest.mark.parametrize('frac', [False, True])
+def test_ordinal_loss_and_grad(cuda_api, oracle_api, frac):
+  b, n, k = 5, 33, 4
+  g = torch.Generator().manual_seed(3)
+  scores = torch.randn(b, n, k, generator=g)
+  labels = torch.rand(b, n, generator=g) * 4.5
+  labels[:, -4:] = -1.0
+  item_w = torch.rand(b, n, generator=g) + 0.5
+  for w in (None, item_w, item_w[:, :1]):
+    lc = cuda_api.keras_losses.OrdinalLoss(ordinal_size=k, use_fraction_label=frac)
+    lo = oracle_api.keras_losses.OrdinalLoss(ordinal_size=k, use_fraction_label=frac)
+    _check_loss_and_grad(lc, lo, scores, labels, w)
+
+
 def _hash_uniforms(seed, numel):
   """The uniforms of tfr_gumbel_sample / dropout (include/tfr_b200.h)."""
   import numpy as np
