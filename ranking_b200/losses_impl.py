@@ -325,10 +325,6 @@ class _RankingLoss(object):
 
   def __init__(self, name=None, lambda_weight=None, temperature=1.0,
                ragged=False):
-    if ragged:
-      raise NotImplementedError(
-          'ragged=True needs tf.RaggedTensor inputs; pass dense [B, N] tensors '
-          'padded with label -1 (utils.py:21-23) instead.')
     self._name = name
     self._lambda_weight = lambda_weight
     self._temperature = temperature
@@ -338,12 +334,23 @@ class _RankingLoss(object):
   def name(self):
     return self._name
 
+  def _densify(self, labels, logits, weights, mask):
+    """ragged=True: inputs are lists of per-list sequences (the torch stand-in for
+    tf.RaggedTensor); they are padded the way utils.ragged_to_dense does
+    (utils.py:421-443) and the mask argument is ignored, as in the reference."""
+    if not self._ragged:
+      return labels, logits, weights, mask
+    from ranking_b200 import utils as tfr_utils
+    return tfr_utils.ragged_to_dense(labels, logits, weights)
+
   def get_logits(self, logits):
     """losses_impl.py:773-785."""
     return _as_f32(logits, what='logits') / self._temperature
 
   def normalize_weights(self, labels, weights):
     """losses_impl.py:745-766."""
+    if self._ragged:
+      labels, _, weights, _ = self._densify(labels, None, weights, None)
     return self._normalize_weights_impl(_as_f32(labels, what='labels'), weights)
 
   def _normalize_weights_impl(self, labels, weights):
@@ -355,6 +362,7 @@ class _PairwiseLoss(_RankingLoss):
   _phi = None
 
   def _run(self, labels, logits, weights, mask, temperature):
+    labels, logits, weights, mask = self._densify(labels, logits, weights, mask)
     labels, logits = _prep_2d(labels, logits)
     w, wpi = _prep_weights(weights, logits)
     m = _prep_mask(mask, logits)
@@ -421,6 +429,7 @@ class _ListwiseLoss(_RankingLoss):
   _kind = None
 
   def _run(self, labels, logits, weights, mask, temperature):
+    labels, logits, weights, mask = self._densify(labels, logits, weights, mask)
     labels, logits = _prep_2d(labels, logits)
     w, wpi = _prep_weights(weights, logits)
     m = _prep_mask(mask, logits)
@@ -535,6 +544,7 @@ class _PointwiseLoss(_RankingLoss):
   _kind = None
 
   def _run(self, labels, logits, weights, mask, temperature):
+    labels, logits, weights, mask = self._densify(labels, logits, weights, mask)
     labels, logits = _prep_2d(labels, logits)
     w, wpi = _prep_weights(weights, logits)
     m = _prep_mask(mask, logits)
@@ -609,6 +619,7 @@ class _MiscListwiseLoss(_ListwiseLoss):
   """UniqueSoftmax / ListMLE share the listwise plumbing of K2/K3."""
 
   def _run(self, labels, logits, weights, mask, temperature):
+    labels, logits, weights, mask = self._densify(labels, logits, weights, mask)
     labels, logits = _prep_2d(labels, logits)
     w, wpi = _prep_weights(weights, logits)
     m = _prep_mask(mask, logits)
@@ -667,8 +678,7 @@ class GumbelSampler(object):
 
   def __init__(self, name=None, sample_size=8, temperature=1.0, seed=None,
                ragged=False):
-    if ragged:
-      raise NotImplementedError('ragged=True: pass dense padded tensors.')
+    self._ragged = ragged
     self._name = name
     self._sample_size = int(sample_size)
     self._temperature = temperature
@@ -696,6 +706,11 @@ class GumbelSampler(object):
     return ex_labels, ex_w
 
   def sample(self, labels, logits, weights=None):
+    """With ragged=True the inputs are lists of per-list sequences and the outputs
+    are DENSE padded tensors (label -1), which every loss here accepts."""
+    if self._ragged:
+      from ranking_b200 import utils as tfr_utils
+      labels, logits, weights, _ = tfr_utils.ragged_to_dense(labels, logits, weights)
     labels, logits = _prep_2d(labels, logits)
     ex_labels, ex_w = self.expand(labels, weights)
     sampled = _GumbelFn.apply(logits, labels, self._sample_size, self._temperature,
@@ -747,6 +762,7 @@ class OrdinalLoss(_PointwiseLoss):
     self._use_fraction_label = use_fraction_label
 
   def _run(self, labels, logits, weights, mask, temperature):
+    labels, logits, weights, mask = self._densify(labels, logits, weights, mask)
     logits = _as_f32(logits, what='logits')
     if logits.dim() != 3:
       raise ValueError('Predictions for ordinal loss must have rank 3.')

@@ -24,10 +24,14 @@ _EXT_KEYS = ('dcg', 'precision', 'recall', 'map', 'hits', 'arp', 'opa')
 
 def rank_metrics(labels, predictions, weights=None, mask=None, topns=(None,),
                  gain_fn=None, rank_discount_fn=None, want_ndcg=True,
-                 want_mrr=True, ext=()):
+                 want_mrr=True, ext=(), ragged=False):
   """One launch of K4.  Returns dict(ndcg [B, T], ndcg_w [B], mrr [B, T],
   mrr_w [B], raw [B, 5]) plus, for every name in `ext` (subset of dcg, precision,
   recall, map, hits [B, T] and arp, opa [B, 2] = value, weight), that tensor."""
+  if ragged:   # lists of per-list sequences, padded like utils.ragged_to_dense
+    from ranking_b200 import utils as tfr_utils
+    labels, predictions, weights, mask = tfr_utils.ragged_to_dense(
+        labels, predictions, weights)
   labels, predictions = _prep_2d(labels, predictions)
   w, wpi = _prep_weights(weights, predictions)
   m = _prep_mask(mask, predictions)
@@ -91,8 +95,6 @@ class _RankingMetric(object):
   """metrics_impl.py:199-291."""
 
   def __init__(self, ragged=False):
-    if ragged:
-      raise NotImplementedError('ragged=True: pass dense padded tensors.')
     self._ragged = ragged
 
   def compute(self, labels, predictions, weights=None, mask=None):
@@ -113,7 +115,7 @@ class MRRMetric(_RankingMetric):
 
   def compute(self, labels, predictions, weights=None, mask=None):
     o = rank_metrics(labels, predictions, weights, mask, (self._topn,),
-                     want_ndcg=False)
+                     want_ndcg=False, ragged=self._ragged)
     return o['mrr'], o['mrr_w'].unsqueeze(1)
 
 
@@ -134,7 +136,7 @@ class NDCGMetric(_RankingMetric):
 
   def compute(self, labels, predictions, weights=None, mask=None):
     o = rank_metrics(labels, predictions, weights, mask, (self._topn,),
-                     self._gain_fn, self._rank_discount_fn, want_mrr=False)
+                     self._gain_fn, self._rank_discount_fn, want_mrr=False, ragged=self._ragged)
     return o['ndcg'], o['ndcg_w'].unsqueeze(1)
 
 
@@ -159,7 +161,7 @@ class _ExtMetric(_RankingMetric):
 
   def compute(self, labels, predictions, weights=None, mask=None):
     o = rank_metrics(labels, predictions, weights, mask, (self._topn,),
-                     want_ndcg=False, want_mrr=True, ext=(self._key,))
+                     want_ndcg=False, want_mrr=True, ext=(self._key,), ragged=self._ragged)
     return o[self._key], o[self._weight].unsqueeze(1)
 
 
@@ -196,7 +198,7 @@ class ARPMetric(_RankingMetric):
 
   def compute(self, labels, predictions, weights=None, mask=None):
     o = rank_metrics(labels, predictions, weights, mask, (None,), want_ndcg=False,
-                     want_mrr=False, ext=('arp',))
+                     want_mrr=False, ext=('arp',), ragged=self._ragged)
     return o['arp'][:, 0:1], o['arp'][:, 1:2]
 
 
@@ -213,7 +215,7 @@ class OPAMetric(_RankingMetric):
 
   def compute(self, labels, predictions, weights=None, mask=None):
     o = rank_metrics(labels, predictions, weights, mask, (None,), want_ndcg=False,
-                     want_mrr=False, ext=('opa',))
+                     want_mrr=False, ext=('opa',), ragged=self._ragged)
     return o['opa'][:, 0:1], o['opa'][:, 1:2]
 
 
@@ -235,6 +237,6 @@ class DCGMetric(_RankingMetric):
   def compute(self, labels, predictions, weights=None, mask=None):
     o = rank_metrics(labels, predictions, weights, mask, (self._topn,),
                      self._gain_fn, self._rank_discount_fn, want_mrr=False,
-                     ext=('dcg',))
+                     ext=('dcg',), ragged=self._ragged)
     w = o['ndcg_w'].unsqueeze(1)
     return _safe_div(o['dcg'], w), w

@@ -55,3 +55,53 @@ def padded_nd_indices(is_valid):
   nv = torch.clamp(num_valid, min=1)
   circular = torch.remainder(idx, nv)
   return torch.gather(organize_valid_indices(is_valid), 1, circular), mask
+
+
+_PADDING_LABEL = -1.          # utils.py:21-23
+_PADDING_PREDICTION = -1e6
+_PADDING_WEIGHT = 0.
+
+
+def _rows(x):
+  """A ragged batch: a list / tuple of 1-D sequences, or a torch nested tensor."""
+  if torch.is_tensor(x) and getattr(x, 'is_nested', False):
+    return list(x.unbind())
+  if torch.is_tensor(x):
+    raise ValueError('ragged=True expects a list of per-list sequences (or a nested '
+                     'tensor), got a dense tensor')
+  return [torch.as_tensor(r) for r in x]
+
+
+def _pad_rows(rows, pad, width, device):
+  trailing = rows[0].shape[1:] if rows and rows[0].dim() > 1 else ()
+  out = torch.full((len(rows), width) + tuple(trailing), pad, dtype=torch.float32,
+                   device=device)
+  for i, r in enumerate(rows):
+    if r.numel():
+      out[i, :r.shape[0]] = r.to(device=device, dtype=torch.float32)
+  return out
+
+
+def ragged_to_dense(labels, predictions, weights, device='cuda'):
+  """utils.py:421-443 for ragged batches given as lists of per-list sequences:
+  labels pad -1, predictions pad -1e6, ragged weights pad 0; returns
+  (labels, predictions, weights, mask)."""
+  lab_rows = _rows(labels)
+  width = max([r.shape[0] for r in lab_rows] + [1])
+  mask = torch.zeros(len(lab_rows), width, dtype=torch.bool, device=device)
+  for i, r in enumerate(lab_rows):
+    mask[i, :r.shape[0]] = True
+  dense_labels = _pad_rows(lab_rows, _PADDING_LABEL, width, device)
+  dense_pred = None
+  if predictions is not None:
+    dense_pred = _pad_rows(_rows(predictions), _PADDING_PREDICTION, width, device)
+  dense_w = weights
+  if isinstance(weights, (list, tuple)) or (torch.is_tensor(weights) and getattr(
+      weights, 'is_nested', False)):
+    w_rows = _rows(weights)
+    if len(w_rows) == len(lab_rows) and all(
+        r.dim() >= 1 and r.shape[0] == l_.shape[0] for r, l_ in zip(w_rows, lab_rows)):
+      dense_w = _pad_rows(w_rows, _PADDING_WEIGHT, width, device)   # per-item, ragged
+    else:
+      dense_w = torch.as_tensor(weights, dtype=torch.float32, device=device)
+  return dense_labels, dense_pred, dense_w, mask

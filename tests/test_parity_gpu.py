@@ -163,6 +163,73 @@ def test_ordinal_loss_and_grad(cuda_api, oracle_api, frac):
     _check_loss_and_grad(lc, lo, scores, labels, w)
 
 
+# ------------------------------ ragged=True ----------------------------------
+@pytest.mark.parametrize('cls,expected_losses,expected_weights', [
+    ('SigmoidCrossEntropyLoss', [1.3644443, -0.8190755], [9., 2.]),
+    ('MeanSquaredLoss', [3.6666667, 1.], [9., 2.]),
+    ('PairwiseHingeLoss', [1., 0.], [8., 1.]),
+    ('PairwiseLogisticLoss', [0.813262, 0.126928], [8., 1.]),
+    ('PairwiseSoftZeroOneLoss', [0.5, 0.119203], [8., 1.]),
+    ('ListMLELoss', [3.534534, 0.126928], [4., 1.]),
+    ('SoftmaxLoss', [1.407606, 0.126928], [4., 2.]),
+    ('UniqueSoftmaxLoss', [1.407606, 0.380784], [4., 1.]),
+    ('ApproxNDCGLoss', [-0.63093, -0.922917], [4., 1.]),
+    ('ApproxMRRLoss', [-0.5, -0.893493], [4., 1.]),
+])
+def test_compute_per_list_with_ragged_inputs(cuda_api, cls, expected_losses,
+                                             expected_weights):
+  """losses_impl_test.py:556-578 with true ragged inputs (lists of sequences stand in
+  for tf.RaggedTensor)."""
+  scores = [[1., 3., 2.], [1., 3.]]
+  labels = [[0., 0., 1.], [0., 2.]]
+  per_item_weights = [[2., 3., 4.], [1., 1.]]
+  loss_fn = getattr(cuda_api.losses_impl, cls)(name=None, ragged=True)
+  losses, weights = loss_fn.compute_per_list(labels, scores, per_item_weights)
+  torch.testing.assert_close(losses.cpu().double().reshape(-1),
+                             torch.tensor(expected_losses, dtype=torch.float64),
+                             rtol=1e-5, atol=1e-5)
+  torch.testing.assert_close(weights.cpu().double().reshape(-1),
+                             torch.tensor(expected_weights, dtype=torch.float64),
+                             rtol=1e-5, atol=1e-5)
+
+
+def test_metrics_with_ragged_inputs(cuda_api):
+  """metrics_impl_test.py: the *_should_handle_ragged_inputs cases."""
+  M = cuda_api.metrics_impl
+  log2p1 = lambda x: math.log2(1. + x)
+
+  def check(metric, labels, scores, want, want_w=None):
+    v, w = metric.compute(labels, scores)
+    torch.testing.assert_close(v.cpu().double(), torch.tensor(want, dtype=torch.float64),
+                               rtol=1e-5, atol=1e-6)
+    if want_w is not None:
+      torch.testing.assert_close(w.cpu().double(),
+                                 torch.tensor(want_w, dtype=torch.float64),
+                                 rtol=1e-5, atol=1e-6)
+
+  check(M.MRRMetric(topn=None, ragged=True), [[0., 1., 0.], [0., 1.]],
+        [[1., 2., 3.], [1., 2.]], [[0.5], [1.]])
+  check(M.HitsMetric(topn=1, ragged=True), [[0., 1., 0.], [0., 1.]],
+        [[1., 2., 3.], [1., 2.]], [[0.], [1.]])
+  check(M.ARPMetric(ragged=True), [[0., 0., 1., 0.], [0., 1., 2.]],
+        [[1., 3., 2., 4.], [1., 2., 3.]], [[3.], [((1. * 2.) + (2. * 1.)) / (2. + 1.)]])
+  check(M.PrecisionMetric(topn=None, ragged=True), [[0., 0., 1., 0.], [1., 0., 2.]],
+        [[1., 3., 2., 4.], [1., 2., 3.]], [[1. / 4.], [2. / 3.]])
+  check(M.MeanAveragePrecisionMetric(topn=None, ragged=True),
+        [[0., 0., 1., 0.], [1., 1., 0.]], [[1., 4., 3., 2.], [1., 3., 2.]],
+        [[(1. / 2.) / 1.], [(1. / 1. + 2. / 3.) / 2.]])
+  check(M.DCGMetric(topn=None, ragged=True), [[0., 1., 0.], [1., 1., 0., 0.]],
+        [[3., 2., 1.], [4., 1., 2., 3.]],
+        [[1. / log2p1(2.)], [1. / log2p1(1.) + 1. / log2p1(4.)]])
+  check(M.OPAMetric(ragged=True), [[0., 1., 0.], [1., 0., 1., 0.]],
+        [[3., 2., 1.], [4., 1., 2., 3.]], [[1. / 2.], [3. / 4.]], [[2.], [4.]])
+  # Keras objects (keras/losses.py docstrings :620-627, 1611-1618)
+  K = cuda_api.keras_losses
+  got = K.OrdinalLoss(ordinal_size=2, ragged=True)(
+      [[2., 1.], [0.]], [[[0.6, 0.2], [0.8, 0.3]], [[0., -0.2]]])
+  assert abs(float(got) - 0.88809216) < 1e-5
+
+
 def _hash_uniforms(seed, numel):
   """The uniforms of tfr_gumbel_sample / dropout (include/tfr_b200.h)."""
   import numpy as np
