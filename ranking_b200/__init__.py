@@ -15,5 +15,7 @@ from ranking_b200 import utils
 from ranking_b200 import dp
 from ranking_b200 import model
 from ranking_b200 import train
+from ranking_b200 import data
+from ranking_b200 import pipeline
 
 __version__ = '0.1.0'
