@@ -138,13 +138,18 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
       bstride = p.tile_stride;
     }
     {
-      // dW[Kin, Nout] = A^T dZ.  Pick the orientation with fewer UMMA cycles:
+      // dW[Kin, Nout] = A^T dZ in one of two orientations:
       //   direct : GM = Kin (tiles of 128), GN = Nout
       //   swapped: GM = Nout,               GN = Kin, stored transposed
+      // Measured (profiles/r01_tc_gemm_wait_cycles.txt): a 128 x N x 8 TF32 MMA costs
+      // ~125 cycles for every N <= 256, so the count of MMA tiles decides, and the
+      // staged bytes per k-block (16 KB of A + 128 B per B column) break ties.
       auto cost = [](int gm, int gn) {
         const int n16 = (gn + 15) / 16 * 16;
         const int ntiles = (n16 + 255) / 256;
-        return (long long)((gm + 127) / 128) * ntiles * (n16 < 256 ? n16 : 256);
+        const int n_umma = n16 < 256 ? n16 : 256;
+        const long long mmas = (long long)((gm + 127) / 128) * ntiles;
+        return mmas * (1 << 20) + mmas * (16384 + 128 * n_umma);
       };
       const bool swapped = cost(Nout, Kin) < cost(Kin, Nout);
       tc::GemmDesc g{};

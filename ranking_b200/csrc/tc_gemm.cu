@@ -132,19 +132,51 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+// The MMA warp runs CONVERGED (all 32 lanes execute the role with warp-uniform values,
+// so descriptors live in uniform registers) and one elected lane issues each
+// tcgen05 instruction.  (Running the role inside `if (lane == 0)` made the compiler wrap
+// every UTCHMMA in an ELECT / BRA.U.ANY loop: ~130 cycles of issue overhead per MMA,
+// which is the tensor-pipe time of an N = 256 MMA and twice that of an N = 128 one.)
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
+// A operand read from tensor memory (lane = row, one 32-bit column per k element).
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]),
+      "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {   // converged warp, one lane commits
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar))
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -229,6 +261,10 @@ struct KernelArgs {
   int epi_smem_bytes;  // bytes of the epilogue staging region
   int colsum_regs;     // column sums kept in registers (single n tile, tma_store)
   int bias_cols;       // floats of the bias copy staged in smem (tma_store + EPI_BIAS_ACT)
+  int a_tmem;          // 3xTF32, K-major A: the splitters write A_hi / A_lo to tensor memory
+                       //   and the MMAs read A from there (halves the smem operand traffic)
+  uint32_t a_col0;     // first TMEM column of the A region: stage s at a_col0 + 64 s
+  uint32_t tmem_alloc_cols;   // power of two >= 2 * tmem_cols (+ 64 * stages with a_tmem)
   uint32_t* bits_out;        // optional (tma_store): ReLU sign bits of the stored values,
   const uint32_t* bits_in;   //   word [(col / 32) * GM + row]; EPI_MASK_BITS reads them
 };
@@ -243,7 +279,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // (pointer arithmetic, not an integer round trip: keeps the shared address space so
   // the compiler emits LDS/STS and knows these never alias global memory)
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int kACopies = PASSES == 3 ? 2 : 1;
+  const int kACopies = (PASSES == 3 && !args.a_tmem) ? 2 : 1;
   constexpr int kBCopies = PASSES == 3 ? 2 : 1;
   const int a_bytes = args.a_tile_bytes * kACopies;
   const int stage_bytes = a_bytes + args.b_tile_bytes * kBCopies;
@@ -285,7 +321,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * args.tmem_cols);   // two accumulator buffers
+    tmem_alloc(tmem_slot, args.tmem_alloc_cols);   // two accumulator buffers (+ A stages)
     tmem_relinquish();
   }
   tc_fence_before();
@@ -351,7 +387,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // --------------------------------------------------------- MMA issuer ----
-    if (lane == 0) {
+    {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) |
                              (static_cast<uint32_t>(A_MN) << 15) |
                              (static_cast<uint32_t>(B_MN) << 16) |
@@ -381,14 +417,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t a_hi = smem_u32(sA_hi(s)), a_lo = smem_u32(sA_lo(s));
           const uint32_t b_hi = smem_u32(sB_hi(s)), b_lo = smem_u32(sB_lo(s));
+          // descriptors of the stage once; a k step only adds (bytes >> 4) to the address field
+          const uint64_t da_hi0 = make_smem_desc(a_hi, a_lbo, a_sbo, a_lt);
+          const uint64_t da_lo0 = make_smem_desc(a_lo, a_lbo, a_sbo, a_lt);
+          const uint64_t db_hi0 = make_smem_desc(b_hi, b_lbo, b_sbo, b_lt);
+          const uint64_t db_lo0 = make_smem_desc(b_lo, b_lbo, b_sbo, b_lt);
+          if (!A_MN && !SPLIT_B && PASSES == 3 && args.a_tmem) {
+            // A_hi / A_lo sit in tensor memory (written by the splitters)
+            const uint32_t ta_hi = tmem_base + args.a_col0 + static_cast<uint32_t>(s) * 64u;
+            const uint32_t ta_lo = ta_hi + 32u;
+#pragma unroll 4
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t db_hi = db_hi0 + static_cast<uint64_t>(ks * (b_step >> 4));
+              const uint64_t db_lo = db_lo0 + static_cast<uint64_t>(ks * (b_step >> 4));
+              umma_tf32_ts(tmem_d, ta_hi + ks * 8, db_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+              umma_tf32_ts(tmem_d, ta_lo + ks * 8, db_hi, idesc, 1u);
+              umma_tf32_ts(tmem_d, ta_hi + ks * 8, db_lo, idesc, 1u);
+            }
+            umma_commit(&empty[s]);
+            continue;
+          }
 #pragma unroll 4
           for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t da_hi = make_smem_desc(a_hi + ks * a_step, a_lbo, a_sbo, a_lt);
-            const uint64_t db_hi = make_smem_desc(b_hi + ks * b_step, b_lbo, b_sbo, b_lt);
+            const uint64_t da_hi = da_hi0 + static_cast<uint64_t>(ks * (a_step >> 4));
+            const uint64_t db_hi = db_hi0 + static_cast<uint64_t>(ks * (b_step >> 4));
             umma_tf32(tmem_d, da_hi, db_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
             if (PASSES == 3) {
-              const uint64_t da_lo = make_smem_desc(a_lo + ks * a_step, a_lbo, a_sbo, a_lt);
-              const uint64_t db_lo = make_smem_desc(b_lo + ks * b_step, b_lbo, b_sbo, b_lt);
+              const uint64_t da_lo = da_lo0 + static_cast<uint64_t>(ks * (a_step >> 4));
+              const uint64_t db_lo = db_lo0 + static_cast<uint64_t>(ks * (b_step >> 4));
               umma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
               umma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
             }
@@ -396,9 +452,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
         }
         if (nkb > 0) umma_commit(&acc_full[ab]);
-        else mbar_arrive(&acc_full[ab]);         // empty k range: epilogue stores zeros
+        else if (lane == 0) mbar_arrive(&acc_full[ab]);   // empty k range: epilogue stores zeros
+        __syncwarp();
       }
-      if (args.dbg) {
+      if (args.dbg && lane == 0) {
         args.dbg[blockIdx.x * 12 + 2] = w_acc;
         args.dbg[blockIdx.x * 12 + 3] = w_full;
         args.dbg[blockIdx.x * 12 + 4] = clock64() - t_start;
@@ -418,6 +475,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           w_tma += mbar_wait(&full[s], ph);
+          if (!A_MN && !SPLIT_B && args.a_tmem) {
+            // lane = row of the K-major tile; the two warps of a TMEM lane quarter take
+            // 16 of the 32 k columns each: 4 swizzled LDS.128 -> hi/lo -> 2 tcgen05.st.x16
+            const int q = warp & 3, hsel = (warp - 2) >> 2;
+            const int row = q * 32 + lane;
+            const unsigned char* src = sA_hi(s) + row * 128;
+            uint32_t h[16], l[16];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = hsel * 4 + jj;
+              const float4 v4 = *reinterpret_cast<const float4*>(src + ((j ^ (row & 7)) << 4));
+              const float xs[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float hh = tf32_rn(xs[e]);
+                h[jj * 4 + e] = __float_as_uint(hh);
+                l[jj * 4 + e] = __float_as_uint(xs[e] - hh);
+              }
+            }
+            const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + args.a_col0 +
+                                static_cast<uint32_t>(s) * 64u + hsel * 16u;
+            tmem_st16(ta, h);
+            tmem_st16(ta + 32u, l);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&split[s]);
+            continue;
+          }
           float4* __restrict__ hi = reinterpret_cast<float4*>(sA_hi(s));
           float4* __restrict__ lo = reinterpret_cast<float4*>(sA_lo(s));
           for (int pass = 0; pass < (SPLIT_B ? 2 : 1); ++pass) {
@@ -798,7 +884,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * args.tmem_cols);
+  if (warp == 1) tmem_dealloc(tmem_base, args.tmem_alloc_cols);
 }
 
 // ------------------------------------------------------------------ host -------
@@ -882,7 +968,13 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   const int a_tile_bytes = g.a_mn ? (BM / 32) * bk * 128 : kATileBytes;
   const int b_tile_bytes = g.b_mn ? ((n_umma + 31) / 32) * bk * 128 : n_umma * 128;
   const int copies = g.passes == 3 ? 2 : 1;
-  const int stage_bytes = (a_tile_bytes + b_tile_bytes) * copies;
+  uint32_t acc_cols = 32;
+  while ((int)acc_cols < n_umma) acc_cols <<= 1;
+  // A in tensor memory: needs 64 columns per stage next to the two accumulators
+  static const bool no_a_tmem = getenv("TFR_TC_NO_A_TMEM") != nullptr;
+  bool a_tmem = !no_a_tmem && g.passes == 3 && !g.a_mn && !g.split_b && 2 * acc_cols + 2 * 64 <= 512;
+  int stage_bytes = a_tmem ? a_tile_bytes + b_tile_bytes * copies
+                           : (a_tile_bytes + b_tile_bytes) * copies;
   int splits = g.splits < 1 ? 1 : g.splits;
   // TMA-store epilogue: row-major, unsplit output with 16-byte aligned rows.
   static const bool no_tma_store = getenv("TFR_TC_NO_TMA_STORE") != nullptr;
@@ -902,6 +994,10 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   const int epi_smem_bytes = tma_store ? kEpiSmemBytes2 : kEpiSmemBytes;
   int stages = (int)((budget - (tma_store ? fixed2 : fixed1)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  if (a_tmem) {
+    const int room = (512 - 2 * (int)acc_cols) / 64;     // A stages that fit tensor memory
+    if (stages > room) stages = room;
+  }
   TFR_REQUIRE(stages >= 1, "tc gemm: tile does not fit shared memory");
   const int nkb_total = (g.GK + bk - 1) / bk;
   int kb_per_split = (nkb_total + splits - 1) / splits;
@@ -934,9 +1030,14 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   ka.bias = g.bias; ka.aux = g.aux;
   ka.kb_per_split = kb_per_split;
   ka.split_stride = g.split_stride;
-  uint32_t cols = 32;
-  while ((int)cols < n_umma) cols <<= 1;
-  ka.tmem_cols = cols;     // per accumulator buffer; the kernel allocates two
+  ka.tmem_cols = acc_cols;     // per accumulator buffer; the kernel allocates two
+  ka.a_tmem = a_tmem ? 1 : 0;
+  ka.a_col0 = 2 * acc_cols;
+  {
+    uint32_t need = 2 * acc_cols + (a_tmem ? 64u * (uint32_t)stages : 0u), alloc = 32;
+    while (alloc < need) alloc <<= 1;
+    ka.tmem_alloc_cols = alloc;
+  }
   ka.dbg = g_dbg;
   ka.vec_ok = (g.ldc % 4 == 0) && (g.GN % 4 == 0) && (g.split_stride % 4 == 0) &&
               ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
