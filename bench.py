@@ -316,6 +316,7 @@ def run_gpu(args):
     if os.path.exists(tpath) and args.precision == 'tf32x3':
       traffic = json.load(open(tpath))
     loss_bytes = (12 * N + 16) * B
+    tf32_peak = measure_tf32_peak(dev)   # cuBLAS TF32, measured now (reference only)
     line = {
         'metric': 'lists_per_sec', 'value': value, 'unit': 'lists/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -336,7 +337,10 @@ def run_gpu(args):
             'algorithmic_flops_per_step': step_fl * B,
             'kernel_ms_per_step': gemm_ms,
             'note': '3xTF32 issues 3 TF32 MMAs per algorithmic product, so the '
-                    'ceiling of this fraction is 1/6 of the bf16 peak',
+                    'ceiling of this fraction is 1/6 of the nominal bf16 peak; the '
+                    'measured ceiling is tf32_cublas_tflops / 3',
+            'tf32_cublas_tflops': tf32_peak,
+            'frac_of_3xtf32_ceiling': (achieved / (tf32_peak / 3.0)) if tf32_peak else None,
         },
         'roofline_hbm': {
             'kernel': 'scorer tower GEMMs (tfr_mlp_fwd + tfr_mlp_bwd)',
@@ -375,6 +379,33 @@ def run_gpu(args):
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
+
+
+def measure_tf32_peak(dev, n=8192, reps=5):
+  """Dense TF32 throughput of this GPU as cuBLAS reaches it (torch.matmul, 8192^3, best
+  of `reps`): the measured roof of `kind::tf32` MMAs — MEASURED_PEAKS.json only carries
+  the bf16 number.  Measurement aid outside every timed region; never on the product path."""
+  try:
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(n, n, device=dev)
+    b = torch.randn(n, n, device=dev)
+    for _ in range(2):
+      a @ b
+    torch.cuda.synchronize(dev)
+    best = float('inf')
+    for _ in range(reps):
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      a @ b
+      e1.record()
+      torch.cuda.synchronize(dev)
+      best = min(best, e0.elapsed_time(e1))
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    del a, b
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+  except Exception:   # noqa: BLE001  (reference number only)
+    return None
 
 
 def phase_times(trainer, resident, steps, stream):

@@ -407,14 +407,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int m0, n0, z, kb_begin, nkb;
         decode(tile, m0, n0, z, kb_begin, nkb);
         const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
-        w_acc += mbar_wait(&acc_empty[ab], aph ^ 1);   // epilogue has drained this buffer
+        const long long th0 = args.dbg ? clock64() : 0;
+        mbar_wait(&acc_empty[ab], aph ^ 1);   // epilogue has drained this buffer
         tc_fence_after();
+        if (args.dbg) w_acc += clock64() - th0;
         const uint32_t tmem_d = tmem_base + ab * args.tmem_cols;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
-          w_full += mbar_wait(PASSES == 3 ? &split[s] : &full[s], ph);
+          const long long tw0 = args.dbg ? clock64() : 0;
+          mbar_wait(PASSES == 3 ? &split[s] : &full[s], ph);
           tc_fence_after();
+          if (args.dbg) w_full += clock64() - tw0;
           const uint32_t a_hi = smem_u32(sA_hi(s)), a_lo = smem_u32(sA_lo(s));
           const uint32_t b_hi = smem_u32(sB_hi(s)), b_lo = smem_u32(sB_lo(s));
           // descriptors of the stage once; a k step only adds (bytes >> 4) to the address field
