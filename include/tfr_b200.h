@@ -255,6 +255,17 @@ int tfr_rank_metrics_ext(const float* scores, const float* labels,
                          float* mrr, float* mrr_w, float* raw,
                          const tfr_metric_ext* ext, void* stream);
 
+/* Diversity metrics (metrics_impl.py:313-427, 746-823): labels [B, N, S] hold per-subtopic
+ * relevance (-1 pads).  precision_ia / alpha_dcg: [B, n_topn] (alpha_dcg unnormalised:
+ * divide by list_w for the reference's per-list value); list_w [B]: per-list weights
+ * with relevance = [any subtopic >= 1]; raw [B, 5] scratch as in tfr_rank_metrics. */
+int tfr_div_metrics(const float* scores, const float* labels, const float* item_w,
+                    int w_per_item, const uint8_t* mask, int B, int N, int S,
+                    const int32_t* topns_host, int n_topn, float alpha,
+                    int disc_fn, const float* disc_table, float* precision_ia,
+                    float* alpha_dcg, float* list_w, float* raw, void* stream);
+
+
 /* out2[0] = scale * sum_i v[i] * (w ? w[i] : 1); out2[1] = sum_i (w ? w[i] : 1).
  * Deterministic single-CTA reduction (Keras Mean state / loss reduction). */
 int tfr_weighted_sum(const float* v, const float* w, int n, float scale,

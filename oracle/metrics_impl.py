@@ -261,6 +261,76 @@ class OPAMetric(_RankingMetric):
     return per_list_opa, per_list_weights
 
 
+def _alpha_dcg_gain_fn(labels, alpha):
+  """metrics_impl.py:36-60."""
+  cum_subtopics = torch.cumsum(labels, 1) - labels        # exclusive
+  return (labels * torch.pow(torch.as_tensor(1. - alpha, dtype=labels.dtype),
+                             cum_subtopics)).sum(-1)
+
+
+class _DivRankingMetric(_RankingMetric):
+  """metrics_impl.py:313-427."""
+
+  def __init__(self, name=None, topn=None):
+    self._topn = topn
+
+  def _prepare_and_validate_params(self, labels, predictions, weights, mask):
+    predictions = torch.as_tensor(predictions)
+    labels = torch.as_tensor(labels, dtype=predictions.dtype)
+    assert labels.dim() == 3
+    if mask is None:
+      mask = utils.is_label_valid(labels)
+    mask = torch.as_tensor(mask)
+    if mask.dim() == 3:
+      mask = mask.any(dim=2)
+    predictions = torch.where(
+        mask, predictions, -1e-6 * torch.ones_like(predictions) +
+        predictions.min(dim=1, keepdim=True).values)
+    labels = torch.where(mask.unsqueeze(2), labels, torch.zeros_like(labels))
+    weights = 1.0 if weights is None else torch.as_tensor(weights, dtype=predictions.dtype)
+    return labels, predictions, torch.ones_like(predictions) * weights, mask
+
+  def _compute_per_list_weights(self, weights, labels):
+    return _per_example_weights_to_per_list_weights(
+        weights, (labels >= 1.0).any(dim=-1).to(weights.dtype))
+
+  def _compute_impl(self, labels, predictions, weights, mask):
+    topn = predictions.shape[1] if self._topn is None else self._topn
+    return (self._compute_per_list_metric(labels, predictions, weights, topn, mask),
+            self._compute_per_list_weights(weights, labels))
+
+
+class PrecisionIAMetric(_DivRankingMetric):
+  """metrics_impl.py:746-782."""
+
+  def _compute_per_list_metric(self, labels, predictions, weights, topn, mask):
+    sorted_labels = utils.sort_by_scores(predictions, [labels], topn=topn, mask=mask)[0]
+    relevance = (sorted_labels >= 1.0).to(predictions.dtype).sum(-1)
+    num_subtopics = (labels >= 1.0).any(dim=1, keepdim=True).to(predictions.dtype).sum(-1)
+    valid_topn = torch.clamp(mask.to(torch.int64).sum(1, keepdim=True), max=topn)
+    return L._divide_no_nan(
+        relevance.sum(1, keepdim=True),
+        (valid_topn.to(predictions.dtype) * num_subtopics).sum(1, keepdim=True))
+
+
+class AlphaDCGMetric(_DivRankingMetric):
+  """metrics_impl.py:785-822."""
+
+  def __init__(self, name=None, topn=None, alpha=0.5,
+               rank_discount_fn=_DEFAULT_RANK_DISCOUNT_FN, seed=None):
+    super().__init__(name, topn)
+    self._alpha = alpha
+    self._rank_discount_fn = rank_discount_fn
+
+  def _compute_per_list_metric(self, labels, predictions, weights, topn, mask):
+    sorted_labels, sorted_weights = utils.sort_by_scores(
+        predictions, [labels, weights], topn=topn, mask=mask)
+    alpha_dcg = _discounted_cumulative_gain(
+        sorted_labels, sorted_weights, lambda l: _alpha_dcg_gain_fn(l, self._alpha),
+        self._rank_discount_fn)
+    return L._divide_no_nan(alpha_dcg, self._compute_per_list_weights(weights, labels))
+
+
 class KerasMean(object):
   """tf.keras.metrics.Mean over (values, sample_weight): keras/metrics.py:171-193."""
 

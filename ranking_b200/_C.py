@@ -80,6 +80,8 @@ _SIGNATURES = {
     'tfr_rank_metrics_ext': (_I, [_P, _P, _P, _I, _P, _I, _I, C.POINTER(C.c_int32),
                                   _I, _I, _I, _P, _P, _P, _P, _P, _P, _P,
                                   C.POINTER(MetricExt), _P]),
+    'tfr_div_metrics': (_I, [_P, _P, _P, _I, _P, _I, _I, _I, C.POINTER(C.c_int32), _I, _F, _I,
+                             _P, _P, _P, _P, _P, _P]),
     'tfr_weighted_sum': (_I, [_P, _P, _I, _F, _P, _P]),
     'tfr_mlp_param_count': (C.c_size_t, [C.POINTER(MlpCfg)]),
     'tfr_mlp_bn_state_count': (C.c_size_t, [C.POINTER(MlpCfg)]),

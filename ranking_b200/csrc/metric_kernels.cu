@@ -266,6 +266,132 @@ rank_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Diversity metrics (metrics_impl.py:36-60, 313-427, 746-823): labels [B, N, S] are
+// per-subtopic relevances; one CTA per list, the same 64-bit key sort as K4.
+//   PrecisionIA@k = sum_{r < k} #{t: l_(r)t >= 1} / (min(k, #valid) * #{t with a relevant doc})
+//   alphaDCG@k    = sum_{r < k} w_(r) disc(r + 1) sum_t l_(r)t (1 - alpha)^(sum_{r' < r} l_(r')t)
+// raw[b] = {sum w, -, -, sum w rel, sum rel} with rel_i = [any_t l_it >= 1] feeds the
+// per-list weight rule (the same finalise kernel as MRR's weights).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMetricThreads)
+div_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
+                   const float* __restrict__ item_w, int w_per_item,
+                   const uint8_t* __restrict__ mask, int N, int S, int P, TopnList topns,
+                   float alpha, int disc_fn, const float* __restrict__ disc_table,
+                   float* __restrict__ precision_ia, float* __restrict__ alpha_dcg,
+                   float* __restrict__ raw) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  float* w = reinterpret_cast<float*>(keys + P);   // [N] example weights
+  float* relcnt = w + N;                            // [N] #subtopics with l >= 1, by position
+  float* term = relcnt + N;                         // [N] alphaDCG terms by position
+  float* red = term + N;                            // [32]
+  int* order = reinterpret_cast<int*>(red + 32);    // [N] item index by position
+  float* topic_any = reinterpret_cast<float*>(order + N);   // [S]
+  float* cum = topic_any + S;                                // [N] scan buffer
+  float* scratch = cum + N;                                  // [blockDim.x]
+  unsigned char* valid = reinterpret_cast<unsigned char*>(scratch + kMetricThreads);
+
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const size_t off = (size_t)b * N;
+  const float* lab = labels + off * S;
+  float pmin = CUDART_INF_F;
+  for (int i = tid; i < N; i += blockDim.x) pmin = fminf(pmin, scores[off + i]);
+  pmin = block_min(pmin, red);
+  float s_w = 0.f, s_wr = 0.f, s_r = 0.f, nv = 0.f;
+  for (int i = tid; i < N; i += blockDim.x) {
+    bool ok;
+    if (mask) {
+      ok = mask[off + i] != 0;
+    } else {                          // is_label_valid reduced over the subtopics (:352-357)
+      ok = false;
+      for (int t = 0; t < S; ++t) ok = ok || lab[(size_t)i * S + t] >= 0.f;
+    }
+    float wv = 1.f;
+    if (item_w) wv = w_per_item ? item_w[off + i] : item_w[b];
+    bool rel = false;
+    for (int t = 0; t < S; ++t) rel = rel || (ok && lab[(size_t)i * S + t] >= 1.f);
+    w[i] = wv;
+    valid[i] = ok;
+    keys[i] = ((unsigned long long)(ok ? 0 : 1) << 45) |
+              ((unsigned long long)desc_bits(sc_clean(ok, scores[off + i], pmin)) << 13) |
+              (unsigned long long)i;
+    s_w += wv;
+    s_wr += rel ? wv : 0.f;
+    s_r += rel ? 1.f : 0.f;
+    nv += ok ? 1.f : 0.f;
+  }
+  for (int i = N + tid; i < P; i += blockDim.x) keys[i] = ~0ull;
+  s_w = block_sum(s_w, red);
+  s_wr = block_sum(s_wr, red);
+  s_r = block_sum(s_r, red);
+  nv = block_sum(nv, red);
+  if (tid == 0 && raw) {
+    raw[b * 5 + 0] = s_w;
+    raw[b * 5 + 1] = 0.f;
+    raw[b * 5 + 2] = 0.f;
+    raw[b * 5 + 3] = s_wr;
+    raw[b * 5 + 4] = s_r;
+  }
+  __syncthreads();
+  bitonic_sort(keys, P);
+  for (int k = tid; k < N; k += blockDim.x) {
+    order[k] = (int)(keys[k] & 0x1fffull);
+    term[k] = 0.f;
+    relcnt[k] = 0.f;
+  }
+  __syncthreads();
+  // subtopic by subtopic (fixed order => deterministic sums): the running coverage along
+  // the ranking is a block scan of that subtopic's sorted labels
+  const float base = 1.f - alpha;
+  for (int t = 0; t < S; ++t) {
+    float any = 0.f;
+    for (int k = tid; k < N; k += blockDim.x) {
+      const int idx = order[k];
+      const float l = valid[idx] ? lab[(size_t)idx * S + t] : 0.f;
+      cum[k] = l;
+      any = fmaxf(any, l >= 1.f ? 1.f : 0.f);
+    }
+    any = block_max(any, red);
+    if (tid == 0) topic_any[t] = any;
+    __syncthreads();
+    block_inclusive_scan(cum, N, scratch);
+    for (int k = tid; k < N; k += blockDim.x) {
+      const int idx = order[k];
+      const float l = valid[idx] ? lab[(size_t)idx * S + t] : 0.f;
+      if (l != 0.f) term[k] += l * powf(base, cum[k] - l);   // exclusive coverage
+      if (l >= 1.f) relcnt[k] += 1.f;
+    }
+    __syncthreads();
+  }
+  float nt = 0.f;
+  for (int t = tid; t < S; t += blockDim.x) nt += topic_any[t];
+  nt = block_sum(nt, red);
+  for (int k = tid; k < N; k += blockDim.x) {
+    const float d = disc_fn == TFR_DISC_TABLE ? disc_table[k + 1] : disc_of(disc_fn, (float)(k + 1));
+    term[k] *= w[order[k]] * d;
+  }
+  __syncthreads();
+  for (int t = 0; t < topns.n; ++t) {
+    const int cut = topns.v[t] > 0 ? min(topns.v[t], N) : N;
+    float a = 0.f, r = 0.f;
+    for (int k = tid; k < cut; k += blockDim.x) {
+      a += term[k];
+      r += relcnt[k];
+    }
+    a = block_sum(a, red);
+    r = block_sum(r, red);
+    if (tid == 0) {
+      const size_t o = (size_t)b * topns.n + t;
+      const float den = fminf((float)cut, nv) * nt;
+      if (precision_ia) precision_ia[o] = den != 0.f ? r / den : 0.f;
+      if (alpha_dcg) alpha_dcg[o] = a;
+    }
+  }
+}
+
 // metrics_impl.py:63-119 over one (single-process) batch.
 __global__ void __launch_bounds__(1024)
 metric_list_weights_kernel(const float* __restrict__ raw, int B, float* __restrict__ ndcg_w,
@@ -348,4 +474,39 @@ extern "C" int tfr_rank_metrics(const float* scores, const float* labels,
   return tfr_rank_metrics_ext(scores, labels, item_w, w_per_item, mask, B, N, topns_host,
                               n_topn, gain_fn, disc_fn, gain_table, disc_table, ndcg, ndcg_w,
                               mrr, mrr_w, raw, nullptr, stream);
+}
+
+extern "C" int tfr_div_metrics(const float* scores, const float* labels, const float* item_w,
+                               int w_per_item, const uint8_t* mask, int B, int N, int S,
+                               const int32_t* topns_host, int n_topn, float alpha, int disc_fn,
+                               const float* disc_table, float* precision_ia, float* alpha_dcg,
+                               float* list_w, float* raw, void* stream) {
+  TFR_REQUIRE(scores && labels, "scores/labels must not be NULL");
+  TFR_REQUIRE(B >= 0 && N >= 1 && N <= kMaxMetricListSize,
+              "need 1 <= list_size <= %d (got %d)", kMaxMetricListSize, N);
+  TFR_REQUIRE(S >= 1 && S <= 4096, "subtopic_size %d out of range", S);
+  TFR_REQUIRE(n_topn >= 1 && n_topn <= kMaxTopn && topns_host, "need 1..%d cut-offs", kMaxTopn);
+  TFR_REQUIRE(disc_fn >= 0 && disc_fn <= TFR_DISC_TABLE, "bad disc_fn");
+  TFR_REQUIRE(disc_fn != TFR_DISC_TABLE || disc_table, "disc_fn TABLE needs disc_table");
+  TFR_REQUIRE(raw != nullptr, "raw [B,5] workspace must not be NULL");
+  if (B == 0) return TFR_OK;
+  TopnList t;
+  t.n = n_topn;
+  for (int i = 0; i < n_topn; ++i) t.v[i] = topns_host[i];
+  int P = 1;
+  while (P < N) P <<= 1;
+  const size_t smem = (size_t)P * 8 + (size_t)(5 * N + 32 + S + kMetricThreads) * 4 + N + 16;
+  if (smem > 48 * 1024)
+    TFR_CUDA_OK(cudaFuncSetAttribute(div_metrics_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaStream_t st = (cudaStream_t)stream;
+  div_metrics_kernel<<<B, kMetricThreads, smem, st>>>(scores, labels, item_w, w_per_item, mask, N,
+                                                     S, P, t, alpha, disc_fn, disc_table,
+                                                     precision_ia, alpha_dcg, raw);
+  TFR_LAUNCH_OK();
+  if (list_w) {
+    metric_list_weights_kernel<<<1, 1024, 0, st>>>(raw, B, nullptr, list_w);
+    TFR_LAUNCH_OK();
+  }
+  return TFR_OK;
 }

@@ -173,7 +173,35 @@ class DCGMetric(_RankingMetric):
     return config
 
 
+class PrecisionIAMetric(_TopnMetric):
+  """keras/metrics.py:643-706: y_true [B, N, subtopic_size]."""
+  _impl = metrics_impl.PrecisionIAMetric
+
+
+class AlphaDCGMetric(_RankingMetric):
+  """keras/metrics.py:1013-1107: y_true [B, N, subtopic_size]."""
+
+  def __init__(self, name='alpha_dcg_metric', topn=None, alpha=0.5,
+               rank_discount_fn=None, seed=None, dtype=None, ragged=False, **kwargs):
+    super().__init__(name=name, dtype=dtype, ragged=ragged, **kwargs)
+    self._topn = topn
+    self._alpha = alpha
+    self._rank_discount_fn = rank_discount_fn or utils.log2_inverse
+    self._seed = seed
+    self._metric = metrics_impl.AlphaDCGMetric(
+        name=name, topn=topn, alpha=alpha, rank_discount_fn=self._rank_discount_fn,
+        seed=seed, ragged=ragged)
+
+  def get_config(self):
+    config = super().get_config()
+    config.update({'topn': self._topn, 'alpha': self._alpha,
+                   'rank_discount_fn': self._rank_discount_fn, 'seed': self._seed})
+    return config
+
+
 _KEY_TO_CLS = {
+    RankingMetricKey.PRECISION_IA: PrecisionIAMetric,
+    RankingMetricKey.ALPHA_DCG: AlphaDCGMetric,
     RankingMetricKey.MRR: MRRMetric, RankingMetricKey.NDCG: NDCGMetric,
     RankingMetricKey.ARP: ARPMetric, RankingMetricKey.DCG: DCGMetric,
     RankingMetricKey.PRECISION: PrecisionMetric,

@@ -240,3 +240,87 @@ class DCGMetric(_RankingMetric):
                      ext=('dcg',), ragged=self._ragged)
     w = o['ndcg_w'].unsqueeze(1)
     return _safe_div(o['dcg'], w), w
+
+
+# ----------------------------------------------------------------------------
+# Diversity metrics (metrics_impl.py:313-427, 746-823)
+# ----------------------------------------------------------------------------
+def div_metrics(labels, predictions, weights=None, mask=None, topns=(None,), alpha=0.5,
+                rank_discount_fn=None, ragged=False):
+  """One launch of the diversity kernel: dict(precision_ia [B, T], alpha_dcg [B, T]
+  (unnormalised), list_w [B], raw [B, 5]).  labels [B, N, S]."""
+  if ragged:
+    from ranking_b200 import utils as tfr_utils
+    labels, predictions, weights, mask = tfr_utils.ragged_to_dense(
+        labels, predictions, weights)
+  predictions = _as_f32(predictions, what='predictions')
+  labels = _as_f32(labels, predictions.device, 'labels')
+  if labels.dim() != 3 or predictions.dim() != 2 or labels.shape[:2] != predictions.shape:
+    raise ValueError('labels must be [batch_size, list_size, subtopic_size] and '
+                     'predictions [batch_size, list_size]')
+  b, n, s_ = labels.shape
+  dev = predictions.device
+  w, wpi = _prep_weights(weights, predictions)
+  m = None
+  if mask is not None:
+    mk = torch.as_tensor(mask, device=dev)
+    if mk.dim() == 3:
+      mk = mk.any(dim=2)
+    m = mk.to(torch.uint8).contiguous()
+  rank_discount_fn = rank_discount_fn or _DEFAULT_RANK_DISCOUNT_FN
+  disc_enum, disc_table = _C.DISC_TABLE, None
+  if rank_discount_fn in _DISC_ENUM:
+    disc_enum = _DISC_ENUM[rank_discount_fn]
+  else:
+    r = torch.arange(0, n + 2, dtype=torch.float32, device=dev)
+    r[0] = 1.0
+    disc_table = torch.as_tensor(rank_discount_fn(r)).to(torch.float32).contiguous()
+  t = len(topns)
+  topn_arr = (ctypes.c_int32 * t)(*[int(x) if x else 0 for x in topns])
+  out = {'precision_ia': torch.empty(b, t, dtype=torch.float32, device=dev),
+         'alpha_dcg': torch.empty(b, t, dtype=torch.float32, device=dev),
+         'list_w': torch.empty(b, dtype=torch.float32, device=dev),
+         'raw': torch.empty(b, 5, dtype=torch.float32, device=dev)}
+  _C.check(_C.lib.tfr_div_metrics(
+      _C.ptr(predictions), _C.ptr(labels), _C.ptr(w), wpi, _C.ptr(m), b, n, s_, topn_arr, t,
+      float(alpha), disc_enum, _C.ptr(disc_table), _C.ptr(out['precision_ia']),
+      _C.ptr(out['alpha_dcg']), _C.ptr(out['list_w']), _C.ptr(out['raw']), _C.stream()))
+  return out
+
+
+class _DivRankingMetric(_RankingMetric):
+  """metrics_impl.py:313-427."""
+
+  def __init__(self, name=None, topn=None, ragged=False):
+    super().__init__(ragged)
+    self._name = name
+    self._topn = topn
+
+  @property
+  def name(self):
+    return self._name
+
+
+class PrecisionIAMetric(_DivRankingMetric):
+  """metrics_impl.py:746-782."""
+
+  def compute(self, labels, predictions, weights=None, mask=None):
+    o = div_metrics(labels, predictions, weights, mask, (self._topn,), ragged=self._ragged)
+    return o['precision_ia'], o['list_w'].unsqueeze(1)
+
+
+class AlphaDCGMetric(_DivRankingMetric):
+  """metrics_impl.py:785-822."""
+
+  def __init__(self, name=None, topn=None, alpha=0.5,
+               rank_discount_fn=_DEFAULT_RANK_DISCOUNT_FN, seed=None, ragged=False):
+    super().__init__(name, topn, ragged)
+    self._alpha = alpha
+    self._rank_discount_fn = rank_discount_fn
+    self._seed = seed
+
+  def compute(self, labels, predictions, weights=None, mask=None):
+    o = div_metrics(labels, predictions, weights, mask, (self._topn,), self._alpha,
+                    self._rank_discount_fn, ragged=self._ragged)
+    w = o['list_w'].unsqueeze(1)
+    return _safe_div(o['alpha_dcg'], w), w

@@ -177,3 +177,105 @@ def test_dcg_custom_gain_and_discount(api):
       api.t([[1., 0., 2.]]), api.t([[1., 3., 2.]]), api.t([[4., 1., 9.]]))
   _close(w, [[((1. + 3.) * 4. + (0. + 3.) * 1. + (2. + 3.) * 9.) /
               ((1. + 3.) + (0. + 3.) + (2. + 3.))]])
+
+
+# ---------------------------------------------------------------------------
+# Diversity metrics: metrics_impl_test.py:1129-1420
+# ---------------------------------------------------------------------------
+def _a(c, r, alpha=0.5, disc=None):
+  """One alphaDCG term: (1 - alpha)^c at rank r."""
+  return (1. - alpha) ** c * (disc(r) if disc else 1. / log2p1(r))
+
+
+DIV_CASES = [
+    ('PrecisionIAMetric', dict(topn=None), [[[0., 0.], [1., 0.], [0., 1.]]], [[1., 3., 2.]],
+     None, None, [[2. / (2. * 3.)]], None),
+    ('PrecisionIAMetric', dict(topn=None), [[[0.], [1.], [0.]]], [[1., 3., 2.]], None, None,
+     [[1. / (1. * 3.)]], None),
+    ('PrecisionIAMetric', dict(topn=None),
+     [[[0., 0., 1., 0.], [1., 1., 1., 1.], [0., 1., 1., 0.]]], [[1., 3., 2.]], None, None,
+     [[7. / (4. * 3.)]], None),
+    ('PrecisionIAMetric', dict(topn=None), [[[0., 0.], [1., 0.], [1., 1.], [0., 1.]]],
+     [[1., 3., 4., 2.]], None, [[T, T, F, T]], [[2. / (2. * 3.)]], None),
+    ('PrecisionIAMetric', dict(topn=None), [[[0., 0.], [0., 1.], [0., 1.], [0., 0.]]],
+     [[1., 3., 2., 4.]], None, None, [[2. / (1. * 4.)]], None),
+    ('PrecisionIAMetric', dict(topn=None), [[[0., 0.], [0., 0.], [0., 0.]]], [[1., 3., 2.]],
+     None, None, [[0.]], None),
+    ('PrecisionIAMetric', dict(topn=None),
+     [[[0., 0.], [0., 0.], [1., 1.], [1., 0.]], [[1., 0.], [1., 1.], [1., 0.], [0., 1.]]],
+     [[1., 3., 2., 4.], [4., 1., 3., 2.]], None, None, [[3. / (2. * 4.)], [5. / (2. * 4.)]],
+     None),
+] + [
+    ('PrecisionIAMetric', dict(topn=k),
+     [[[1., 1.], [0., 0.], [1., 0.]], [[0., 0.], [0., 1.], [1., 0.]],
+      [[0., 1.], [0., 0.], [1., 0.]], [[1., 1.], [1., 1.], [1., 1.]]],
+     [[3., 2., 1.]] * 4, None, None, want, None)
+    for k, want in ((1, [[2. / 2.], [0.], [1. / 2.], [2. / 2.]]),
+                    (2, [[2. / 4.], [1. / 4.], [1. / 4.], [4. / 4.]]),
+                    (6, [[3. / 6.], [2. / 6.], [2. / 6.], [6. / 6.]]))
+] + [
+    ('PrecisionIAMetric', dict(topn=None), [[[0., 1.], [0., 0.], [1., 1.]]], [[1., 3., 2.]],
+     [[3., 7., 9.]], None, None, [[(3. + 9.) / 2.]]),
+    ('PrecisionIAMetric', dict(topn=1), [[[1., 1.], [1., 0.], [0., 0.]]], [[1., 3., 2.]],
+     [[3., 4., 5.]], None, None, [[(3. + 4.) / 2.]]),
+    ('PrecisionIAMetric', dict(topn=None), [[[0., 0.], [0., 0.], [0., 0.]]], [[1., 3., 2.]],
+     [[3., 7., 2.]], None, None, [[1.]]),
+    # ---- alphaDCG :1267-1420
+    ('AlphaDCGMetric', dict(topn=None), [[[0., 0.], [1., 0.], [0., 1.]]], [[1., 3., 2.]],
+     None, None, [[_a(0, 1) + _a(0, 2)]], None),
+    ('AlphaDCGMetric', dict(topn=None), [[[0.], [0.], [1.]]], [[1., 3., 2.]], None, None,
+     [[_a(0, 2)]], None),
+    ('AlphaDCGMetric', dict(topn=None),
+     [[[0., 1., 0., 0.], [1., 1., 0., 1.], [0., 1., 1., 0.]]], [[1., 3., 2.]], None, None,
+     [[3 * _a(0, 1) + _a(1, 2) + _a(0, 2) + _a(2, 3)]], None),
+    ('AlphaDCGMetric', dict(topn=None), [[[0., 0.], [0., 0.], [0., 0.]]], [[1., 3., 2.]],
+     None, None, [[0.]], None),
+    ('AlphaDCGMetric', dict(topn=None), [[[0., 0.], [1., 1.], [1., 0.], [0., 1.], [1., 0.]]],
+     [[1., 4., 3., 2., 2.]], None, [[T, F, T, T, F]], [[_a(0, 1) + _a(0, 2)]], None),
+    ('AlphaDCGMetric', dict(topn=None),
+     [[[0., 0.], [0., 0.], [1., 1.], [1., 0.]], [[1., 0.], [1., 1.], [1., 0.], [0., 1.]]],
+     [[1., 3., 2., 4.], [4., 1., 3., 2.]], None, None,
+     [[_a(0, 1) + _a(0, 3) + _a(1, 3)],
+      [_a(0, 1) + _a(1, 2) + _a(0, 3) + _a(1, 4) + _a(2, 4)]], None),
+    ('AlphaDCGMetric', dict(topn=None, alpha=0.2), [[[1., 1.], [0., 1.], [0., 1.], [1., 0.]]],
+     [[1., 3., 2., 4.]], None, None,
+     [[_a(0, 1, .2) + _a(0, 2, .2) + _a(1, 3, .2) + _a(1, 4, .2) + _a(2, 4, .2)]], None),
+    ('AlphaDCGMetric', dict(topn=None, alpha=0.95),
+     [[[1., 1.], [0., 1.], [0., 1.], [1., 0.]]], [[1., 3., 2., 4.]], None, None,
+     [[_a(0, 1, .95) + _a(0, 2, .95) + _a(1, 3, .95) + _a(1, 4, .95) + _a(2, 4, .95)]], None),
+] + [
+    ('AlphaDCGMetric', dict(topn=k), [[[1., 0.], [0., 0.], [1., 0.], [1., 1.], [0., 1.]]],
+     [[3., 2., 1., 4., 5.]], None, None, want, None)
+    for k, want in ((1, [[_a(0, 1)]]), (2, [[_a(0, 1) + _a(0, 2) + _a(1, 2)]]),
+                    (6, [[_a(0, 1) + _a(0, 2) + _a(1, 2) + _a(1, 3) + _a(2, 5)]]))
+] + [
+    ('AlphaDCGMetric', dict(topn=None), [[[0., 1.], [0., 0.], [1., 1.]]], [[1., 3., 2.]],
+     [[3., 7., 9.]], None, None, [[(3. + 9.) / 2.]]),
+    ('AlphaDCGMetric', dict(topn=1), [[[1., 1.], [1., 0.], [0., 0.]]], [[1., 3., 2.]],
+     [[3., 4., 5.]], None, None, [[(3. + 4.) / 2.]]),
+    ('AlphaDCGMetric', dict(topn=None), [[[0., 0.], [0., 0.], [0., 0.]]], [[1., 3., 2.]],
+     [[3., 7., 2.]], None, None, [[1.]]),
+]
+
+
+@pytest.mark.parametrize('case', range(len(DIV_CASES)))
+def test_diversity_reference_cases(api, case):
+  cls, kw, labels, scores, weights, mask, want_v, want_w = DIV_CASES[case]
+  metric = getattr(api.metrics_impl, cls)(name=None, **kw)
+  m = None if mask is None else torch.tensor(mask, device=api.device)
+  w = None if weights is None else api.t(weights)
+  got_v, got_w = metric.compute(api.t(labels), api.t(scores), w, mask=m)
+  if want_v is not None:
+    _close(got_v, want_v)
+  if want_w is not None:
+    _close(got_w, want_w)
+
+
+def test_alpha_dcg_custom_rank_discount(api):
+  """metrics_impl_test.py:1366-1378."""
+  disc = lambda rank: 1. / (10. + rank)
+  metric = api.metrics_impl.AlphaDCGMetric(name=None, topn=None, rank_discount_fn=disc)
+  v, _ = metric.compute(api.t([[[1., 0.], [1., 1.], [0., 1.], [1., 0.]]]),
+                        api.t([[1., 3., 2., 4.]]))
+  _close(v, [[_a(0, 1, disc=disc) + _a(0, 2, disc=disc) + _a(1, 2, disc=disc) +
+              _a(1, 3, disc=disc) + _a(2, 4, disc=disc)]])

@@ -432,6 +432,28 @@ def test_rank_metrics_extended(cuda_api, oracle_api, n):
       torch.testing.assert_close(w.cpu().double(), rw, rtol=2e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize('n,s_', [(1, 1), (9, 3), (150, 7), (700, 2)])
+def test_diversity_metrics(cuda_api, oracle_api, n, s_):
+  g = torch.Generator().manual_seed(n + s_)
+  b = 6
+  scores = torch.randn(b, n, generator=g)
+  scores = torch.round(scores * 4) / 4          # ties, broken by index on both sides
+  labels = (torch.rand(b, n, s_, generator=g) < 0.3).float()
+  labels[:, -max(1, n // 5):] = -1.0
+  labels[1] = torch.where(labels[1] >= 0, torch.zeros_like(labels[1]), labels[1])  # no relevance
+  item_w = torch.rand(b, n, generator=g) + 0.2
+  MO, MC = oracle_api.metrics_impl, cuda_api.metrics_impl
+  for w in (None, item_w):
+    for topn in (1, 5, None):
+      for cls, kw in (('PrecisionIAMetric', {}), ('AlphaDCGMetric', dict(alpha=0.3))):
+        v, lw = getattr(MC, cls)(topn=topn, **kw).compute(
+            labels.cuda(), scores.cuda(), None if w is None else w.cuda())
+        rv, rw = getattr(MO, cls)(topn=topn, **kw).compute(
+            labels.double(), scores.double(), None if w is None else w.double())
+        torch.testing.assert_close(v.cpu().double(), rv, rtol=2e-5, atol=1e-6)
+        torch.testing.assert_close(lw.cpu().double(), rw, rtol=2e-5, atol=1e-6)
+
+
 def test_default_keras_metrics_one_launch(cuda_api, oracle_api):
   """`MetricGroup.default()` (one launch per batch) equals the eleven separate
   `default_keras_metrics()` objects (keras/metrics.py:131-153)."""
