@@ -161,6 +161,10 @@ int tfr_softmax_loss_fwd_bwd(const float* scores, const float* labels,
  *     by index (the reference shuffles them randomly); invalid items are last.
  *     loss[b] = list loss, weight[b] = label-weighted mean of the item weights
  *     (:1004-1015, 1 without weights); grad = grad_scale * d loss[b] / d scores.
+ *     With order_scores [B, N] the order is a plain descending sort of those scores and
+ *     only the first topk (> 0) positions contribute: the Plackett-Luce term of
+ *     CoupledRankDistilLoss (:1984-2116) for one sampled teacher permutation; weight[b]
+ *     is then additionally zero for lists whose cleaned labels sum to 0.
  * ------------------------------------------------------------------------- */
 typedef enum {
   TFR_MISC_SIGMOID_CE = 0,
@@ -172,7 +176,8 @@ typedef enum {
 int tfr_misc_loss_fwd_bwd(const float* scores, const float* labels,
                           const float* item_w, int w_per_item,
                           const uint8_t* mask, int B, int N, float temperature,
-                          int kind, const float* rank_weight, float grad_scale,
+                          int kind, const float* rank_weight,
+                          const float* order_scores, int topk, float grad_scale,
                           float* grad, float* row, float* loss, float* weight,
                           float* nonzero, void* stream);
 
@@ -198,9 +203,12 @@ int tfr_ordinal_loss_fwd_bwd(const float* scores, const float* labels,
  * (the reference draws tf.random.uniform).  Labels / weights are tiled by the caller.
  * Forward: pass out_logits.  Backward: pass grad_out [B * sample_size, N] and
  * grad_scores [B, N] with the same seed (the noise is regenerated, not stored).
+ * mode 1 samples the TEACHER of CoupledRankDistilLoss (losses_impl.py:2031-2046):
+ * out = log(softmax((label valid ? label : log 1e-10) + G) + 1e-10); scores may be NULL,
+ * forward only.
  * ------------------------------------------------------------------------- */
 int tfr_gumbel_sample(const float* scores, const float* labels, int B, int N,
-                      int sample_size, float temperature, uint64_t seed,
+                      int sample_size, float temperature, uint64_t seed, int mode,
                       float* out_logits, const float* grad_out,
                       float* grad_scores, void* stream);
 

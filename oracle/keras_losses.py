@@ -259,6 +259,16 @@ class GumbelApproxNDCGLoss(_GumbelMixin, ApproxNDCGLoss):
     self._init_gumbel(sample_size, gumbel_temperature)
 
 
+class CoupledRankDistilLoss(_ListwiseLoss):
+  """keras/losses.py:1659-1750 (set `loss._loss.uniforms` before calling)."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, sample_size=8, topk=None,
+               temperature=1.):
+    _RankingLoss.__init__(self, reduction, name)
+    self._loss = losses_impl.CoupledRankDistilLoss(
+        name=name, sample_size=sample_size, topk=topk, temperature=temperature)
+
+
 class OrdinalLoss(_RankingLoss):
   """keras/losses.py:1603-1656."""
 
@@ -271,6 +281,7 @@ class OrdinalLoss(_RankingLoss):
 
 _KEY_TO_CLS = {
     'ordinal_loss': OrdinalLoss,
+    'coupled_rankdistil_loss': CoupledRankDistilLoss,
     'yeti_logistic_loss': YetiLogisticLoss,
     'gumbel_approx_ndcg_loss': GumbelApproxNDCGLoss,
     'unique_softmax_loss': UniqueSoftmaxLoss,
@@ -294,6 +305,7 @@ def get(loss, reduction=Reduction.AUTO, lambda_weight=None, name=None, **kwargs)
     raise ValueError('unsupported loss: {}'.format(loss))
   kw = dict(reduction=reduction, name=name, **kwargs)
   if loss not in ('approx_ndcg_loss', 'approx_mrr_loss', 'sigmoid_cross_entropy_loss',
-                  'mean_squared_loss', 'gumbel_approx_ndcg_loss', 'ordinal_loss'):
+                  'mean_squared_loss', 'gumbel_approx_ndcg_loss', 'ordinal_loss',
+                  'coupled_rankdistil_loss'):
     kw['lambda_weight'] = lambda_weight
   return _KEY_TO_CLS[loss](**kw)

@@ -763,3 +763,46 @@ class OrdinalLoss(_PointwiseLoss):
         torch.exp(-logits.abs()))
     losses = torch.where(mask.unsqueeze(-1), ce, torch.zeros_like(ce))
     return losses.sum(-1), mask.to(logits.dtype)
+
+
+class CoupledRankDistilLoss(_ListwiseLoss):
+  """losses_impl.py:1984-2116 with the uniforms of the teacher sampler passed in
+  (`uniforms` [B, S, N]); ties of the sampled teacher scores are broken by index."""
+
+  def __init__(self, name=None, sample_size=8, topk=None, temperature=1.):
+    super().__init__(name, None, temperature)
+    self._sample_size = sample_size
+    self._topk = topk
+    self.uniforms = None            # set by the caller before compute()
+    self.sampled_teacher = None     # or: the sampled teacher scores directly
+
+  def _compute_unreduced_loss_impl(self, labels, logits, mask=None):
+    if mask is None:
+      mask = utils.is_label_valid(labels)
+    labels = torch.where(mask, labels, torch.zeros_like(labels))
+    label_sum = labels.sum(1, keepdim=True)
+    nonzero_mask = label_sum.reshape(-1) > 0.0
+    log_eps = math.log(_EPSILON)
+    teacher_scores = torch.where(mask, labels, log_eps * torch.ones_like(labels))
+    student_scores = torch.where(mask, logits, log_eps * torch.ones_like(logits))
+    b, n = labels.shape
+    s = self._sample_size
+    if self.sampled_teacher is not None:
+      sampled = torch.as_tensor(self.sampled_teacher, dtype=logits.dtype).reshape(b, s, n)
+    else:
+      u = torch.as_tensor(self.uniforms, dtype=logits.dtype).reshape(b, s, n)
+      gumbel = -torch.log(-torch.log(u + 1e-20) + 1e-20)
+      sampled = teacher_scores.unsqueeze(1).repeat(1, s, 1) + gumbel
+      sampled = torch.log(torch.softmax(sampled, dim=-1) + _EPSILON)
+    expanded_student = student_scores.unsqueeze(1).repeat(1, s, 1)
+    sorted_student = utils.sort_by_scores(
+        sampled.reshape(b * s, n), [expanded_student.reshape(b * s, n)])[0].reshape(b, s, n)
+    topk = self._topk or n
+    topk_student = sorted_student[:, :, :topk]
+    ones_upper = torch.triu(torch.ones(topk, n, dtype=logits.dtype))
+    denom_mask = ones_upper.bool().unsqueeze(0).unsqueeze(0).expand(b, s, topk, n)
+    tiled = sorted_student.unsqueeze(2).expand(b, s, topk, n)
+    denom = torch.where(denom_mask, tiled, log_eps * torch.ones_like(tiled))
+    logprob = topk_student - torch.logsumexp(denom, dim=3)
+    nll = (-logprob.sum(2)).mean(1, keepdim=True)
+    return nll, nonzero_mask.to(logits.dtype).reshape(-1, 1)

@@ -70,11 +70,11 @@ _SIGNATURES = {
     'tfr_softmax_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _P, _I, _I, _F,
                                       C.POINTER(LambdaCfg), _F, _I, _P, _P, _P,
                                       _P]),
-    'tfr_misc_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _P, _I, _I, _F, _I, _P, _F, _P, _P, _P, _P,
-                                   _P, _P]),
+    'tfr_misc_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _P, _I, _I, _F, _I, _P, _P, _I, _F, _P, _P,
+                                   _P, _P, _P, _P]),
     'tfr_ordinal_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _F, _I, _F, _P, _P, _P,
                                       _P, _P, _P]),
-    'tfr_gumbel_sample': (_I, [_P, _P, _I, _I, _I, _F, C.c_uint64, _P, _P, _P, _P]),
+    'tfr_gumbel_sample': (_I, [_P, _P, _I, _I, _I, _F, C.c_uint64, _I, _P, _P, _P, _P]),
     'tfr_rank_metrics': (_I, [_P, _P, _P, _I, _P, _I, _I, C.POINTER(C.c_int32),
                               _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'tfr_rank_metrics_ext': (_I, [_P, _P, _P, _I, _P, _I, _I, C.POINTER(C.c_int32),

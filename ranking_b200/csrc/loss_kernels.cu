@@ -743,9 +743,10 @@ __global__ void __launch_bounds__(kLossThreads)
 misc_loss_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
                  const float* __restrict__ item_w, int w_per_item,
                  const uint8_t* __restrict__ mask, int N, float temperature,
-                 const float* __restrict__ rank_weight, float grad_scale,
-                 float* __restrict__ grad, float* __restrict__ row, float* __restrict__ loss,
-                 float* __restrict__ weight, float* __restrict__ nonzero) {
+                 const float* __restrict__ rank_weight, const float* __restrict__ order_scores,
+                 int topk, float grad_scale, float* __restrict__ grad, float* __restrict__ row,
+                 float* __restrict__ loss, float* __restrict__ weight,
+                 float* __restrict__ nonzero) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const ListView v = carve(smem_raw, N);
   float* scratch = reinterpret_cast<float*>(smem_raw + ((list_smem_bytes(N) + 15) & ~(size_t)15));
@@ -791,12 +792,13 @@ misc_loss_kernel(const float* __restrict__ scores, const float* __restrict__ lab
   }
 
   // ---- listwise: cleaned labels / logits and the list weight (:1004-1015) ----
-  float wl = 0.f, lvsum = 0.f;
+  float wl = 0.f, lvsum = 0.f, lsum_clean = 0.f;
   for (int i = tid; i < N; i += blockDim.x) {
     const bool mvalid = v.mv[i];
     const float lv = v.lv[i] ? v.l[i] : 0.f;
     wl += v.w[i] * lv;              // v.w is already 0 for invalid labels
     lvsum += lv;
+    lsum_clean += mvalid ? v.l[i] : 0.f;
     if (!mvalid) {
       v.z[i] = kLogEpsilon;
       v.l[i] = 0.f;
@@ -804,6 +806,7 @@ misc_loss_kernel(const float* __restrict__ scores, const float* __restrict__ lab
   }
   wl = block_sum(wl, v.red);
   lvsum = block_sum(lvsum, v.red);
+  lsum_clean = block_sum(lsum_clean, v.red);
   const float list_w = item_w ? (lvsum != 0.f ? wl / lvsum : 0.f) : 1.f;
   __syncthreads();
 
@@ -854,20 +857,38 @@ misc_loss_kernel(const float* __restrict__ scores, const float* __restrict__ lab
   float* A = v.w;                                    // prefix sums of w_p / C_p
   int* pos = v.rank;                                 // position of item i
   float zmax = -CUDART_INF_F;
-  for (int i = tid; i < N; i += blockDim.x) {
-    const float li = v.l[i];
-    const bool vi = v.mv[i];
-    int cnt = 0;
-    for (int j = 0; j < N; ++j) {
-      const bool vj = v.mv[j];
-      const float lj = v.l[j];
-      const bool before = vi == vj ? ((vi && lj > li) || ((!vi || lj == li) && j < i)) : vj;
-      cnt += before;
+  const int kmax = topk > 0 ? min(topk, N) : N;     // only the first kmax positions count
+  if (order_scores) {
+    // CoupledRankDistilLoss (:1984-2116): the order is that of the given (sampled teacher)
+    // scores, a plain descending sort with ties by index; the list weight is [sum l > 0]
+    float* key = A;                                   // free until the prefix sums
+    for (int i = tid; i < N; i += blockDim.x) key[i] = order_scores[off + i];
+    __syncthreads();
+    for (int i = tid; i < N; i += blockDim.x) {
+      const float ki = key[i];
+      int cnt = 0;
+      for (int j = 0; j < N; ++j) cnt += (key[j] > ki) || (key[j] == ki && j < i);
+      pos[i] = cnt;
+      zmax = fmaxf(zmax, v.z[i]);
     }
-    pos[i] = cnt;
-    zmax = fmaxf(zmax, v.z[i]);
+    __syncthreads();
+  } else {
+    for (int i = tid; i < N; i += blockDim.x) {
+      const float li = v.l[i];
+      const bool vi = v.mv[i];
+      int cnt = 0;
+      for (int j = 0; j < N; ++j) {
+        const bool vj = v.mv[j];
+        const float lj = v.l[j];
+        const bool before = vi == vj ? ((vi && lj > li) || ((!vi || lj == li) && j < i)) : vj;
+        cnt += before;
+      }
+      pos[i] = cnt;
+      zmax = fmaxf(zmax, v.z[i]);
+    }
   }
   zmax = block_max(zmax, v.red);
+  const float lead_eps = order_scores ? expf(kLogEpsilon - zmax) : 0.f;
   for (int i = tid; i < N; i += blockDim.x) zs[pos[i]] = v.z[i] - zmax;
   __syncthreads();
   // suffix sums: exclusive prefix over the reversed order, plus the own term
@@ -876,8 +897,10 @@ misc_loss_kernel(const float* __restrict__ scores, const float* __restrict__ lab
   block_exclusive_scan(C, N, scratch);               // C[r] = sum_{r' < r} e_rev[r']
   float part = 0.f;
   for (int p = tid; p < N; p += blockDim.x) {
-    const float suffix = C[N - 1 - p] + expf(zs[p]);  // sum_{m >= p}
-    const float wp = rank_weight ? rank_weight[p] : 1.f;
+    // sum_{m >= p}; RankDistil masks the p leading entries of the denominator to
+    // log(1e-10) instead of dropping them (:2094-2097), i.e. adds p * 1e-10
+    const float suffix = C[N - 1 - p] + expf(zs[p]) + (float)p * lead_eps;
+    const float wp = p < kmax ? (rank_weight ? rank_weight[p] : 1.f) : 0.f;
     part += wp * (logf(suffix) - zs[p]);
     A[p] = wp / suffix;
   }
@@ -887,16 +910,17 @@ misc_loss_kernel(const float* __restrict__ scores, const float* __restrict__ lab
     block_exclusive_scan(A, N, scratch);             // A[p] = sum_{k < p} w_k / C_k
     for (int i = tid; i < N; i += blockDim.x) {
       const int p = pos[i];
-      const float wp = rank_weight ? rank_weight[p] : 1.f;
+      const float wp = p < kmax ? (rank_weight ? rank_weight[p] : 1.f) : 0.f;
       const float e = expf(zs[p]);
-      const float suffix = C[N - 1 - p] + e;
+      const float suffix = C[N - 1 - p] + e + (float)p * lead_eps;
       const float gsum = A[p] + wp / suffix;          // inclusive prefix
       grad[off + i] = v.mv[i] ? (e * gsum - wp) * gs : 0.f;
     }
   }
   if (tid == 0) {
     loss[b] = part;
-    if (weight) weight[b] = list_w;
+    // RankDistil: loss weight = [sum of the cleaned labels > 0] (:2027-2029, :2116)
+    if (weight) weight[b] = order_scores ? (lsum_clean > 0.f ? list_w : 0.f) : list_w;
   }
 }
 
@@ -914,18 +938,24 @@ __device__ __forceinline__ float hash_uniform01(unsigned long long seed, unsigne
   return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
+// mode 0: GumbelSampler (:540-649): z = label valid ? (score + G) / T : log(1e-20).
+// mode 1: CoupledRankDistil teacher (:2031-2046): the teacher scores ARE the labels,
+//         z = (label valid ? label : log(1e-10)) + G.
 __device__ __forceinline__ float gumbel_logit(float score, float label, float inv_t,
-                                              unsigned long long seed, unsigned long long idx) {
-  if (!(label >= 0.f)) return logf(1e-20f);
+                                              unsigned long long seed, unsigned long long idx,
+                                              int mode) {
+  const bool ok = label >= 0.f;
+  if (mode == 0 && !ok) return logf(1e-20f);
   const float u = hash_uniform01(seed, idx);
   const float g = -logf(-logf(u + 1e-20f) + 1e-20f);
+  if (mode == 1) return (ok ? label : logf(1e-10f)) + g;
   return (score + g) * inv_t;
 }
 
 // grid (S, B): list (b, s) -> row b * S + s of out.
 __global__ void __launch_bounds__(kLossThreads)
 gumbel_sample_fwd_kernel(const float* __restrict__ scores, const float* __restrict__ labels,
-                         int N, int S, float inv_t, unsigned long long seed,
+                         int N, int S, float inv_t, unsigned long long seed, int mode,
                          float* __restrict__ out) {
   extern __shared__ float zs[];          // [N] + red[32]
   float* red = zs + N;
@@ -933,8 +963,8 @@ gumbel_sample_fwd_kernel(const float* __restrict__ scores, const float* __restri
   const size_t in_off = (size_t)b * N, row = (size_t)b * S + s;
   float zmax = -CUDART_INF_F;
   for (int i = tid; i < N; i += blockDim.x) {
-    const float z = gumbel_logit(scores[in_off + i], labels[in_off + i], inv_t, seed,
-                                 row * N + i);
+    const float z = gumbel_logit(scores ? scores[in_off + i] : 0.f, labels[in_off + i], inv_t,
+                                 seed, row * N + i, mode);
     zs[i] = z;
     zmax = fmaxf(zmax, z);
   }
@@ -943,8 +973,9 @@ gumbel_sample_fwd_kernel(const float* __restrict__ scores, const float* __restri
   for (int i = tid; i < N; i += blockDim.x) se += expf(zs[i] - zmax);
   se = block_sum(se, red);
   const float inv = 1.f / se;
+  const float eps = mode == 1 ? 1e-10f : 1e-20f;
   for (int i = tid; i < N; i += blockDim.x)
-    out[row * N + i] = logf(expf(zs[i] - zmax) * inv + 1e-20f);
+    out[row * N + i] = logf(expf(zs[i] - zmax) * inv + eps);
 }
 
 // grid (B): d scores[b, i] = sum_s (1/T) (a_i - p_i sum_j a_j), a_j = gout_j p_j / (p_j + 1e-20)
@@ -963,7 +994,7 @@ gumbel_sample_bwd_kernel(const float* __restrict__ scores, const float* __restri
     float zmax = -CUDART_INF_F;
     for (int i = tid; i < N; i += blockDim.x) {
       const float z = gumbel_logit(scores[in_off + i], labels[in_off + i], inv_t, seed,
-                                   row * N + i);
+                                   row * N + i, 0);
       zs[i] = z;
       zmax = fmaxf(zmax, z);
     }
@@ -1252,14 +1283,17 @@ extern "C" int tfr_softmax_loss_fwd_bwd(const float* scores, const float* labels
 extern "C" int tfr_misc_loss_fwd_bwd(const float* scores, const float* labels,
                                      const float* item_w, int w_per_item, const uint8_t* mask,
                                      int B, int N, float temperature, int kind,
-                                     const float* rank_weight, float grad_scale, float* grad,
-                                     float* row, float* loss, float* weight, float* nonzero,
+                                     const float* rank_weight, const float* order_scores,
+                                     int topk, float grad_scale, float* grad, float* row,
+                                     float* loss, float* weight, float* nonzero,
                                      void* stream) {
   int rc = check_list_args(scores, labels, B, N, temperature);
   if (rc) return rc;
   TFR_REQUIRE(loss != nullptr, "loss must not be NULL");
   TFR_REQUIRE(kind >= TFR_MISC_SIGMOID_CE && kind <= TFR_MISC_LIST_MLE,
               "kind %d is not a tfr_misc_loss", kind);
+  TFR_REQUIRE((order_scores == nullptr && topk <= 0) || kind == TFR_MISC_LIST_MLE,
+              "order_scores / topk apply to TFR_MISC_LIST_MLE only");
   if (B == 0) return TFR_OK;
   const size_t smem = ((list_smem_bytes(N) + 15) & ~(size_t)15) + kLossThreads * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1269,8 +1303,8 @@ extern "C" int tfr_misc_loss_fwd_bwd(const float* scores, const float* labels,
     if (rc) return rc;                                                                       \
     misc_loss_kernel<K_><<<B, kLossThreads, smem, st>>>(scores, labels, item_w, w_per_item,   \
                                                         mask, N, temperature, rank_weight,   \
-                                                        grad_scale, grad, row, loss, weight, \
-                                                        nonzero);                            \
+                                                        order_scores, topk, grad_scale,      \
+                                                        grad, row, loss, weight, nonzero);   \
     break;
   switch (kind) {
     TFR_MISC_CASE(TFR_MISC_SIGMOID_CE)
@@ -1284,10 +1318,13 @@ extern "C" int tfr_misc_loss_fwd_bwd(const float* scores, const float* labels,
 }
 
 extern "C" int tfr_gumbel_sample(const float* scores, const float* labels, int B, int N,
-                                 int sample_size, float temperature, uint64_t seed,
+                                 int sample_size, float temperature, uint64_t seed, int mode,
                                  float* out_logits, const float* grad_out, float* grad_scores,
                                  void* stream) {
-  int rc = check_list_args(scores, labels, B, N, temperature);
+  TFR_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (GumbelSampler) or 1 (teacher labels)");
+  TFR_REQUIRE(mode == 0 || !(grad_out || grad_scores),
+              "the teacher mode has no gradient (labels are constants)");
+  int rc = check_list_args(mode == 1 ? labels : scores, labels, B, N, temperature);
   if (rc) return rc;
   TFR_REQUIRE(sample_size >= 1 && sample_size <= 65535, "sample_size %d out of range", sample_size);
   TFR_REQUIRE(out_logits || (grad_out && grad_scores),
@@ -1300,7 +1337,7 @@ extern "C" int tfr_gumbel_sample(const float* scores, const float* labels, int B
     rc = prep_smem(gumbel_sample_fwd_kernel, smem);
     if (rc) return rc;
     gumbel_sample_fwd_kernel<<<dim3(sample_size, B), kLossThreads, smem, st>>>(
-        scores, labels, N, sample_size, inv_t, seed, out_logits);
+        scores, labels, N, sample_size, inv_t, seed, mode, out_logits);
     TFR_LAUNCH_OK();
   }
   if (grad_out && grad_scores) {

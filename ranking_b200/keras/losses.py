@@ -389,11 +389,11 @@ class _GumbelMixin(object):
     sampled, g_ex, pl_ex = self._bufs
     seed = smp.next_seed()
     _C.check(_C.lib.tfr_gumbel_sample(
-        _C.ptr(logits), _C.ptr(labels), b, n, s_, float(smp._temperature), seed,
+        _C.ptr(logits), _C.ptr(labels), b, n, s_, float(smp._temperature), seed, 0,
         _C.ptr(sampled), None, None, _C.stream()))
     super().fused_fwd_bwd(ex_labels, sampled, ex_w, g_ex, pl_ex, total2)
     _C.check(_C.lib.tfr_gumbel_sample(
-        _C.ptr(logits), _C.ptr(labels), b, n, s_, float(smp._temperature), seed, None,
+        _C.ptr(logits), _C.ptr(labels), b, n, s_, float(smp._temperature), seed, 0, None,
         _C.ptr(g_ex), _C.ptr(grad_out), _C.stream()))
     per_list.copy_(pl_ex.reshape(2, b, s_).mean(2))
 
@@ -446,7 +446,7 @@ class _MiscListwiseLoss(_ListwiseLoss):
     _C.check(_C.lib.tfr_misc_loss_fwd_bwd(
         _C.ptr(logits), _C.ptr(labels), _C.ptr(w), wpi, None, b, n,
         float(self._temperature), losses_impl._MISC[self._loss._kind],
-        _C.ptr(table), scale, _C.ptr(grad_out), None, _C.ptr(per_list[0]),
+        _C.ptr(table), None, 0, scale, _C.ptr(grad_out), None, _C.ptr(per_list[0]),
         _C.ptr(per_list[1]), None, _C.stream()))
     if w is not None:
       grad_out.mul_(per_list[1].unsqueeze(1))
@@ -492,7 +492,7 @@ class _PointwiseLoss(_RankingLoss):
     _C.check(_C.lib.tfr_misc_loss_fwd_bwd(
         _C.ptr(logits), _C.ptr(labels), _C.ptr(w), wpi, None, b, n,
         float(self._loss._temperature), losses_impl._MISC[self._loss._kind], None,
-        scale, _C.ptr(grad_out), None, _C.ptr(per_list[0]), _C.ptr(per_list[1]),
+        None, 0, scale, _C.ptr(grad_out), None, _C.ptr(per_list[0]), _C.ptr(per_list[1]),
         None, _C.stream()))
     _C.check(_C.lib.tfr_weighted_sum(_C.ptr(per_list[0]), None, b, scale,
                                      _C.ptr(total2), _C.stream()))
@@ -516,6 +516,34 @@ class MeanSquaredLoss(_PointwiseLoss):
         name='{}_impl'.format(name) if name else None, ragged=ragged)
 
 
+class CoupledRankDistilLoss(_RankingLoss):
+  """keras/losses.py:1659-1750."""
+
+  def __init__(self, reduction=Reduction.AUTO, name=None, ragged=False, sample_size=8,
+               topk=None, temperature=1.):
+    super().__init__(reduction, name, ragged)
+    self._sample_size = sample_size
+    self._topk = topk
+    self._temperature = temperature
+    self._loss = losses_impl.CoupledRankDistilLoss(
+        name='{}_impl'.format(name) if name else None, sample_size=sample_size,
+        topk=topk, temperature=temperature, ragged=ragged)
+
+  def __call__(self, y_true, y_pred, sample_weight=None):
+    losses, weights = self._loss._run(y_true, y_pred, sample_weight, None,
+                                      self._temperature)
+    return _keras_reduce((losses * weights).unsqueeze(1), None, self.reduction)
+
+  def fused_fwd_bwd(self, *args, **kwargs):
+    raise NotImplementedError('CoupledRankDistilLoss: use the autograd path')
+
+  def get_config(self):
+    config = super().get_config()
+    config.update({'sample_size': self._sample_size, 'topk': self._topk,
+                   'temperature': self._temperature})
+    return config
+
+
 class OrdinalLoss(_PointwiseLoss):
   """keras/losses.py:1603-1656: y_pred [B, N, ordinal_size]."""
 
@@ -531,6 +559,7 @@ class OrdinalLoss(_PointwiseLoss):
 
 
 _KEY_TO_CLS = {
+    RankingLossKey.COUPLED_RANKDISTIL_LOSS: CoupledRankDistilLoss,
     RankingLossKey.ORDINAL_LOSS: OrdinalLoss,
     RankingLossKey.APPROX_NDCG_LOSS: ApproxNDCGLoss,
     RankingLossKey.APPROX_MRR_LOSS: ApproxMRRLoss,

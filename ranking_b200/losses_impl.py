@@ -507,7 +507,7 @@ class _MiscFn(torch.autograd.Function):
 
   @staticmethod
   def forward(ctx, logits, labels, w, w_per_item, mask, temperature, kind,
-              rank_weight):
+              rank_weight, order_scores=None, topk=0):
     b, n = logits.shape
     dev = logits.device
     grad = torch.empty_like(logits)
@@ -518,8 +518,9 @@ class _MiscFn(torch.autograd.Function):
     row = torch.empty_like(logits) if pointwise else None
     _C.check(_C.lib.tfr_misc_loss_fwd_bwd(
         _C.ptr(logits), _C.ptr(labels), _C.ptr(w), w_per_item, _C.ptr(mask), b, n,
-        float(temperature), _MISC[kind], _C.ptr(rank_weight), 1.0, _C.ptr(grad),
-        _C.ptr(row), _C.ptr(loss), _C.ptr(weight), _C.ptr(nonzero), _C.stream()))
+        float(temperature), _MISC[kind], _C.ptr(rank_weight), _C.ptr(order_scores),
+        int(topk or 0), 1.0, _C.ptr(grad), _C.ptr(row), _C.ptr(loss), _C.ptr(weight),
+        _C.ptr(nonzero), _C.stream()))
     ctx.set_materialize_grads(False)
     ctx.save_for_backward(grad)
     ctx.mark_non_differentiable(weight)
@@ -536,7 +537,7 @@ class _MiscFn(torch.autograd.Function):
       out = grad * g_loss.reshape(-1, 1)
     if len(rest) == 2 and rest[1] is not None:     # d row_i / d s_i = grad_i
       out = grad * rest[1] if out is None else out + grad * rest[1]
-    return out, None, None, None, None, None, None, None
+    return out, None, None, None, None, None, None, None, None, None
 
 
 class _PointwiseLoss(_RankingLoss):
@@ -651,7 +652,7 @@ class _GumbelFn(torch.autograd.Function):
     b, n = logits.shape
     out = torch.empty(b * sample_size, n, dtype=torch.float32, device=logits.device)
     _C.check(_C.lib.tfr_gumbel_sample(
-        _C.ptr(logits), _C.ptr(labels), b, n, sample_size, float(temperature), seed,
+        _C.ptr(logits), _C.ptr(labels), b, n, sample_size, float(temperature), seed, 0,
         _C.ptr(out), None, None, _C.stream()))
     ctx.save_for_backward(logits, labels)
     ctx.cfg = (sample_size, float(temperature), seed)
@@ -665,7 +666,7 @@ class _GumbelFn(torch.autograd.Function):
     gin = torch.empty_like(logits)
     g_out = g_out.contiguous()
     _C.check(_C.lib.tfr_gumbel_sample(
-        _C.ptr(logits), _C.ptr(labels), b, n, sample_size, temperature, seed, None,
+        _C.ptr(logits), _C.ptr(labels), b, n, sample_size, temperature, seed, 0, None,
         _C.ptr(g_out), _C.ptr(gin), _C.stream()))
     return gin, None, None, None, None
 
@@ -778,3 +779,50 @@ class OrdinalLoss(_PointwiseLoss):
     m = _prep_mask(mask, labels)
     return _OrdinalFn.apply(logits, labels, w, wpi, m, temperature,
                             self._use_fraction_label)
+
+
+# ----------------------------------------------------------------------------
+# CoupledRankDistilLoss (losses_impl.py:1984-2116)
+# ----------------------------------------------------------------------------
+class CoupledRankDistilLoss(_ListwiseLoss):
+  """Cross entropy between the top-k Plackett-Luce models of the labels (teacher) and
+  the logits (student): `sample_size` permutations are drawn from the teacher with
+  Gumbel noise (counter hash, see tfr_gumbel_sample mode 1) and each one is a top-k
+  ListMLE term on the student scores (K3b with `order_scores`)."""
+  _kind = 'list_mle'
+
+  def __init__(self, name=None, sample_size=8, topk=None, temperature=1.,
+               ragged=False):
+    super().__init__(name, None, temperature, ragged)
+    self._sample_size = int(sample_size)
+    self._topk = topk
+    self._base = int(torch.seed()) & 0xFFFFFFFF
+    self._calls = 0
+
+  def seed(self, base):
+    """Fixes the noise stream (tests / reproducible runs)."""
+    self._base = int(base) & 0xFFFFFFFF
+    self._calls = 0
+
+  def _run(self, labels, logits, weights, mask, temperature):
+    labels, logits, weights, mask = self._densify(labels, logits, weights, mask)
+    labels, logits = _prep_2d(labels, logits)
+    w, wpi = _prep_weights(weights, logits)
+    m = _prep_mask(mask, logits)
+    b, n = logits.shape
+    s_ = self._sample_size
+    self._calls += 1
+    seed = (self._base << 32) | (self._calls & 0xFFFFFFFF)
+    # the teacher's validity is the loss mask: pass masked labels as -1
+    t_labels = labels if m is None else torch.where(m != 0, labels,
+                                                    torch.full_like(labels, -1.))
+    teacher = torch.empty(b * s_, n, dtype=torch.float32, device=logits.device)
+    _C.check(_C.lib.tfr_gumbel_sample(
+        None, _C.ptr(t_labels.contiguous()), b, n, s_, 1.0, seed, 1, _C.ptr(teacher), None,
+        None, _C.stream()))
+    rep = lambda t: None if t is None else t.repeat_interleave(s_, dim=0).contiguous()
+    ex_w = None if w is None else (w.repeat_interleave(s_, dim=0).contiguous())
+    loss, weight = _MiscFn.apply(rep(logits), rep(labels), ex_w, wpi, rep(m), temperature,
+                                 'list_mle', None, teacher, self._topk or 0)
+    # mean over the samples (:2113); the list weight is the same for every sample
+    return loss.reshape(b, s_).mean(1), weight.reshape(b, s_)[:, 0]

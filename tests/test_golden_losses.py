@@ -543,3 +543,33 @@ def test_ordinal_loss_keras_docstring(api):
   """keras/losses.py:1609-1613."""
   loss = api.keras_losses.get('ordinal_loss', ordinal_size=2)
   _close(loss(api.t([[1., 0.]]), api.t([[[0.6, 0.2], [0.8, 0.3]]])), 1.6305413)
+
+
+def test_coupled_rank_distil_loss(oracle_api):
+  """losses_impl_test.py:1850-1930.  The reference's tests pin the RNG and quote the
+  teacher scores it sampled; the restatement takes those sampled scores as input."""
+  L = oracle_api.losses_impl
+  red = oracle_api.Reduction.SUM_BY_NONZERO_WEIGHTS
+  t = oracle_api.t
+  sampled = [[-5.128768, -5.8270807, -0.00891006], [-4.3828382, -4.4031367, -0.02503967]]
+  scores = [[0., ln(3), ln(2)], [0., ln(2), ln(3)]]
+  labels = [[0., 2., 1.], [1., 0., 2.]]
+  a = ln(2. / (2 + 1 + 3)) + ln(1. / (1 + 3)) + ln(3. / 3)
+  b = ln(3. / (3 + 1 + 2)) + ln(1. / (1 + 2)) + ln(2. / 2)
+  loss_fn = L.CoupledRankDistilLoss(name=None, sample_size=1)
+  loss_fn.sampled_teacher = sampled
+  _close(loss_fn.compute(t(labels), t(scores), None, red), -(a + b) / 2)
+  _close(loss_fn.compute(t(labels), t(scores), t([[2.], [1.]]), red), -(2 * a + b) / 2)
+  big = [[0., ln(3e30), ln(2e30)], [0., ln(2e30), ln(3e30)]]
+  _close(loss_fn.compute(t(labels, torch.float64), t(big, torch.float64), None, red),
+         -((ln(2. / (2 + 1e-30 + 3)) + ln(1e-30 / (1e-30 + 3)) + ln(3. / 3)) +
+           (ln(3. / (3 + 1e-30 + 2)) + ln(1e-30 / (1e-30 + 2)) + ln(2. / 2))) / 2, tol=1e-5)
+  loss_fn = L.CoupledRankDistilLoss(name=None, sample_size=1)
+  loss_fn.sampled_teacher = [[-5.1262169e+00, -7.8245292e+00, -6.3590105e-03]]
+  _close(loss_fn.compute(t([[0., 0., 1.]]), t([[0., ln(2), ln(3)]]), None, red),
+         -(ln(3. / (3 + 1 + 2)) + ln(1. / (1 + 2)) + ln(2. / 2)))
+  # invalid item + topk = 2 (the permutation the reference drew: items 0, 1, then the pad)
+  loss_fn = L.CoupledRankDistilLoss(name=None, sample_size=1, topk=2)
+  loss_fn.sampled_teacher = [[-0.5, -1.0, -23.0], sampled[1]]
+  _close(loss_fn.compute(t([[0., 1., -1.], [1., 0., 2.]]), t(scores), None, red),
+         -((ln(1. / (1 + 3)) + ln(3. / 3)) + (ln(3. / (3 + 1 + 2)) + ln(1. / (1 + 2)))) / 2)

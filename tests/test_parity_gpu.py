@@ -296,6 +296,23 @@ def test_gumbel_losses(cuda_api, oracle_api, key, wkind):
   assert _rel_err(grad, so.grad) <= 5e-5
 
 
+@pytest.mark.parametrize('topk', [None, 3])
+@pytest.mark.parametrize('wkind', ['none', 'list', 'item'])
+def test_coupled_rank_distil_loss(cuda_api, oracle_api, topk, wkind):
+  """CoupledRankDistilLoss (keras/losses.py:1659-1750): teacher permutations from the
+  counter-hash Gumbel noise, replayed through the oracle."""
+  b, n, s_ = 5, 17, 3
+  scores, labels, item_w, list_w = _batch(b, n, seed=71)
+  labels[2] = torch.where(labels[2] >= 0, torch.zeros_like(labels[2]), labels[2])  # weight 0
+  weights = {'none': None, 'list': list_w, 'item': item_w}[wkind]
+  lc = cuda_api.keras_losses.CoupledRankDistilLoss(sample_size=s_, topk=topk, temperature=0.8)
+  lo = oracle_api.keras_losses.CoupledRankDistilLoss(sample_size=s_, topk=topk,
+                                                     temperature=0.8)
+  lc._loss.seed(5)
+  lo._loss.uniforms = _hash_uniforms((5 << 32) | 1, b * s_ * n).reshape(b, s_, n).double()
+  _check_loss_and_grad(lc, lo, scores, labels, weights)
+
+
 def test_softmax_with_dcg_lambda(cuda_api, oracle_api):
   scores, labels, item_w, _ = _batch(8, 50, seed=3)
   KC, KO = cuda_api.keras_losses, oracle_api.keras_losses
