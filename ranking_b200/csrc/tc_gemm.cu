@@ -569,9 +569,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
     }
     uint32_t tcount = 0;
-    float ccol[8];   // register column sums: lane = column of chunk k (colsum_regs mode)
+    // register column sums (colsum_regs mode): this warp only sees the chunks of its
+    // parity, so slot j holds chunk 2 j + half; lane = column within the chunk
+    float ccol[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) ccol[k] = 0.f;
+    for (int k = 0; k < 4; ++k) ccol[k] = 0.f;
     long long w_accfull = 0, w_ld = 0, w_smem = 0, w_st = 0, w_x = 0;
     const long long t_start = clock64();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
@@ -702,7 +704,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (args.colsum_regs) {
               const int ci = c0 >> 5;
 #pragma unroll
-              for (int k = 0; k < 8; ++k) ccol[k] += ci == k ? cs : 0.f;
+              for (int k = 0; k < 4; ++k) ccol[k] += (ci >> 1) == k ? cs : 0.f;
             } else if (colb + lane < args.colsum_cols) {
               cacc[colb + lane] += cs;
             }
@@ -870,9 +872,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       float* dst = args.colsum + static_cast<size_t>(blockIdx.x * kEpiWarps + ew) * args.colsum_stride;
       if (args.colsum_regs) {
+        // every warp writes a full row of its slot: its own chunks, zeros elsewhere
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          if (k * 32 + lane < args.GN) dst[k * 32 + lane] = ccol[k];
+          if (k * 32 + lane < args.GN)
+            dst[k * 32 + lane] = (k & 1) == half ? ccol[k >> 1] : 0.f;
       } else {
         for (int c = lane; c < args.GN; c += 32) dst[c] = cacc[c];
       }
