@@ -391,6 +391,32 @@ reduce2_vec_kernel(const float4* __restrict__ srcA, int slotsA, size_t strideA4,
                    const float4* __restrict__ srcB, int slotsB, size_t strideB4, size_t nB4,
                    float4* __restrict__ out) {
   __shared__ float4 part[32][9];
+  const unsigned blocksA = (unsigned)((nA4 + 7) / 8);
+  if (blockIdx.x >= blocksA) {
+    // B part (bias gradients): few outputs, many slots (one per CTA and epilogue warp of the
+    // producing GEMM, or one per block of the output-layer backward) -> one float4 per
+    // block, 256 slot lanes, fixed-order tree.  (16 lanes per output made this the tail of
+    // the launch: ~40 dependent iterations.)
+    const size_t j = blockIdx.x - blocksA;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int z = threadIdx.x; z < slotsB; z += 256) {
+      const float4 v = srcB[(size_t)z * strideB4 + j];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4* flat = &part[0][0];          // 288 float4 >= 256
+    flat[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+      if ((int)threadIdx.x < w) {
+        const float4 a = flat[threadIdx.x], b = flat[threadIdx.x + w];
+        flat[threadIdx.x] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) out[nA4 + j] = flat[0];
+    return;
+  }
   const int o = threadIdx.x & 7, sl = threadIdx.x >> 3;
   const size_t i = (size_t)blockIdx.x * 8 + o;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -400,17 +426,10 @@ reduce2_vec_kernel(const float4* __restrict__ srcA, int slotsA, size_t strideA4,
       const float4 v = srcA[(size_t)z * strideA4 + i];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-  } else if (i < nA4 + nB4) {
-    const size_t j = i - nA4;
-#pragma unroll 4
-    for (int z = sl; z < slotsB; z += 32) {
-      const float4 v = srcB[(size_t)z * strideB4 + j];
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
   }
   part[sl][o] = acc;
   __syncthreads();
-  if (sl == 0 && i < nA4 + nB4) {
+  if (sl == 0 && i < nA4) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int l = 0; l < 32; ++l) {
@@ -421,6 +440,20 @@ reduce2_vec_kernel(const float4* __restrict__ srcA, int slotsA, size_t strideA4,
   }
 }
 
+// One output per block, 256 slot lanes: for few outputs over many slots (the output
+// layer's [K * O + O] gradient over ~600 block slots).
+__global__ void __launch_bounds__(256)
+reduce_tall_kernel(const float* __restrict__ src, int slots, size_t stride, size_t n,
+                   float* __restrict__ out) {
+  __shared__ float red[32];
+  const size_t i = blockIdx.x;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int z = threadIdx.x; z < slots; z += 256) acc += src[(size_t)z * stride + i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && i < n) out[i] = acc;
+}
+
 // ------------------------------------------------------------- host side ---
 int mlp_reduce2(const float* srcA, int slotsA, size_t strideA, size_t nA, const float* srcB,
                 int slotsB, size_t strideB, size_t nB, float* out, cudaStream_t st) {
@@ -428,10 +461,15 @@ int mlp_reduce2(const float* srcA, int slotsA, size_t strideA, size_t nA, const 
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (nA % 4 == 0 && nB % 4 == 0 && strideA % 4 == 0 && strideB % 4 == 0 && al16(srcA) &&
       al16(srcB) && al16(out)) {
-    reduce2_vec_kernel<<<(unsigned)((n / 4 + 7) / 8), 256, 0, st>>>(
+    reduce2_vec_kernel<<<(unsigned)((nA / 4 + 7) / 8 + nB / 4), 256, 0, st>>>(
         reinterpret_cast<const float4*>(srcA), slotsA, strideA / 4, nA / 4,
         reinterpret_cast<const float4*>(srcB), slotsB, strideB / 4, nB / 4,
         reinterpret_cast<float4*>(out));
+    TFR_LAUNCH_OK();
+    return TFR_OK;
+  }
+  if (nB == 0 && slotsA >= 128 && nA <= 4096) {
+    reduce_tall_kernel<<<(unsigned)nA, 256, 0, st>>>(srcA, slotsA, strideA, nA, out);
     TFR_LAUNCH_OK();
     return TFR_OK;
   }
