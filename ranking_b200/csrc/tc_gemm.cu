@@ -2,17 +2,21 @@
 //
 //   * operands are staged global -> shared by TMA (cp.async.bulk.tensor, 128-byte
 //     swizzle) into a ring of stages guarded by mbarriers;
-//   * one elected thread issues tcgen05.mma.kind::tf32 with the fp32 accumulator
-//     tile [128 x N] living in TMEM;
-//   * for the fp32-faithful mode (3xTF32) four "splitter" warps turn each landed
-//     fp32 tile into an exact TF32 hi part (in place) and an fp32 lo residual, so
-//     that D = Ahi*Bhi + Alo*Bhi + Ahi*Blo carries ~22 mantissa bits;
-//   * the same four warps drain TMEM with tcgen05.ld in the epilogue (bias/ReLU,
-//     ReLU-mask, plain or transposed store).
+//   * one converged warp issues tcgen05.mma.kind::tf32 (elect.sync picks the lane) with the
+//     fp32 accumulator tile [128 x N] living in TMEM;
+//   * for the fp32-faithful mode (3xTF32) eight "splitter" warps turn each landed fp32 tile
+//     into a round-to-nearest TF32 hi part and an fp32 lo residual, so that
+//     D = Ahi*Bhi + Alo*Bhi + Ahi*Blo carries ~22 mantissa bits.  K-major A operands are
+//     written straight into tensor memory (tcgen05.st) and read from there by the MMAs;
+//     MN-major operands are split in place in shared memory;
+//   * eight epilogue warps (two per TMEM lane quarter) drain the accumulators with
+//     tcgen05.ld: bias / ReLU / 1-bit ReLU masks / column sums in registers, a swizzled
+//     staging tile and a TMA store for row-major outputs; STG paths for the transposed and
+//     split-K partial stores of the dW GEMMs.
 //
 // The kernel is persistent: one CTA per SM walks a static list of output tiles.
-// Warp roles (448 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
-// issuer, warps 2..9 = hi/lo splitters, warps 10..13 = epilogue.  The accumulator is
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer, warps 2..9 = hi/lo splitters, warps 10..17 = epilogue.  The accumulator is
 // double-buffered in TMEM, so the epilogue of tile i overlaps the main loop of
 // tile i+1 and the prologue (barrier init, TMEM allocation) is paid once per SM.
 #include <cuda.h>
