@@ -366,6 +366,31 @@ int tfr_tc_gemm(const float* A, int lda, const float* B, int ldb, const float* B
 int tfr_tc_set_debug(long long* buf);
 
 /* ---------------------------------------------------------------------------
+ * Input side (host code, no device work): a batch of serialized
+ * `ExampleListWithContext` protos -> dense float buffers, with the padding /
+ * truncation rules of data.py:133-208, 391-540 for FixedLen float / int64 features:
+ *   context_out [B, sum context dims], example_out [B, list_size, sum example dims]
+ *   (features in spec order; a missing feature or a padded slot takes its default; a
+ *   present feature must have exactly `dim` values; int64 values are cast to float;
+ *   examples past list_size are dropped), sizes_out [B] = untruncated list lengths,
+ *   mask_out [B, list_size] = sequence_mask(sizes, list_size).  All pointers are HOST
+ *   pointers (pinned memory recommended: the result feeds one H2D copy).
+ * tfr_masked_crc32c: the checksum of the TFRecord framing.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  const char* name;
+  int32_t dim;
+  float default_value;
+} tfr_feature_spec;
+
+int tfr_elwc_parse(const uint8_t* const* records, const int64_t* record_sizes,
+                   int B, int list_size, const tfr_feature_spec* context_spec,
+                   int n_context, const tfr_feature_spec* example_spec,
+                   int n_example, float* context_out, float* example_out,
+                   int32_t* sizes_out, uint8_t* mask_out);
+uint32_t tfr_masked_crc32c(const uint8_t* data, size_t n);
+
+/* ---------------------------------------------------------------------------
  * Fused optimizer over the flat parameter buffer (the reference delegates to
  * tf.keras.optimizers; Adagrad is what its examples use:
  * examples/tf_ranking_libsvm.py:386-387).  grad_scale multiplies the gradient

@@ -37,6 +37,10 @@ class LambdaCfg(C.Structure):
               ('disc_table', C.c_void_p)]
 
 
+class FeatureSpec(C.Structure):
+  _fields_ = [('name', C.c_char_p), ('dim', C.c_int32), ('default_value', C.c_float)]
+
+
 class MetricExt(C.Structure):
   _fields_ = [(k, C.c_void_p) for k in ('dcg', 'precision', 'recall', 'map', 'hits',
                                         'arp', 'opa')]
@@ -82,6 +86,10 @@ _SIGNATURES = {
                                   C.POINTER(MetricExt), _P]),
     'tfr_div_metrics': (_I, [_P, _P, _P, _I, _P, _I, _I, _I, C.POINTER(C.c_int32), _I, _F, _I,
                              _P, _P, _P, _P, _P, _P]),
+    'tfr_elwc_parse': (_I, [C.POINTER(C.c_char_p), C.POINTER(C.c_int64), _I, _I,
+                            C.POINTER(FeatureSpec), _I, C.POINTER(FeatureSpec), _I, _P, _P, _P,
+                            _P]),
+    'tfr_masked_crc32c': (C.c_uint32, [C.c_char_p, C.c_size_t]),
     'tfr_weighted_sum': (_I, [_P, _P, _I, _F, _P, _P]),
     'tfr_mlp_param_count': (C.c_size_t, [C.POINTER(MlpCfg)]),
     'tfr_mlp_bn_state_count': (C.c_size_t, [C.POINTER(MlpCfg)]),

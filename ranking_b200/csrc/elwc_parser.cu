@@ -1,0 +1,266 @@
+// Input side of the hot path (host code, no device work): decoding batches of serialized
+// `ExampleListWithContext` protos — the reference's training data format — straight into
+// the dense [B, N, D] / [B, Dc] float buffers the scorer consumes, with the padding /
+// truncation semantics of data.py:133-208 (`_ExampleInExampleParser.parse`) and
+// data.py:391-540 (`parse_from_example_list`) for FixedLen float / int64 features.
+//
+// Wire format handled here (protobuf, proto3 encodings):
+//   ExampleListWithContext { repeated Example examples = 1; Example context = 2; }
+//   Example  { Features features = 1; }
+//   Features { map<string, Feature> feature = 1; }   entry { string key = 1; Feature value = 2; }
+//   Feature  { oneof { BytesList bytes_list = 1; FloatList float_list = 2; Int64List int64_list = 3; } }
+//   FloatList { repeated float value = 1; }  Int64List { repeated int64 value = 1; }   (packed or not)
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tfr {
+namespace {
+
+struct Span {
+  const uint8_t* p;
+  const uint8_t* end;
+  bool ok() const { return p <= end; }
+  bool done() const { return p >= end; }
+};
+
+bool read_varint(Span& s, uint64_t* out) {
+  uint64_t v = 0;
+  for (int shift = 0; shift < 64 && s.p < s.end; shift += 7) {
+    const uint8_t b = *s.p++;
+    v |= static_cast<uint64_t>(b & 0x7f) << shift;
+    if (!(b & 0x80)) {
+      *out = v;
+      return true;
+    }
+  }
+  return false;
+}
+
+// Reads a tag; for length-delimited fields returns the payload span.
+bool read_field(Span& s, uint32_t* field, uint32_t* wire, Span* payload, uint64_t* scalar) {
+  uint64_t tag;
+  if (!read_varint(s, &tag)) return false;
+  *field = static_cast<uint32_t>(tag >> 3);
+  *wire = static_cast<uint32_t>(tag & 7);
+  switch (*wire) {
+    case 0:
+      return read_varint(s, scalar);
+    case 1:
+      if (s.end - s.p < 8) return false;
+      std::memcpy(scalar, s.p, 8);
+      s.p += 8;
+      return true;
+    case 2: {
+      uint64_t len;
+      if (!read_varint(s, &len) || len > static_cast<uint64_t>(s.end - s.p)) return false;
+      payload->p = s.p;
+      payload->end = s.p + len;
+      s.p += len;
+      return true;
+    }
+    case 5: {
+      if (s.end - s.p < 4) return false;
+      uint32_t v;
+      std::memcpy(&v, s.p, 4);
+      *scalar = v;
+      s.p += 4;
+      return true;
+    }
+    default:
+      return false;
+  }
+}
+
+struct Spec {
+  std::string name;
+  int dim;
+  float default_value;
+  int offset;   // column offset in the output row
+};
+
+// Parses a FloatList / Int64List payload into dst[0..dim); returns the value count.
+int parse_values(Span list, bool is_float, float* dst, int dim) {
+  int n = 0;
+  while (!list.done()) {
+    uint32_t f, w;
+    Span pl{nullptr, nullptr};
+    uint64_t sc = 0;
+    if (!read_field(list, &f, &w, &pl, &sc)) return -1;
+    if (f != 1) continue;
+    if (is_float) {
+      if (w == 2) {               // packed
+        const size_t cnt = static_cast<size_t>(pl.end - pl.p) / 4;
+        for (size_t i = 0; i < cnt; ++i, ++n)
+          if (n < dim) std::memcpy(dst + n, pl.p + 4 * i, 4);
+      } else if (w == 5) {
+        const uint32_t bits = static_cast<uint32_t>(sc);
+        if (n < dim) std::memcpy(dst + n, &bits, 4);
+        ++n;
+      } else {
+        return -1;
+      }
+    } else {
+      if (w == 2) {               // packed varints
+        while (!pl.done()) {
+          uint64_t v;
+          if (!read_varint(pl, &v)) return -1;
+          if (n < dim) dst[n] = static_cast<float>(static_cast<int64_t>(v));
+          ++n;
+        }
+      } else if (w == 0) {
+        if (n < dim) dst[n] = static_cast<float>(static_cast<int64_t>(sc));
+        ++n;
+      } else {
+        return -1;
+      }
+    }
+  }
+  return n;
+}
+
+// One serialized tf.Example -> row (already filled with the defaults).
+int parse_example(Span ex, const std::vector<Spec>& specs, float* row) {
+  while (!ex.done()) {
+    uint32_t f, w;
+    Span features{nullptr, nullptr};
+    uint64_t sc;
+    if (!read_field(ex, &f, &w, &features, &sc)) return TFR_INVALID_ARGUMENT;
+    if (f != 1 || w != 2) continue;
+    while (!features.done()) {
+      Span entry{nullptr, nullptr};
+      if (!read_field(features, &f, &w, &entry, &sc)) return TFR_INVALID_ARGUMENT;
+      if (f != 1 || w != 2) continue;
+      Span key{nullptr, nullptr}, value{nullptr, nullptr};
+      while (!entry.done()) {
+        Span pl{nullptr, nullptr};
+        if (!read_field(entry, &f, &w, &pl, &sc)) return TFR_INVALID_ARGUMENT;
+        if (w != 2) continue;
+        if (f == 1) key = pl;
+        if (f == 2) value = pl;
+      }
+      if (!key.p || !value.p) continue;
+      const size_t klen = static_cast<size_t>(key.end - key.p);
+      const Spec* spec = nullptr;
+      for (const Spec& s : specs)
+        if (s.name.size() == klen && std::memcmp(s.name.data(), key.p, klen) == 0) {
+          spec = &s;
+          break;
+        }
+      if (!spec) continue;            // feature not requested
+      while (!value.done()) {
+        Span list{nullptr, nullptr};
+        if (!read_field(value, &f, &w, &list, &sc)) return TFR_INVALID_ARGUMENT;
+        if (w != 2) continue;
+        if (f == 1) {
+          set_error("feature '%s' is a bytes_list; only float_list / int64_list features can "
+                    "be decoded into the dense scorer input", spec->name.c_str());
+          return TFR_UNSUPPORTED;
+        }
+        const int n = parse_values(list, f == 2, row + spec->offset, spec->dim);
+        if (n < 0) return TFR_INVALID_ARGUMENT;
+        if (n != spec->dim && n != 0) {   // tf.io.FixedLenFeature: exact length or missing
+          set_error("feature '%s' has %d values, the spec says %d", spec->name.c_str(), n,
+                    spec->dim);
+          return TFR_INVALID_ARGUMENT;
+        }
+      }
+    }
+  }
+  return TFR_OK;
+}
+
+std::vector<Spec> make_specs(const tfr_feature_spec* in, int n, int* total) {
+  std::vector<Spec> out;
+  int off = 0;
+  for (int i = 0; i < n; ++i) {
+    out.push_back(Spec{in[i].name ? in[i].name : "", in[i].dim, in[i].default_value, off});
+    off += in[i].dim;
+  }
+  *total = off;
+  return out;
+}
+
+void fill_defaults(const std::vector<Spec>& specs, float* row) {
+  for (const Spec& s : specs)
+    for (int j = 0; j < s.dim; ++j) row[s.offset + j] = s.default_value;
+}
+
+// CRC-32C (Castagnoli), the checksum of the TFRecord framing.
+uint32_t crc32c(const uint8_t* p, size_t n) {
+  static uint32_t table[256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[i] = c;
+    }
+    init = true;
+  }
+  uint32_t c = 0xFFFFFFFFu;
+  for (size_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+
+}  // namespace
+}  // namespace tfr
+
+using namespace tfr;
+
+extern "C" uint32_t tfr_masked_crc32c(const uint8_t* data, size_t n) {
+  const uint32_t c = crc32c(data, n);
+  return ((c >> 15) | (c << 17)) + 0xa282ead8u;   // TFRecord's masking
+}
+
+extern "C" int tfr_elwc_parse(const uint8_t* const* records, const int64_t* record_sizes, int B,
+                              int list_size, const tfr_feature_spec* context_spec, int n_context,
+                              const tfr_feature_spec* example_spec, int n_example,
+                              float* context_out, float* example_out, int32_t* sizes_out,
+                              uint8_t* mask_out) {
+  TFR_REQUIRE(records && record_sizes && B >= 0 && list_size >= 1, "bad arguments");
+  TFR_REQUIRE(n_context >= 0 && n_example >= 0, "bad feature counts");
+  TFR_REQUIRE(n_example == 0 || example_out, "example_out must not be NULL");
+  TFR_REQUIRE(n_context == 0 || context_out, "context_out must not be NULL");
+  int dc = 0, de = 0;
+  const std::vector<Spec> cspec = make_specs(context_spec, n_context, &dc);
+  const std::vector<Spec> espec = make_specs(example_spec, n_example, &de);
+  for (int b = 0; b < B; ++b) {
+    Span rec{records[b], records[b] + record_sizes[b]};
+    float* crow = dc ? context_out + static_cast<size_t>(b) * dc : nullptr;
+    if (crow) fill_defaults(cspec, crow);
+    // padded slots are parsed from an empty Example in the reference: every feature takes
+    // its default (data.py:170-183)
+    for (int i = 0; i < list_size && de; ++i)
+      fill_defaults(espec, example_out + (static_cast<size_t>(b) * list_size + i) * de);
+    int count = 0;
+    while (!rec.done()) {
+      uint32_t f, w;
+      Span pl{nullptr, nullptr};
+      uint64_t sc;
+      if (!read_field(rec, &f, &w, &pl, &sc)) {
+        set_error("record %d is not a valid ExampleListWithContext", b);
+        return TFR_INVALID_ARGUMENT;
+      }
+      if (w != 2) continue;
+      if (f == 1) {                 // one example of the list; extra ones are truncated
+        if (count < list_size && de) {
+          const int rc = parse_example(
+              pl, espec, example_out + (static_cast<size_t>(b) * list_size + count) * de);
+          if (rc) return rc;
+        }
+        ++count;
+      } else if (f == 2 && crow) {
+        const int rc = parse_example(pl, cspec, crow);
+        if (rc) return rc;
+      }
+    }
+    if (sizes_out) sizes_out[b] = count;      // the untruncated list length (data.py:148)
+    if (mask_out)
+      for (int i = 0; i < list_size; ++i)
+        mask_out[static_cast<size_t>(b) * list_size + i] = i < count ? 1 : 0;
+  }
+  return TFR_OK;
+}

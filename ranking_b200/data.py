@@ -75,3 +75,184 @@ def batch_iterator(features, labels, batch_size, shuffle=False, seed=0,
       yield x, y
     if not repeat:
       return
+
+
+# ----------------------------------------------------------------------------
+# TFRecord files of ExampleListWithContext protos (the reference's training format:
+# data.py:80-208, 391-540).  Decoding runs in the native parser behind
+# tfr_elwc_parse (csrc/elwc_parser.cu, host code).
+# ----------------------------------------------------------------------------
+import ctypes
+import struct
+
+
+def _masked_crc(data):
+  from ranking_b200 import _C
+  return int(_C.lib.tfr_masked_crc32c(data, len(data)))
+
+
+def read_tfrecords(path, verify_crc=True):
+  """Yields the payload bytes of every record of a TFRecord file
+  (uint64 length, uint32 masked crc32c(length), data, uint32 masked crc32c(data))."""
+  with open(path, 'rb') as f:
+    while True:
+      head = f.read(12)
+      if not head:
+        return
+      if len(head) < 12:
+        raise ValueError('truncated TFRecord header in %s' % path)
+      length, len_crc = struct.unpack('<QI', head)
+      if verify_crc and _masked_crc(head[:8]) != len_crc:
+        raise ValueError('corrupted TFRecord length in %s' % path)
+      data = f.read(length)
+      tail = f.read(4)
+      if len(data) < length or len(tail) < 4:
+        raise ValueError('truncated TFRecord in %s' % path)
+      if verify_crc and _masked_crc(data) != struct.unpack('<I', tail)[0]:
+        raise ValueError('corrupted TFRecord data in %s' % path)
+      yield data
+
+
+def write_tfrecords(path, records):
+  with open(path, 'wb') as f:
+    for data in records:
+      head = struct.pack('<Q', len(data))
+      f.write(head)
+      f.write(struct.pack('<I', _masked_crc(head)))
+      f.write(data)
+      f.write(struct.pack('<I', _masked_crc(data)))
+
+
+# -- a small protobuf writer for tf.Example / ExampleListWithContext (tests, data prep) --
+def _varint(v):
+  out = bytearray()
+  v &= (1 << 64) - 1
+  while True:
+    b = v & 0x7f
+    v >>= 7
+    if v:
+      out.append(b | 0x80)
+    else:
+      out.append(b)
+      return bytes(out)
+
+
+def _ld(field, payload):
+  return _varint((field << 3) | 2) + _varint(len(payload)) + payload
+
+
+def encode_example(features):
+  """{name: list of float | list of int | list of bytes} -> serialized tf.Example."""
+  entries = b''
+  for name, values in features.items():
+    values = list(values)
+    if values and isinstance(values[0], (bytes, str)):
+      body = b''.join(_ld(1, v if isinstance(v, bytes) else v.encode()) for v in values)
+      feat = _ld(1, body)
+    elif values and isinstance(values[0], int) and not isinstance(values[0], bool):
+      feat = _ld(3, _ld(1, b''.join(_varint(int(v)) for v in values)))
+    else:
+      feat = _ld(2, _ld(1, struct.pack('<%df' % len(values), *[float(v) for v in values])))
+    entries += _ld(1, _ld(1, name.encode()) + _ld(2, feat))
+  return _ld(1, entries)
+
+
+def encode_elwc(context, examples):
+  """ExampleListWithContext{examples = 1 (repeated), context = 2}."""
+  out = b''.join(_ld(1, encode_example(e)) for e in examples)
+  if context is not None:
+    out += _ld(2, encode_example(context))
+  return out
+
+
+def _spec_array(spec):
+  from ranking_b200 import _C
+  items = list(spec.items()) if spec else []
+  arr = (_C.FeatureSpec * max(len(items), 1))()
+  keep = []
+  for i, (name, (dim, default)) in enumerate(items):
+    key = name.encode()
+    keep.append(key)
+    arr[i].name = key
+    arr[i].dim = int(dim)
+    arr[i].default_value = float(default)
+  return arr, len(items), sum(int(d) for _, (d, _) in items), keep
+
+
+def parse_from_example_list(serialized, list_size, context_feature_spec=None,
+                            example_feature_spec=None, pin_memory=False):
+  """data.py:391-540 for dense float / int64 features.  `serialized`: a sequence of
+  serialized ELWC protos; the specs map feature name -> (dim, default_value), in the
+  column order wanted.  Returns dict(context [B, Dc], examples [B, list_size, De],
+  sizes [B] int32, mask [B, list_size] bool) of CPU tensors."""
+  from ranking_b200 import _C
+  records = [bytes(r) for r in serialized]
+  b = len(records)
+  carr, nc, dc, keep_c = _spec_array(context_feature_spec)
+  earr, ne, de, keep_e = _spec_array(example_feature_spec)
+  ptrs = (ctypes.c_char_p * max(b, 1))(*records)
+  lens = (ctypes.c_int64 * max(b, 1))(*[len(r) for r in records])
+
+  def alloc(*shape, dtype=torch.float32):
+    t = torch.empty(*shape, dtype=dtype)
+    return t.pin_memory() if pin_memory and torch.cuda.is_available() else t
+
+  ctx = alloc(b, dc)
+  ex = alloc(b, list_size, de)
+  sizes = torch.empty(b, dtype=torch.int32)
+  mask = torch.empty(b, list_size, dtype=torch.uint8)
+  _C.check(_C.lib.tfr_elwc_parse(
+      ptrs, lens, b, int(list_size), carr, nc, earr, ne,
+      ctypes.c_void_p(ctx.data_ptr()) if dc else None,
+      ctypes.c_void_p(ex.data_ptr()) if de else None,
+      ctypes.c_void_p(sizes.data_ptr()), ctypes.c_void_p(mask.data_ptr())))
+  del keep_c, keep_e
+  return {'context': ctx, 'examples': ex, 'sizes': sizes, 'mask': mask.bool()}
+
+
+def elwc_batches(paths, batch_size, list_size, context_feature_spec, example_feature_spec,
+                 label_feature, drop_remainder=True, pin_memory=True):
+  """Yields (x [B, list_size, Dc + De], y [B, list_size]) from TFRecord files of ELWC
+  protos: context features first (repeated over the list), then the example features —
+  the layout `DNNScorer` builds (keras/model.py:800-817).  `label_feature` names the
+  example feature that holds the relevance label (give it the default -1 so that padded
+  slots are invalid); it is removed from x."""
+  ex_spec = dict(example_feature_spec)
+  if label_feature not in ex_spec:
+    raise ValueError('label feature %r is not in example_feature_spec' % label_feature)
+  names = list(ex_spec)
+  off = 0
+  cols = []
+  for name in names:
+    dim = int(ex_spec[name][0])
+    if name == label_feature:
+      label_col = off
+      if dim != 1:
+        raise ValueError('the label feature must have dim 1')
+    else:
+      cols.extend(range(off, off + dim))
+    off += dim
+  buf = []
+
+  def flush():
+    out = parse_from_example_list(buf, list_size, context_feature_spec, ex_spec)
+    ex = out['examples']
+    y = ex[:, :, label_col].clone()
+    y = torch.where(out['mask'], y, torch.full_like(y, -1.))
+    feats = ex[:, :, cols]
+    if out['context'].shape[1]:
+      ctx = out['context'].unsqueeze(1).expand(-1, list_size, -1)
+      feats = torch.cat([ctx, feats], 2)
+    x = feats.contiguous()
+    if pin_memory and torch.cuda.is_available():
+      x, y = x.pin_memory(), y.pin_memory()
+    return x, y
+
+  for path in ([paths] if isinstance(paths, str) else paths):
+    for rec in read_tfrecords(path):
+      buf.append(rec)
+      if len(buf) == batch_size:
+        yield flush()
+        buf = []
+  if buf and not drop_remainder:
+    yield flush()

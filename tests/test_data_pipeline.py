@@ -82,3 +82,154 @@ def test_fit_checkpoint_resume(tmp_path):
   res = pipeline.evaluate(resumed, data.batch_iterator(x, y, 8, drop_remainder=False))
   assert set(res) >= {'metric/ndcg_10', 'metric/mrr', 'metric/arp', 'metric/map',
                       'metric/ordered_pair_accuracy', 'metric/precision', 'metric/dcg'}
+
+
+# ------------------------- ELWC / TFRecord input side ------------------------
+def _elwc_records():
+  from ranking_b200 import data
+  recs = [
+      data.encode_elwc({'query_length': [3], 'qf': [0.5, 1.5]},
+                       [{'utility': [0.0], 'f': [1.0, 2.0, 3.0]},
+                        {'utility': [1.0], 'f': [4.0, 5.0, 6.0], 'unigrams': [b'to', b'rank']},
+                        {'utility': [2.0]}]),                       # 'f' missing -> default
+      data.encode_elwc({'query_length': [2]},                        # 'qf' missing -> default
+                       [{'utility': [1.0], 'f': [7.0, 8.0, 9.0]}]),
+      data.encode_elwc(None, [{'utility': [0.0], 'f': [1.0, 1.0, 1.0]}] * 5),   # truncated to 4
+  ]
+  return recs
+
+
+def test_parse_from_example_list():
+  """data.py:133-208 semantics: padding with defaults, truncation, sizes, mask."""
+  from ranking_b200 import data
+  out = data.parse_from_example_list(
+      _elwc_records(), list_size=4,
+      context_feature_spec={'query_length': (1, 0.0), 'qf': (2, -7.0)},
+      example_feature_spec={'utility': (1, -1.0), 'f': (3, 0.25)})
+  assert out['sizes'].tolist() == [3, 1, 5]
+  assert out['mask'].tolist() == [[True, True, True, False], [True, False, False, False],
+                                  [True, True, True, True]]
+  np.testing.assert_array_equal(out['context'].numpy(),
+                                [[3., 0.5, 1.5], [2., -7., -7.], [0., -7., -7.]])
+  ex = out['examples'].numpy()
+  np.testing.assert_array_equal(ex[0], [[0., 1., 2., 3.], [1., 4., 5., 6.],
+                                        [2., .25, .25, .25], [-1., .25, .25, .25]])
+  np.testing.assert_array_equal(ex[1], [[1., 7., 8., 9.]] + [[-1., .25, .25, .25]] * 3)
+  np.testing.assert_array_equal(ex[2], [[0., 1., 1., 1.]] * 4)
+
+
+def test_parse_from_example_list_errors():
+  from ranking_b200 import data
+  recs = _elwc_records()
+  with pytest.raises(ValueError):      # wrong fixed length
+    data.parse_from_example_list(recs, 4, None, {'f': (2, 0.0)})
+  with pytest.raises(ValueError):      # bytes feature requested as dense input
+    data.parse_from_example_list(recs, 4, None, {'unigrams': (1, 0.0)})
+  with pytest.raises(ValueError):      # garbage bytes
+    data.parse_from_example_list([b'\xff\xff\xff'], 4, None, {'f': (3, 0.0)})
+
+
+def test_tfrecord_roundtrip_and_batches(tmp_path):
+  from ranking_b200 import data
+  path = str(tmp_path / 'train.tfrecord')
+  recs = _elwc_records()
+  data.write_tfrecords(path, recs)
+  assert list(data.read_tfrecords(path)) == recs
+  raw = bytearray(open(path, 'rb').read())
+  raw[20] ^= 0xff                      # flip a payload byte: the data crc must catch it
+  bad = str(tmp_path / 'bad.tfrecord')
+  open(bad, 'wb').write(bytes(raw))
+  with pytest.raises(ValueError):
+    list(data.read_tfrecords(bad))
+  batches = list(data.elwc_batches(
+      path, batch_size=2, list_size=4, context_feature_spec={'qf': (2, 0.0)},
+      example_feature_spec={'f': (3, 0.0), 'utility': (1, -1.0)}, label_feature='utility',
+      drop_remainder=False, pin_memory=False))
+  assert [tuple(x.shape) for x, _ in batches] == [(2, 4, 5), (1, 4, 5)]
+  x, y = batches[0]
+  np.testing.assert_array_equal(y.numpy(), [[0., 1., 2., -1.], [1., -1., -1., -1.]])
+  np.testing.assert_array_equal(x[0, 1].numpy(), [0.5, 1.5, 4., 5., 6.])   # context first
+  np.testing.assert_array_equal(x[1, 0].numpy(), [0., 0., 7., 8., 9.])
+
+
+def _protobuf_classes():
+  """tf.Example / ExampleListWithContext rebuilt with the real protobuf runtime
+  (tensorflow/core/example/{example,feature}.proto and
+  tensorflow_serving/apis/input.proto field numbers)."""
+  from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+  fd = descriptor_pb2.FileDescriptorProto()
+  fd.name = 'tfr_b200_test_example.proto'
+  fd.package = 'tfrtest'
+  fd.syntax = 'proto3'
+  T = descriptor_pb2.FieldDescriptorProto
+
+  def msg(name, fields):
+    m = fd.message_type.add()
+    m.name = name
+    for fname, num, typ, label, tname in fields:
+      f = m.field.add()
+      f.name, f.number, f.type, f.label = fname, num, typ, label
+      if tname:
+        f.type_name = '.tfrtest.' + tname
+    return m
+
+  R, O = T.LABEL_REPEATED, T.LABEL_OPTIONAL
+  msg('BytesList', [('value', 1, T.TYPE_BYTES, R, None)])
+  msg('FloatList', [('value', 1, T.TYPE_FLOAT, R, None)])
+  msg('Int64List', [('value', 1, T.TYPE_INT64, R, None)])
+  feat = msg('Feature', [('bytes_list', 1, T.TYPE_MESSAGE, O, 'BytesList'),
+                         ('float_list', 2, T.TYPE_MESSAGE, O, 'FloatList'),
+                         ('int64_list', 3, T.TYPE_MESSAGE, O, 'Int64List')])
+  del feat
+  features = msg('Features', [('feature', 1, T.TYPE_MESSAGE, R, 'Features.FeatureEntry')])
+  entry = features.nested_type.add()
+  entry.name = 'FeatureEntry'
+  entry.options.map_entry = True
+  for fname, num, typ, tname in (('key', 1, T.TYPE_STRING, None),
+                                 ('value', 2, T.TYPE_MESSAGE, 'Feature')):
+    f = entry.field.add()
+    f.name, f.number, f.type, f.label = fname, num, typ, O
+    if tname:
+      f.type_name = '.tfrtest.' + tname
+  msg('Example', [('features', 1, T.TYPE_MESSAGE, O, 'Features')])
+  msg('ExampleListWithContext', [('examples', 1, T.TYPE_MESSAGE, R, 'Example'),
+                                 ('context', 2, T.TYPE_MESSAGE, O, 'Example')])
+  pool = descriptor_pool.DescriptorPool()
+  pool.Add(fd)
+  get = lambda n: message_factory.GetMessageClass(pool.FindMessageTypeByName('tfrtest.' + n))
+  return get('Example'), get('ExampleListWithContext')
+
+
+def test_parser_reads_protobuf_runtime_output():
+  """Records serialized by the real protobuf runtime (packed repeated fields, map
+  entries in its own order) decode to the same tensors as our writer's."""
+  pytest.importorskip('google.protobuf')
+  from ranking_b200 import data
+  Example, ELWC = _protobuf_classes()
+  elwc = ELWC()
+  elwc.context.features.feature['qf'].float_list.value.extend([0.5, 1.5])
+  elwc.context.features.feature['query_length'].int64_list.value.append(3)
+  for util, f in ((0.0, [1.0, 2.0, 3.0]), (1.0, [4.0, 5.0, 6.0])):
+    ex = elwc.examples.add()
+    ex.features.feature['utility'].float_list.value.append(util)
+    ex.features.feature['f'].float_list.value.extend(f)
+    ex.features.feature['unigrams'].bytes_list.value.append(b'x')
+  ex = elwc.examples.add()
+  ex.features.feature['utility'].int64_list.value.append(-2)       # int64 -> float cast
+  spec_c = {'query_length': (1, 0.0), 'qf': (2, -7.0)}
+  spec_e = {'utility': (1, -1.0), 'f': (3, 0.25)}
+  got = data.parse_from_example_list([elwc.SerializeToString()], 4, spec_c, spec_e)
+  np.testing.assert_array_equal(got['context'].numpy(), [[3., 0.5, 1.5]])
+  np.testing.assert_array_equal(
+      got['examples'][0].numpy(),
+      [[0., 1., 2., 3.], [1., 4., 5., 6.], [-2., .25, .25, .25], [-1., .25, .25, .25]])
+  assert got['sizes'].tolist() == [3]
+  # and the runtime parses what our writer emits
+  mine = data.encode_elwc({'qf': [0.5, 1.5], 'query_length': [3]},
+                          [{'utility': [0.0], 'f': [1.0, 2.0, 3.0], 'unigrams': [b'x']}])
+  back = ELWC()
+  back.ParseFromString(mine)
+  assert list(back.context.features.feature['qf'].float_list.value) == [0.5, 1.5]
+  assert list(back.context.features.feature['query_length'].int64_list.value) == [3]
+  assert list(back.examples[0].features.feature['f'].float_list.value) == [1.0, 2.0, 3.0]
+  assert list(back.examples[0].features.feature['unigrams'].bytes_list.value) == [b'x']
