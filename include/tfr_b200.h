@@ -374,7 +374,8 @@ int tfr_tc_set_debug(long long* buf);
  *   present feature must have exactly `dim` values; int64 values are cast to float;
  *   examples past list_size are dropped), sizes_out [B] = untruncated list lengths,
  *   mask_out [B, list_size] = sequence_mask(sizes, list_size).  All pointers are HOST
- *   pointers (pinned memory recommended: the result feeds one H2D copy).
+ *   pointers (pinned memory recommended: the result feeds one H2D copy).  Lists are
+ *   decoded in parallel by n_threads host threads (<= 0: all hardware threads).
  * tfr_masked_crc32c: the checksum of the TFRecord framing.
  * ------------------------------------------------------------------------- */
 typedef struct {
@@ -387,7 +388,7 @@ int tfr_elwc_parse(const uint8_t* const* records, const int64_t* record_sizes,
                    int B, int list_size, const tfr_feature_spec* context_spec,
                    int n_context, const tfr_feature_spec* example_spec,
                    int n_example, float* context_out, float* example_out,
-                   int32_t* sizes_out, uint8_t* mask_out);
+                   int32_t* sizes_out, uint8_t* mask_out, int n_threads);
 uint32_t tfr_masked_crc32c(const uint8_t* data, size_t n);
 
 /* ---------------------------------------------------------------------------

@@ -10,8 +10,10 @@
 //   Features { map<string, Feature> feature = 1; }   entry { string key = 1; Feature value = 2; }
 //   Feature  { oneof { BytesList bytes_list = 1; FloatList float_list = 2; Int64List int64_list = 3; } }
 //   FloatList { repeated float value = 1; }  Int64List { repeated int64 value = 1; }   (packed or not)
+#include <atomic>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -219,7 +221,7 @@ extern "C" int tfr_elwc_parse(const uint8_t* const* records, const int64_t* reco
                               int list_size, const tfr_feature_spec* context_spec, int n_context,
                               const tfr_feature_spec* example_spec, int n_example,
                               float* context_out, float* example_out, int32_t* sizes_out,
-                              uint8_t* mask_out) {
+                              uint8_t* mask_out, int n_threads) {
   TFR_REQUIRE(records && record_sizes && B >= 0 && list_size >= 1, "bad arguments");
   TFR_REQUIRE(n_context >= 0 && n_example >= 0, "bad feature counts");
   TFR_REQUIRE(n_example == 0 || example_out, "example_out must not be NULL");
@@ -227,7 +229,9 @@ extern "C" int tfr_elwc_parse(const uint8_t* const* records, const int64_t* reco
   int dc = 0, de = 0;
   const std::vector<Spec> cspec = make_specs(context_spec, n_context, &dc);
   const std::vector<Spec> espec = make_specs(example_spec, n_example, &de);
-  for (int b = 0; b < B; ++b) {
+
+  // one list = one independent unit of work
+  auto parse_one = [&](int b) -> int {
     Span rec{records[b], records[b] + record_sizes[b]};
     float* crow = dc ? context_out + static_cast<size_t>(b) * dc : nullptr;
     if (crow) fill_defaults(cspec, crow);
@@ -261,6 +265,39 @@ extern "C" int tfr_elwc_parse(const uint8_t* const* records, const int64_t* reco
     if (mask_out)
       for (int i = 0; i < list_size; ++i)
         mask_out[static_cast<size_t>(b) * list_size + i] = i < count ? 1 : 0;
+    return TFR_OK;
+  };
+
+  int threads = n_threads > 0 ? n_threads : static_cast<int>(std::thread::hardware_concurrency());
+  if (threads < 1) threads = 1;
+  if (threads > B) threads = B;
+  if (threads <= 1) {
+    for (int b = 0; b < B; ++b) {
+      const int rc = parse_one(b);
+      if (rc) return rc;
+    }
+    return TFR_OK;
+  }
+  // lists are handed out by an atomic counter; the first failure wins and its message
+  // (thread-local in the worker) is re-raised on the calling thread
+  std::atomic<int> next{0}, status{TFR_OK};
+  std::vector<std::string> messages(threads);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&, t] {
+      for (int b = next.fetch_add(1); b < B && status.load() == TFR_OK; b = next.fetch_add(1)) {
+        const int rc = parse_one(b);
+        if (rc) {
+          int expected = TFR_OK;
+          if (status.compare_exchange_strong(expected, rc)) messages[t] = tfr_last_error();
+        }
+      }
+    });
+  for (std::thread& th : pool) th.join();
+  if (status.load() != TFR_OK) {
+    for (const std::string& m : messages)
+      if (!m.empty()) set_error("%s", m.c_str());
+    return status.load();
   }
   return TFR_OK;
 }

@@ -180,7 +180,7 @@ def _spec_array(spec):
 
 
 def parse_from_example_list(serialized, list_size, context_feature_spec=None,
-                            example_feature_spec=None, pin_memory=False):
+                            example_feature_spec=None, pin_memory=False, num_threads=0):
   """data.py:391-540 for dense float / int64 features.  `serialized`: a sequence of
   serialized ELWC protos; the specs map feature name -> (dim, default_value), in the
   column order wanted.  Returns dict(context [B, Dc], examples [B, list_size, De],
@@ -205,7 +205,8 @@ def parse_from_example_list(serialized, list_size, context_feature_spec=None,
       ptrs, lens, b, int(list_size), carr, nc, earr, ne,
       ctypes.c_void_p(ctx.data_ptr()) if dc else None,
       ctypes.c_void_p(ex.data_ptr()) if de else None,
-      ctypes.c_void_p(sizes.data_ptr()), ctypes.c_void_p(mask.data_ptr())))
+      ctypes.c_void_p(sizes.data_ptr()), ctypes.c_void_p(mask.data_ptr()),
+      int(num_threads)))
   del keep_c, keep_e
   return {'context': ctx, 'examples': ex, 'sizes': sizes, 'mask': mask.bool()}
 
