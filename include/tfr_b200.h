@@ -10,7 +10,8 @@
  *
  * Conventions
  *   - every data pointer is a DEVICE pointer owned by the caller unless the
- *     name ends in `_host`; the library never allocates or frees caller memory
+ *     name ends in `_host` or the entry point says otherwise (tfr_elwc_parse works on
+ *     host buffers); the library never allocates or frees caller memory
  *   - config structs are HOST pointers, read during the call
  *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered,
  *     re-entrant and keep no global state besides the last-error string
