@@ -390,6 +390,24 @@ int tfr_elwc_parse(const uint8_t* const* records, const int64_t* record_sizes,
                    int n_context, const tfr_feature_spec* example_spec,
                    int n_example, float* context_out, float* example_out,
                    int32_t* sizes_out, uint8_t* mask_out, int n_threads);
+/* The other two record formats of data.py (`make_parsing_fn`, :857-911), same outputs:
+ *   EXAMPLE_IN_EXAMPLE  an outer tf.Example with bytes features `serialized_context` and
+ *                       `serialized_examples` (:133-208)
+ *   SEQUENCE_EXAMPLE    context features in `context`, item i of every example feature in
+ *                       frame i of its feature list (:572-711); the list length is the
+ *                       longest requested feature list */
+typedef enum {
+  TFR_FORMAT_ELWC = 0,
+  TFR_FORMAT_EXAMPLE_IN_EXAMPLE = 1,
+  TFR_FORMAT_SEQUENCE_EXAMPLE = 2
+} tfr_data_format;
+
+int tfr_ranking_parse(int format, const uint8_t* const* records,
+                      const int64_t* record_sizes, int B, int list_size,
+                      const tfr_feature_spec* context_spec, int n_context,
+                      const tfr_feature_spec* example_spec, int n_example,
+                      float* context_out, float* example_out, int32_t* sizes_out,
+                      uint8_t* mask_out, int n_threads);
 uint32_t tfr_masked_crc32c(const uint8_t* data, size_t n);
 
 /* ---------------------------------------------------------------------------

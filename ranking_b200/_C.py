@@ -89,6 +89,9 @@ _SIGNATURES = {
     'tfr_elwc_parse': (_I, [C.POINTER(C.c_char_p), C.POINTER(C.c_int64), _I, _I,
                             C.POINTER(FeatureSpec), _I, C.POINTER(FeatureSpec), _I, _P, _P, _P,
                             _P, _I]),
+    'tfr_ranking_parse': (_I, [_I, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), _I, _I,
+                               C.POINTER(FeatureSpec), _I, C.POINTER(FeatureSpec), _I, _P, _P,
+                               _P, _P, _I]),
     'tfr_masked_crc32c': (C.c_uint32, [C.c_char_p, C.c_size_t]),
     'tfr_weighted_sum': (_I, [_P, _P, _I, _F, _P, _P]),
     'tfr_mlp_param_count': (C.c_size_t, [C.POINTER(MlpCfg)]),

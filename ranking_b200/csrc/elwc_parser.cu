@@ -123,7 +123,71 @@ int parse_values(Span list, bool is_float, float* dst, int dim) {
   return n;
 }
 
-// One serialized tf.Example -> row (already filled with the defaults).
+// One Feature message (oneof bytes / float / int64 list) -> row[spec.offset ..].
+int parse_feature_value(Span value, const Spec& spec, float* row) {
+  while (!value.done()) {
+    uint32_t f, w;
+    Span list{nullptr, nullptr};
+    uint64_t sc;
+    if (!read_field(value, &f, &w, &list, &sc)) return TFR_INVALID_ARGUMENT;
+    if (w != 2) continue;
+    if (f == 1) {
+      set_error("feature '%s' is a bytes_list; only float_list / int64_list features can "
+                "be decoded into the dense scorer input", spec.name.c_str());
+      return TFR_UNSUPPORTED;
+    }
+    const int n = parse_values(list, f == 2, row + spec.offset, spec.dim);
+    if (n < 0) return TFR_INVALID_ARGUMENT;
+    if (n != spec.dim && n != 0) {   // tf.io.FixedLenFeature: exact length or missing
+      set_error("feature '%s' has %d values, the spec says %d", spec.name.c_str(), n, spec.dim);
+      return TFR_INVALID_ARGUMENT;
+    }
+  }
+  return TFR_OK;
+}
+
+const Spec* find_spec(const std::vector<Spec>& specs, Span key) {
+  const size_t klen = static_cast<size_t>(key.end - key.p);
+  for (const Spec& s : specs)
+    if (s.name.size() == klen && std::memcmp(s.name.data(), key.p, klen) == 0) return &s;
+  return nullptr;
+}
+
+// Splits one map entry { key = 1; value = 2 } of Features / FeatureLists.
+bool read_entry(Span entry, Span* key, Span* value) {
+  key->p = value->p = nullptr;
+  while (!entry.done()) {
+    uint32_t f, w;
+    Span pl{nullptr, nullptr};
+    uint64_t sc;
+    if (!read_field(entry, &f, &w, &pl, &sc)) return false;
+    if (w != 2) continue;
+    if (f == 1) *key = pl;
+    if (f == 2) *value = pl;
+  }
+  return true;
+}
+
+// A Features message -> row (already filled with the defaults).
+int parse_features(Span features, const std::vector<Spec>& specs, float* row) {
+  while (!features.done()) {
+    uint32_t f, w;
+    Span entry{nullptr, nullptr};
+    uint64_t sc;
+    if (!read_field(features, &f, &w, &entry, &sc)) return TFR_INVALID_ARGUMENT;
+    if (f != 1 || w != 2) continue;
+    Span key, value;
+    if (!read_entry(entry, &key, &value)) return TFR_INVALID_ARGUMENT;
+    if (!key.p || !value.p) continue;
+    const Spec* spec = find_spec(specs, key);
+    if (!spec) continue;            // feature not requested
+    const int rc = parse_feature_value(value, *spec, row);
+    if (rc) return rc;
+  }
+  return TFR_OK;
+}
+
+// One serialized tf.Example { Features features = 1 } -> row.
 int parse_example(Span ex, const std::vector<Spec>& specs, float* row) {
   while (!ex.done()) {
     uint32_t f, w;
@@ -131,44 +195,27 @@ int parse_example(Span ex, const std::vector<Spec>& specs, float* row) {
     uint64_t sc;
     if (!read_field(ex, &f, &w, &features, &sc)) return TFR_INVALID_ARGUMENT;
     if (f != 1 || w != 2) continue;
-    while (!features.done()) {
-      Span entry{nullptr, nullptr};
-      if (!read_field(features, &f, &w, &entry, &sc)) return TFR_INVALID_ARGUMENT;
+    const int rc = parse_features(features, specs, row);
+    if (rc) return rc;
+  }
+  return TFR_OK;
+}
+
+// Visits the values of a bytes_list Feature.
+template <typename Fn>
+int for_each_bytes(Span feature, Fn fn) {
+  while (!feature.done()) {
+    uint32_t f, w;
+    Span list{nullptr, nullptr};
+    uint64_t sc;
+    if (!read_field(feature, &f, &w, &list, &sc)) return TFR_INVALID_ARGUMENT;
+    if (f != 1 || w != 2) continue;       // bytes_list
+    while (!list.done()) {
+      Span v{nullptr, nullptr};
+      if (!read_field(list, &f, &w, &v, &sc)) return TFR_INVALID_ARGUMENT;
       if (f != 1 || w != 2) continue;
-      Span key{nullptr, nullptr}, value{nullptr, nullptr};
-      while (!entry.done()) {
-        Span pl{nullptr, nullptr};
-        if (!read_field(entry, &f, &w, &pl, &sc)) return TFR_INVALID_ARGUMENT;
-        if (w != 2) continue;
-        if (f == 1) key = pl;
-        if (f == 2) value = pl;
-      }
-      if (!key.p || !value.p) continue;
-      const size_t klen = static_cast<size_t>(key.end - key.p);
-      const Spec* spec = nullptr;
-      for (const Spec& s : specs)
-        if (s.name.size() == klen && std::memcmp(s.name.data(), key.p, klen) == 0) {
-          spec = &s;
-          break;
-        }
-      if (!spec) continue;            // feature not requested
-      while (!value.done()) {
-        Span list{nullptr, nullptr};
-        if (!read_field(value, &f, &w, &list, &sc)) return TFR_INVALID_ARGUMENT;
-        if (w != 2) continue;
-        if (f == 1) {
-          set_error("feature '%s' is a bytes_list; only float_list / int64_list features can "
-                    "be decoded into the dense scorer input", spec->name.c_str());
-          return TFR_UNSUPPORTED;
-        }
-        const int n = parse_values(list, f == 2, row + spec->offset, spec->dim);
-        if (n < 0) return TFR_INVALID_ARGUMENT;
-        if (n != spec->dim && n != 0) {   // tf.io.FixedLenFeature: exact length or missing
-          set_error("feature '%s' has %d values, the spec says %d", spec->name.c_str(), n,
-                    spec->dim);
-          return TFR_INVALID_ARGUMENT;
-        }
-      }
+      const int rc = fn(v);
+      if (rc) return rc;
     }
   }
   return TFR_OK;
@@ -217,11 +264,14 @@ extern "C" uint32_t tfr_masked_crc32c(const uint8_t* data, size_t n) {
   return ((c >> 15) | (c << 17)) + 0xa282ead8u;   // TFRecord's masking
 }
 
-extern "C" int tfr_elwc_parse(const uint8_t* const* records, const int64_t* record_sizes, int B,
-                              int list_size, const tfr_feature_spec* context_spec, int n_context,
-                              const tfr_feature_spec* example_spec, int n_example,
-                              float* context_out, float* example_out, int32_t* sizes_out,
-                              uint8_t* mask_out, int n_threads) {
+extern "C" int tfr_ranking_parse(int format, const uint8_t* const* records,
+                                 const int64_t* record_sizes, int B, int list_size,
+                                 const tfr_feature_spec* context_spec, int n_context,
+                                 const tfr_feature_spec* example_spec, int n_example,
+                                 float* context_out, float* example_out, int32_t* sizes_out,
+                                 uint8_t* mask_out, int n_threads) {
+  TFR_REQUIRE(format >= TFR_FORMAT_ELWC && format <= TFR_FORMAT_SEQUENCE_EXAMPLE,
+              "format %d is not a tfr_data_format", format);
   TFR_REQUIRE(records && record_sizes && B >= 0 && list_size >= 1, "bad arguments");
   TFR_REQUIRE(n_context >= 0 && n_example >= 0, "bad feature counts");
   TFR_REQUIRE(n_example == 0 || example_out, "example_out must not be NULL");
@@ -240,25 +290,105 @@ extern "C" int tfr_elwc_parse(const uint8_t* const* records, const int64_t* reco
     for (int i = 0; i < list_size && de; ++i)
       fill_defaults(espec, example_out + (static_cast<size_t>(b) * list_size + i) * de);
     int count = 0;
-    while (!rec.done()) {
-      uint32_t f, w;
-      Span pl{nullptr, nullptr};
-      uint64_t sc;
-      if (!read_field(rec, &f, &w, &pl, &sc)) {
-        set_error("record %d is not a valid ExampleListWithContext", b);
-        return TFR_INVALID_ARGUMENT;
-      }
-      if (w != 2) continue;
-      if (f == 1) {                 // one example of the list; extra ones are truncated
-        if (count < list_size && de) {
-          const int rc = parse_example(
-              pl, espec, example_out + (static_cast<size_t>(b) * list_size + count) * de);
+    auto example_row = [&](int i) {
+      return example_out + (static_cast<size_t>(b) * list_size + i) * de;
+    };
+    auto bad_record = [&]() {
+      set_error("record %d is not a valid %s", b,
+                format == TFR_FORMAT_ELWC ? "ExampleListWithContext"
+                : format == TFR_FORMAT_EXAMPLE_IN_EXAMPLE ? "Example-in-Example record"
+                                                          : "SequenceExample");
+      return TFR_INVALID_ARGUMENT;
+    };
+    if (format == TFR_FORMAT_ELWC) {
+      // ExampleListWithContext { repeated Example examples = 1; Example context = 2; }
+      while (!rec.done()) {
+        uint32_t f, w;
+        Span pl{nullptr, nullptr};
+        uint64_t sc;
+        if (!read_field(rec, &f, &w, &pl, &sc)) return bad_record();
+        if (w != 2) continue;
+        if (f == 1) {                 // one example of the list; extra ones are truncated
+          if (count < list_size && de) {
+            const int rc = parse_example(pl, espec, example_row(count));
+            if (rc) return rc;
+          }
+          ++count;
+        } else if (f == 2 && crow) {
+          const int rc = parse_example(pl, cspec, crow);
           if (rc) return rc;
         }
-        ++count;
-      } else if (f == 2 && crow) {
-        const int rc = parse_example(pl, cspec, crow);
-        if (rc) return rc;
+      }
+    } else if (format == TFR_FORMAT_EXAMPLE_IN_EXAMPLE) {
+      // an outer Example whose bytes features `serialized_context` [1] and
+      // `serialized_examples` [n] hold serialized Examples (data.py:136-150)
+      while (!rec.done()) {
+        uint32_t f, w;
+        Span features{nullptr, nullptr};
+        uint64_t sc;
+        if (!read_field(rec, &f, &w, &features, &sc)) return bad_record();
+        if (f != 1 || w != 2) continue;
+        while (!features.done()) {
+          Span entry{nullptr, nullptr};
+          if (!read_field(features, &f, &w, &entry, &sc)) return bad_record();
+          if (f != 1 || w != 2) continue;
+          Span key, value;
+          if (!read_entry(entry, &key, &value)) return bad_record();
+          if (!key.p || !value.p) continue;
+          const std::string k(reinterpret_cast<const char*>(key.p),
+                              static_cast<size_t>(key.end - key.p));
+          int rc = TFR_OK;
+          if (k == "serialized_context") {
+            rc = for_each_bytes(value, [&](Span v) {
+              return crow ? parse_example(v, cspec, crow) : TFR_OK;
+            });
+          } else if (k == "serialized_examples") {
+            rc = for_each_bytes(value, [&](Span v) {
+              int r = TFR_OK;
+              if (count < list_size && de) r = parse_example(v, espec, example_row(count));
+              ++count;
+              return r;
+            });
+          }
+          if (rc) return rc;
+        }
+      }
+    } else {
+      // SequenceExample { Features context = 1; FeatureLists feature_lists = 2; }
+      // FeatureLists { map<string, FeatureList> = 1 }, FeatureList { repeated Feature = 1 }:
+      // frame i of a feature list is item i (data.py:572-711)
+      while (!rec.done()) {
+        uint32_t f, w;
+        Span pl{nullptr, nullptr};
+        uint64_t sc;
+        if (!read_field(rec, &f, &w, &pl, &sc)) return bad_record();
+        if (w != 2) continue;
+        if (f == 1 && crow) {
+          const int rc = parse_features(pl, cspec, crow);
+          if (rc) return rc;
+        } else if (f == 2) {
+          while (!pl.done()) {
+            Span entry{nullptr, nullptr};
+            if (!read_field(pl, &f, &w, &entry, &sc)) return bad_record();
+            if (f != 1 || w != 2) continue;
+            Span key, value;
+            if (!read_entry(entry, &key, &value)) return bad_record();
+            if (!key.p || !value.p) continue;
+            const Spec* spec = find_spec(espec, key);
+            int frame = 0;
+            while (!value.done()) {           // FeatureList.feature
+              Span feat{nullptr, nullptr};
+              if (!read_field(value, &f, &w, &feat, &sc)) return bad_record();
+              if (f != 1 || w != 2) continue;
+              if (spec && frame < list_size) {
+                const int rc = parse_feature_value(feat, *spec, example_row(frame));
+                if (rc) return rc;
+              }
+              ++frame;
+            }
+            if (spec && frame > count) count = frame;
+          }
+        }
       }
     }
     if (sizes_out) sizes_out[b] = count;      // the untruncated list length (data.py:148)
@@ -300,4 +430,14 @@ extern "C" int tfr_elwc_parse(const uint8_t* const* records, const int64_t* reco
     return status.load();
   }
   return TFR_OK;
+}
+
+extern "C" int tfr_elwc_parse(const uint8_t* const* records, const int64_t* record_sizes, int B,
+                              int list_size, const tfr_feature_spec* context_spec, int n_context,
+                              const tfr_feature_spec* example_spec, int n_example,
+                              float* context_out, float* example_out, int32_t* sizes_out,
+                              uint8_t* mask_out, int n_threads) {
+  return tfr_ranking_parse(TFR_FORMAT_ELWC, records, record_sizes, B, list_size, context_spec,
+                           n_context, example_spec, n_example, context_out, example_out,
+                           sizes_out, mask_out, n_threads);
 }

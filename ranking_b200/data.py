@@ -179,13 +179,79 @@ def _spec_array(spec):
   return arr, len(items), sum(int(d) for _, (d, _) in items), keep
 
 
+EXAMPLE_LIST_WITH_CONTEXT = 'example_list_with_context'   # data.py:45-51 data formats
+EXAMPLE_IN_EXAMPLE = 'example_in_example'
+SEQUENCE_EXAMPLE = 'sequence_example'
+_FORMATS = {EXAMPLE_LIST_WITH_CONTEXT: 0, EXAMPLE_IN_EXAMPLE: 1, SEQUENCE_EXAMPLE: 2}
+
+
+def parse_from_example_in_example(serialized, list_size, context_feature_spec=None,
+                                  example_feature_spec=None, **kwargs):
+  """data.py:211-380 (dense features): outer Examples with `serialized_context` /
+  `serialized_examples` bytes features."""
+  return parse_from_example_list(serialized, list_size, context_feature_spec,
+                                 example_feature_spec, data_format=EXAMPLE_IN_EXAMPLE,
+                                 **kwargs)
+
+
+def parse_from_sequence_example(serialized, list_size, context_feature_spec=None,
+                                example_feature_spec=None, **kwargs):
+  """data.py:713-855 (dense features): SequenceExamples, item i = frame i."""
+  return parse_from_example_list(serialized, list_size, context_feature_spec,
+                                 example_feature_spec, data_format=SEQUENCE_EXAMPLE,
+                                 **kwargs)
+
+
+def make_parsing_fn(data_format, list_size, context_feature_spec=None,
+                    example_feature_spec=None, **kwargs):
+  """data.py:857-911: serialized records -> feature dict, for any of the three formats."""
+  if data_format not in _FORMATS:
+    raise ValueError('Data format {} is not supported.'.format(data_format))
+  return lambda serialized: parse_from_example_list(
+      serialized, list_size, context_feature_spec, example_feature_spec,
+      data_format=data_format, **kwargs)
+
+
+def encode_example_in_example(context, examples):
+  """The EIE record for `context` / `examples` feature dicts (see encode_example)."""
+  return encode_example({
+      'serialized_context': [encode_example(context or {})],
+      'serialized_examples': [encode_example(e) for e in examples]})
+
+
+def _encode_feature(values):
+  """One Feature message (oneof bytes / float / int64 list)."""
+  values = list(values)
+  if values and isinstance(values[0], (bytes, str)):
+    return _ld(1, b''.join(_ld(1, v if isinstance(v, bytes) else v.encode()) for v in values))
+  if values and isinstance(values[0], int) and not isinstance(values[0], bool):
+    return _ld(3, _ld(1, b''.join(_varint(int(v)) for v in values)))
+  return _ld(2, _ld(1, struct.pack('<%df' % len(values), *[float(v) for v in values])))
+
+
+def encode_sequence_example(context, examples, feature_names=None):
+  """SequenceExample{context = 1, feature_lists = 2}: one feature list per example
+  feature, one frame per item (items that lack a feature get an empty Feature)."""
+  names = feature_names or sorted({k for e in examples for k in e})
+  lists = b''
+  for name in names:
+    frames = b''.join(_ld(1, _encode_feature(e[name]) if name in e else b'') for e in examples)
+    lists += _ld(1, _ld(1, name.encode()) + _ld(2, frames))
+  ctx_features = b''.join(_ld(1, _ld(1, k.encode()) + _ld(2, _encode_feature(v)))
+                          for k, v in (context or {}).items())
+  return _ld(1, ctx_features) + _ld(2, lists)
+
+
 def parse_from_example_list(serialized, list_size, context_feature_spec=None,
-                            example_feature_spec=None, pin_memory=False, num_threads=0):
+                            example_feature_spec=None, pin_memory=False, num_threads=0,
+                            data_format=EXAMPLE_LIST_WITH_CONTEXT):
   """data.py:391-540 for dense float / int64 features.  `serialized`: a sequence of
   serialized ELWC protos; the specs map feature name -> (dim, default_value), in the
   column order wanted.  Returns dict(context [B, Dc], examples [B, list_size, De],
   sizes [B] int32, mask [B, list_size] bool) of CPU tensors."""
   from ranking_b200 import _C
+  if data_format not in _FORMATS:
+    raise ValueError('Data format {} is not supported.'.format(data_format))
   records = [bytes(r) for r in serialized]
   b = len(records)
   carr, nc, dc, keep_c = _spec_array(context_feature_spec)
@@ -201,8 +267,8 @@ def parse_from_example_list(serialized, list_size, context_feature_spec=None,
   ex = alloc(b, list_size, de)
   sizes = torch.empty(b, dtype=torch.int32)
   mask = torch.empty(b, list_size, dtype=torch.uint8)
-  _C.check(_C.lib.tfr_elwc_parse(
-      ptrs, lens, b, int(list_size), carr, nc, earr, ne,
+  _C.check(_C.lib.tfr_ranking_parse(
+      _FORMATS[data_format], ptrs, lens, b, int(list_size), carr, nc, earr, ne,
       ctypes.c_void_p(ctx.data_ptr()) if dc else None,
       ctypes.c_void_p(ex.data_ptr()) if de else None,
       ctypes.c_void_p(sizes.data_ptr()), ctypes.c_void_p(mask.data_ptr()),

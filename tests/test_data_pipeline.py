@@ -233,3 +233,101 @@ def test_parser_reads_protobuf_runtime_output():
   assert list(back.context.features.feature['query_length'].int64_list.value) == [3]
   assert list(back.examples[0].features.feature['f'].float_list.value) == [1.0, 2.0, 3.0]
   assert list(back.examples[0].features.feature['unigrams'].bytes_list.value) == [b'x']
+
+
+def _protobuf_sequence_example():
+  from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+  fd = descriptor_pb2.FileDescriptorProto()
+  fd.name = 'tfr_b200_test_seq.proto'
+  fd.package = 'tfrseq'
+  fd.syntax = 'proto3'
+  T = descriptor_pb2.FieldDescriptorProto
+  R, O = T.LABEL_REPEATED, T.LABEL_OPTIONAL
+
+  def msg(name, fields, parent=None):
+    m = (parent.nested_type if parent is not None else fd.message_type).add()
+    m.name = name
+    for fname, num, typ, label, tname in fields:
+      f = m.field.add()
+      f.name, f.number, f.type, f.label = fname, num, typ, label
+      if tname:
+        f.type_name = '.tfrseq.' + tname
+    return m
+
+  msg('BytesList', [('value', 1, T.TYPE_BYTES, R, None)])
+  msg('FloatList', [('value', 1, T.TYPE_FLOAT, R, None)])
+  msg('Int64List', [('value', 1, T.TYPE_INT64, R, None)])
+  msg('Feature', [('bytes_list', 1, T.TYPE_MESSAGE, O, 'BytesList'),
+                  ('float_list', 2, T.TYPE_MESSAGE, O, 'FloatList'),
+                  ('int64_list', 3, T.TYPE_MESSAGE, O, 'Int64List')])
+  features = msg('Features', [('feature', 1, T.TYPE_MESSAGE, R, 'Features.FeatureEntry')])
+  e = msg('FeatureEntry', [('key', 1, T.TYPE_STRING, O, None),
+                           ('value', 2, T.TYPE_MESSAGE, O, 'Feature')], features)
+  e.options.map_entry = True
+  msg('FeatureList', [('feature', 1, T.TYPE_MESSAGE, R, 'Feature')])
+  fls = msg('FeatureLists', [('feature_list', 1, T.TYPE_MESSAGE, R,
+                              'FeatureLists.FeatureListEntry')])
+  e = msg('FeatureListEntry', [('key', 1, T.TYPE_STRING, O, None),
+                               ('value', 2, T.TYPE_MESSAGE, O, 'FeatureList')], fls)
+  e.options.map_entry = True
+  msg('SequenceExample', [('context', 1, T.TYPE_MESSAGE, O, 'Features'),
+                          ('feature_lists', 2, T.TYPE_MESSAGE, O, 'FeatureLists')])
+  msg('Example', [('features', 1, T.TYPE_MESSAGE, O, 'Features')])
+  pool = descriptor_pool.DescriptorPool()
+  pool.Add(fd)
+  get = lambda n: message_factory.GetMessageClass(pool.FindMessageTypeByName('tfrseq.' + n))
+  return get('SequenceExample'), get('Example')
+
+
+def test_example_in_example_and_sequence_example_formats():
+  """The three record formats of data.py:857-911 decode to the same tensors."""
+  pytest.importorskip('google.protobuf')
+  from ranking_b200 import data
+  context = {'qf': [0.5, 1.5], 'query_length': [3]}
+  examples = [{'utility': [0.0], 'f': [1.0, 2.0, 3.0]},
+              {'utility': [1.0], 'f': [4.0, 5.0, 6.0]},
+              {'utility': [2.0], 'f': [7.0, 8.0, 9.0]}]
+  spec_c = {'query_length': (1, 0.0), 'qf': (2, -7.0)}
+  spec_e = {'utility': (1, -1.0), 'f': (3, 0.25)}
+  want = data.parse_from_example_list([data.encode_elwc(context, examples)], 4, spec_c, spec_e)
+  for fmt, rec in ((data.EXAMPLE_IN_EXAMPLE, data.encode_example_in_example(context, examples)),
+                   (data.SEQUENCE_EXAMPLE, data.encode_sequence_example(context, examples))):
+    got = data.make_parsing_fn(fmt, 4, spec_c, spec_e)([rec])
+    for k in ('context', 'examples', 'sizes', 'mask'):
+      assert torch.equal(got[k], want[k]), (fmt, k)
+  with pytest.raises(ValueError):
+    data.make_parsing_fn('libsvm', 4, spec_c, spec_e)
+  # truncation + a shorter / missing feature list in a SequenceExample
+  rec = data.encode_sequence_example({}, [{'utility': [1.0], 'f': [1., 1., 1.]},
+                                          {'utility': [0.0]}, {'utility': [2.0]}],
+                                     feature_names=['utility', 'f'])
+  got = data.parse_from_sequence_example([rec], 2, None, spec_e)
+  assert got['sizes'].tolist() == [3]
+  np.testing.assert_array_equal(got['examples'][0].numpy(),
+                                [[1., 1., 1., 1.], [0., .25, .25, .25]])
+  # records produced by the protobuf runtime
+  SequenceExample, Example = _protobuf_sequence_example()
+  se = SequenceExample()
+  se.context.feature['qf'].float_list.value.extend([0.5, 1.5])
+  se.context.feature['query_length'].int64_list.value.append(3)
+  for ex in examples:
+    se.feature_lists.feature_list['utility'].feature.add().float_list.value.extend(ex['utility'])
+    se.feature_lists.feature_list['f'].feature.add().float_list.value.extend(ex['f'])
+  got = data.parse_from_sequence_example([se.SerializeToString()], 4, spec_c, spec_e)
+  for k in ('context', 'examples', 'sizes', 'mask'):
+    assert torch.equal(got[k], want[k]), k
+  outer = Example()
+  inner_c = Example()
+  inner_c.features.feature['qf'].float_list.value.extend([0.5, 1.5])
+  inner_c.features.feature['query_length'].int64_list.value.append(3)
+  outer.features.feature['serialized_context'].bytes_list.value.append(
+      inner_c.SerializeToString())
+  for ex in examples:
+    inner = Example()
+    inner.features.feature['utility'].float_list.value.extend(ex['utility'])
+    inner.features.feature['f'].float_list.value.extend(ex['f'])
+    outer.features.feature['serialized_examples'].bytes_list.value.append(
+        inner.SerializeToString())
+  got = data.parse_from_example_in_example([outer.SerializeToString()], 4, spec_c, spec_e)
+  for k in ('context', 'examples', 'sizes', 'mask'):
+    assert torch.equal(got[k], want[k]), k
