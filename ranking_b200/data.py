@@ -244,15 +244,17 @@ def encode_sequence_example(context, examples, feature_names=None):
 
 def parse_from_example_list(serialized, list_size, context_feature_spec=None,
                             example_feature_spec=None, pin_memory=False, num_threads=0,
-                            data_format=EXAMPLE_LIST_WITH_CONTEXT):
+                            data_format=EXAMPLE_LIST_WITH_CONTEXT, out=None):
   """data.py:391-540 for dense float / int64 features.  `serialized`: a sequence of
   serialized ELWC protos; the specs map feature name -> (dim, default_value), in the
   column order wanted.  Returns dict(context [B, Dc], examples [B, list_size, De],
-  sizes [B] int32, mask [B, list_size] bool) of CPU tensors."""
+  sizes [B] int32, mask [B, list_size] bool) of CPU tensors.  Pass a previous result as
+  `out` to decode into the same (e.g. pinned) buffers: fresh allocations are first touched
+  inside the decoder threads and the page faults serialise them."""
   from ranking_b200 import _C
   if data_format not in _FORMATS:
     raise ValueError('Data format {} is not supported.'.format(data_format))
-  records = [bytes(r) for r in serialized]
+  records = [r if isinstance(r, bytes) else bytes(r) for r in serialized]
   b = len(records)
   carr, nc, dc, keep_c = _spec_array(context_feature_spec)
   earr, ne, de, keep_e = _spec_array(example_feature_spec)
@@ -263,10 +265,15 @@ def parse_from_example_list(serialized, list_size, context_feature_spec=None,
     t = torch.empty(*shape, dtype=dtype)
     return t.pin_memory() if pin_memory and torch.cuda.is_available() else t
 
-  ctx = alloc(b, dc)
-  ex = alloc(b, list_size, de)
-  sizes = torch.empty(b, dtype=torch.int32)
-  mask = torch.empty(b, list_size, dtype=torch.uint8)
+  if out is not None and tuple(out['examples'].shape) == (b, list_size, de) and \
+      tuple(out['context'].shape) == (b, dc):
+    ctx, ex, sizes = out['context'], out['examples'], out['sizes']
+    mask = out['mask'].view(torch.uint8)
+  else:
+    ctx = alloc(b, dc)
+    ex = alloc(b, list_size, de)
+    sizes = torch.empty(b, dtype=torch.int32)
+    mask = torch.empty(b, list_size, dtype=torch.uint8)
   _C.check(_C.lib.tfr_ranking_parse(
       _FORMATS[data_format], ptrs, lens, b, int(list_size), carr, nc, earr, ne,
       ctypes.c_void_p(ctx.data_ptr()) if dc else None,
@@ -274,7 +281,7 @@ def parse_from_example_list(serialized, list_size, context_feature_spec=None,
       ctypes.c_void_p(sizes.data_ptr()), ctypes.c_void_p(mask.data_ptr()),
       int(num_threads)))
   del keep_c, keep_e
-  return {'context': ctx, 'examples': ex, 'sizes': sizes, 'mask': mask.bool()}
+  return {'context': ctx, 'examples': ex, 'sizes': sizes, 'mask': mask.view(torch.bool)}
 
 
 def elwc_batches(paths, batch_size, list_size, context_feature_spec, example_feature_spec,
