@@ -336,17 +336,57 @@ size_t tfr_mlp_bn_state_count(const tfr_mlp_cfg* cfg);
 /* bytes of caller-provided workspace that carries activations from fwd to bwd */
 size_t tfr_mlp_workspace_bytes(const tfr_mlp_cfg* cfg, int M);
 
-/* scores_out [M, dims[n_dense]]; if mask (uint8 [M]) is given and the output
+/* X [M, dims[0]] row-major: fp32 for TFR_PREC_FP32 / TF32X3 / TF32, bf16 (2-byte) for
+ * TFR_PREC_BF16 — in that mode hidden activations and backward signals are also bf16 in
+ * the workspace, parameters / gradients / scores stay fp32, layer widths must be
+ * multiples of 8 and BatchNormalization / Dropout are not offered.
+ * scores_out [M, dims[n_dense]]; if mask (uint8 [M]) is given and the output
  * width is 1, masked-out rows are set to ln(1e-10) (RestoreList). */
-int tfr_mlp_fwd(const float* X, int M, const tfr_mlp_cfg* cfg,
+int tfr_mlp_fwd(const void* X, int M, const tfr_mlp_cfg* cfg,
                 const float* params, const uint8_t* mask, void* workspace,
                 float* scores_out, int precision, void* stream);
 
 /* dscores [M, dims[n_dense]] -> grads (flat, same layout as params).
  * Must follow a tfr_mlp_fwd on the same X / workspace. */
-int tfr_mlp_bwd(const float* X, int M, const tfr_mlp_cfg* cfg,
+int tfr_mlp_bwd(const void* X, int M, const tfr_mlp_cfg* cfg,
                 const float* params, const float* dscores, const uint8_t* mask,
                 void* workspace, float* grads, int precision, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K8  groupwise scoring folded into the tower (tfr.model._GroupwiseRankingModel,
+ * model.py:273-421; group formation model.py:164-244 stays with the caller).
+ *   X      [B * N, D] fp32 item features (NOT gathered)
+ *   idx    [B, G, gs] int32: list positions of the members of every group; G = S * N
+ *          (S = num_shuffles blocks of N rolling-window groups)
+ *   gmask  [B, G] uint8: group validity (`indices_mask`)
+ *   cfg    the group score function as a tower over the concatenated member features:
+ *          dims[0] = gs * D, >= 1 hidden layer, output_units = gs
+ *          (examples/tf_ranking_libsvm.py:313-349); no BN / Dropout on this path
+ *   logits [B, N]: mean of the member scores every item received, 0 for items in no
+ *          valid group (scatter_nd + div_no_nan, model.py:388-412)
+ * The first Dense layer runs on the ungathered matrix (one GEMM per member slot) and the
+ * gather happens on its [B * N, h1] outputs, so the [B, G, gs, D] tensor of the reference
+ * is never formed.  precision: TFR_PREC_TF32X3 or TFR_PREC_TF32.
+ * Within one shuffle block an item may occupy a given slot in at most one valid group
+ * (true for rolling windows); tfr_group_mlp_check (host-synchronising) reports a
+ * violation seen by the last forward.
+ * ------------------------------------------------------------------------- */
+/* Group formation on the device (model.py:164-244): is_valid [B, N] uint8; perm NULL
+ * (no shuffle: the reference's PREDICT mode) or [num_shuffles, B, N] int32 permutations
+ * of the valid-first order (TF's shuffle stream is not reproducible, so the shuffle is an
+ * input); idx [B, num_shuffles * N, gs] int32, gmask [B, num_shuffles * N] uint8. */
+int tfr_group_indices(const uint8_t* is_valid, const int32_t* perm, int B, int N,
+                      int num_shuffles, int gs, int32_t* idx, uint8_t* gmask, void* stream);
+size_t tfr_group_mlp_workspace_bytes(const tfr_mlp_cfg* cfg, int B, int N, int G, int gs);
+int tfr_group_mlp_fwd(const float* X, int B, int N, int G, int gs, const int32_t* idx,
+                      const uint8_t* gmask, const tfr_mlp_cfg* cfg, const float* params,
+                      void* workspace, float* logits_out, int precision, void* stream);
+int tfr_group_mlp_bwd(const float* X, int B, int N, int G, int gs, const int32_t* idx,
+                      const uint8_t* gmask, const tfr_mlp_cfg* cfg, const float* params,
+                      const float* dlogits, void* workspace, float* grads, int precision,
+                      void* stream);
+int tfr_group_mlp_check(const tfr_mlp_cfg* cfg, int B, int N, int G, int gs,
+                        void* workspace, void* stream);
 
 /* Parity helper: one GEMM through the tcgen05 TF32 engine that the scorer tower
  * uses (D[GM,GN] = A[GM,GK] * B[GK,GN]).  a_mn/b_mn select the operand storage
@@ -361,6 +401,21 @@ int tfr_tc_gemm(const float* A, int lda, const float* B, int ldb, const float* B
                 const float* aux, int act, int store_transposed, int splits,
                 size_t split_stride, uint32_t* mask_bits_out,
                 const uint32_t* mask_bits_in, void* stream);
+
+/* Parity helper for the bf16 engine (tcgen05 kind::f16, csrc/tc_gemm_bf16.cuh):
+ * D[GM,GN] = A[GM,GK] * B[GK,GN] with bf16 operands and fp32 accumulation.
+ *   mn = 0: A stored [GM,GK], B stored [GN,GK]; C bf16 [GM,GN]; epi 0 store, 1 bias+act
+ *           (+ ReLU sign bits to mask_bits_out), 3 mask by mask_bits_in (+ fp32 column sums
+ *           of C per CTA and epilogue warp into colsum[slot * colsum_stride + col],
+ *           *colsum_slots_out slots);
+ *   mn = 1: A stored [GK,GM], B stored [GK,GN]; the GK range is cut into `splits` pieces,
+ *           piece z writes its fp32 partial to C + z * split_stride floats, with
+ *           split_stride = roundup(GM, 128) * ldc. */
+int tfr_tc_gemm_bf16(const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+                     int GM, int GN, int GK, int mn, int epi, const float* bias, int act,
+                     uint32_t* mask_bits_out, const uint32_t* mask_bits_in,
+                     float* colsum, int colsum_stride, int* colsum_slots_out,
+                     int splits, size_t split_stride, void* stream);
 
 /* Profiling aid for the engine above: device buffer [num_SMs][12] of int64 that each
  * GEMM launch fills with per-warp-role mbarrier wait cycles (NULL disables). */
@@ -421,6 +476,33 @@ uint32_t tfr_masked_crc32c(const uint8_t* data, size_t n);
 int tfr_optimizer_step(float* params, const float* grads, float* accum, size_t n,
                        int kind, float lr, float eps, float grad_scale,
                        void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K7  data-parallel step: all-reduce(SUM) of the flat gradient fused with the optimizer,
+ * over NVLink peer memory (one process per GPU on one node).  Replaces the reference's
+ * tf.distribute all-reduce + optimizer (keras/strategy_utils.py:45-116,
+ * extension/task.py:256-262).
+ *   tfr_dp_alloc   zero-filled device memory that peers may map + its 64-byte IPC handle
+ *   tfr_dp_open    map a peer's allocation from its handle (exchange the handles with any
+ *                  host-side channel, e.g. the process group)
+ *   tfr_allreduce_optimizer_step
+ *                  grad_ptrs / flag_ptrs: HOST arrays of `world` device pointers (own +
+ *                  peer mappings): this step's gradient slot and the flag pad (>= 16
+ *                  uint32, zero before the first step) of every rank.  `epoch` must grow by
+ *                  one per step on every rank; alternate between TWO gradient slots from
+ *                  step to step (the flag round of step e + 1 is what proves every peer
+ *                  finished reading slot e % 2).  Sums in rank order (bit-identical
+ *                  replicas), scales by grad_scale, applies kind 0 SGD / 1 Adagrad.
+ *                  summed_out (optional): the unscaled sum.
+ * ------------------------------------------------------------------------- */
+int tfr_dp_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out);
+int tfr_dp_open(const unsigned char* handle, void** ptr_out);
+int tfr_dp_close(void* peer_ptr);
+int tfr_dp_free(void* ptr);
+int tfr_allreduce_optimizer_step(const void* const* grad_ptrs, void* const* flag_ptrs,
+                                 int rank, int world, uint32_t epoch, float* params,
+                                 float* accum, float* summed_out, size_t n, int kind,
+                                 float lr, float eps, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

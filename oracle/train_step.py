@@ -15,9 +15,12 @@ class OracleTrainer(object):
   def __init__(self, input_dim, hidden_layer_dims, loss_key='approx_ndcg_loss',
                activation='relu', learning_rate=0.001, epsilon=1e-7,
                initial_accumulator_value=0.1, seed=1238, dtype=torch.float32,
-               loss_kwargs=None):
-    self.params = scorer.init_tower_params(input_dim, hidden_layer_dims, 1,
-                                           seed=seed, dtype=dtype)
+               loss_kwargs=None, group_size=1):
+    # group_size > 1: groupwise scoring (model.py:273-421), the tower is the group score
+    # function over the concatenated member features
+    self.group_size = group_size
+    self.params = scorer.init_tower_params(input_dim * group_size, hidden_layer_dims,
+                                           group_size, seed=seed, dtype=dtype)
     self.activation = activation
     self.loss = keras_losses.get(loss_key, **(loss_kwargs or {}))
     self.lr = learning_rate
@@ -30,6 +33,11 @@ class OracleTrainer(object):
 
   def forward(self, x, mask):
     b, n, d = x.shape
+    if self.group_size > 1:
+      gs = self.group_size
+      score_fn = lambda gf: scorer.tower_forward(   # noqa: E731
+          gf.reshape(gf.shape[0], gs * d), self.params, activation=self.activation)
+      return scorer.groupwise_logits(x, mask, gs, score_fn)
     flat = scorer.tower_forward(x.reshape(b * n, d), self.params,
                                 activation=self.activation)
     return scorer.restore_list(flat, mask)

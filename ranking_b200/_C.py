@@ -99,9 +99,24 @@ _SIGNATURES = {
     'tfr_mlp_workspace_bytes': (C.c_size_t, [C.POINTER(MlpCfg), _I]),
     'tfr_mlp_fwd': (_I, [_P, _I, C.POINTER(MlpCfg), _P, _P, _P, _P, _I, _P]),
     'tfr_mlp_bwd': (_I, [_P, _I, C.POINTER(MlpCfg), _P, _P, _P, _P, _P, _I, _P]),
+    'tfr_group_indices': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    'tfr_group_mlp_workspace_bytes': (C.c_size_t, [C.POINTER(MlpCfg), _I, _I, _I, _I]),
+    'tfr_group_mlp_fwd': (_I, [_P, _I, _I, _I, _I, _P, _P, C.POINTER(MlpCfg), _P, _P, _P, _I,
+                               _P]),
+    'tfr_group_mlp_bwd': (_I, [_P, _I, _I, _I, _I, _P, _P, C.POINTER(MlpCfg), _P, _P, _P, _P,
+                               _I, _P]),
+    'tfr_group_mlp_check': (_I, [C.POINTER(MlpCfg), _I, _I, _I, _I, _P, _P]),
     'tfr_tc_gemm': (_I, [_P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I,
                          _P, _P, _I, _I, _I, C.c_size_t, _P, _P, _P]),
+    'tfr_tc_gemm_bf16': (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P,
+                              _I, _P, _I, C.c_size_t, _P]),
     'tfr_tc_set_debug': (_I, [_P]),
+    'tfr_dp_alloc': (_I, [C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte * 64)]),
+    'tfr_dp_open': (_I, [C.POINTER(C.c_ubyte * 64), C.POINTER(C.c_void_p)]),
+    'tfr_dp_close': (_I, [_P]),
+    'tfr_dp_free': (_I, [_P]),
+    'tfr_allreduce_optimizer_step': (_I, [_P, _P, _I, _I, C.c_uint32, _P, _P, _P, C.c_size_t,
+                                          _I, _F, _F, _F, _P]),
     'tfr_optimizer_step': (_I, [_P, _P, _P, C.c_size_t, _I, _F, _F, _F, _P]),
 }
 

@@ -43,7 +43,8 @@ int make_mlp_plan(const tfr_mlp_cfg* cfg, int M, MlpPlan* p) {
     off += (size_t)p->dims[d] * p->dims[d + 1];
     p->b_off[d] = off;
     off += p->dims[d + 1];
-    const size_t wb = (size_t)p->dims[d] * p->dims[d + 1] + p->dims[d + 1];
+    // (rows rounded up to 128: the bf16 dW GEMM stores whole 128-row blocks per split)
+    const size_t wb = (size_t)((p->dims[d] + 127) / 128 * 128) * p->dims[d + 1] + p->dims[d + 1];
     if (wb > max_wb) max_wb = wb;
     if (d < L && p->dims[d + 1] > max_hidden) max_hidden = p->dims[d + 1];
   }
@@ -201,12 +202,13 @@ static float* ws_base(void* workspace) {
   return reinterpret_cast<float*>(a);
 }
 
-extern "C" int tfr_mlp_fwd(const float* X, int M, const tfr_mlp_cfg* cfg,
+extern "C" int tfr_mlp_fwd(const void* Xv, int M, const tfr_mlp_cfg* cfg,
                            const float* params, const uint8_t* mask, void* workspace,
                            float* scores_out, int precision, void* stream) {
   MlpPlan p;
   int rc = make_mlp_plan(cfg, M, &p);
   if (rc) return rc;
+  const float* X = static_cast<const float*>(Xv);   // bf16 when precision == TFR_PREC_BF16
   TFR_REQUIRE(X && params && workspace && scores_out, "NULL argument");
   TFR_REQUIRE(!(p.use_bn || p.input_bn) || p.bn_state, "cfg->bn_state must be set with BN");
   if (M == 0) return TFR_OK;
@@ -218,21 +220,28 @@ extern "C" int tfr_mlp_fwd(const float* X, int M, const tfr_mlp_cfg* cfg,
     case TFR_PREC_TF32:
       return mlp_tc_fwd(X, M, p, params, mask, ws_base(workspace), scores_out,
                         precision == TFR_PREC_TF32X3 ? 3 : 1, (cudaStream_t)stream);
+    case TFR_PREC_BF16:
+      return mlp_bf16_fwd(Xv, M, p, params, mask, ws_base(workspace), scores_out,
+                          (cudaStream_t)stream);
     default:
       set_error("precision %d is not available in this build", precision);
       return TFR_UNSUPPORTED;
   }
 }
 
-extern "C" int tfr_mlp_bwd(const float* X, int M, const tfr_mlp_cfg* cfg,
+extern "C" int tfr_mlp_bwd(const void* Xv, int M, const tfr_mlp_cfg* cfg,
                            const float* params, const float* dscores, const uint8_t* mask,
                            void* workspace, float* grads, int precision, void* stream) {
   MlpPlan p;
   int rc = make_mlp_plan(cfg, M, &p);
   if (rc) return rc;
+  const float* X = static_cast<const float*>(Xv);
   TFR_REQUIRE(X && params && workspace && dscores && grads, "NULL argument");
   TFR_REQUIRE(!(p.use_bn || p.input_bn) || p.bn_state, "cfg->bn_state must be set with BN");
-  if (M == 0) return TFR_OK;
+  if (M == 0) {   // an empty shard contributes a zero gradient (never stale memory)
+    TFR_CUDA_OK(cudaMemsetAsync(grads, 0, p.n_params * sizeof(float), (cudaStream_t)stream));
+    return TFR_OK;
+  }
   switch (precision) {
     case TFR_PREC_FP32:
       return mlp_simt_bwd(X, M, p, params, dscores, mask, ws_base(workspace), grads,
@@ -241,6 +250,9 @@ extern "C" int tfr_mlp_bwd(const float* X, int M, const tfr_mlp_cfg* cfg,
     case TFR_PREC_TF32:
       return mlp_tc_bwd(X, M, p, params, dscores, mask, ws_base(workspace), grads,
                         precision == TFR_PREC_TF32X3 ? 3 : 1, (cudaStream_t)stream);
+    case TFR_PREC_BF16:
+      return mlp_bf16_bwd(Xv, M, p, params, dscores, mask, ws_base(workspace), grads,
+                          (cudaStream_t)stream);
     default:
       set_error("precision %d is not available in this build", precision);
       return TFR_UNSUPPORTED;

@@ -75,6 +75,30 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
                const float* dscores, const uint8_t* mask, float* ws, float* grads,
                int passes, cudaStream_t st);
 
+// bf16 tensor-core path (tcgen05 kind::f16): X and all activations are bf16 in HBM
+int mlp_bf16_fwd(const void* X, int M, const MlpPlan& p, const float* params,
+                 const uint8_t* mask, float* ws, float* scores, cudaStream_t st);
+int mlp_bf16_bwd(const void* X, int M, const MlpPlan& p, const float* params,
+                 const float* dscores, const uint8_t* mask, float* ws, float* grads,
+                 cudaStream_t st);
+
+// partial walks of the tensor-core path (the groupwise fold supplies / consumes layer 0)
+struct MlpBwdTail {
+  float* dz;               // dL/dZ of Dense stop_layer - 1, [M, dims[stop_layer]]
+  float* dz_other;         // the other ping-pong buffer (free)
+  const float* bias_src;   // per-slot column sums of dz
+  int bias_slots;
+  size_t bias_stride;
+};
+int mlp_tc_split_params(const MlpPlan& p, const float* params, float* ws, int passes,
+                        cudaStream_t st);
+int mlp_tc_fwd_from(int first_layer, const float* X, int M, const MlpPlan& p,
+                    const float* params, const uint8_t* mask, float* ws, float* scores,
+                    int passes, cudaStream_t st);
+int mlp_tc_bwd_until(int stop_layer, MlpBwdTail* tail, const float* X, int M, const MlpPlan& p,
+                     const float* params, const float* dscores, const uint8_t* mask,
+                     float* ws, float* grads, int passes, cudaStream_t st);
+
 // pieces of the CUDA-core path reused by the tensor-core path
 int mlp_out_layer_fwd(const float* H, int M, int K, int O, const float* W, const float* bias,
                       const uint8_t* mask, float* scores, cudaStream_t st);

@@ -47,22 +47,39 @@ static int split_params(const MlpPlan& p, const float* params, float* ws, int pa
   return TFR_OK;
 }
 
-int mlp_tc_fwd(const float* X, int M, const MlpPlan& p, const float* params,
-               const uint8_t* mask, float* ws, float* scores, int passes, cudaStream_t st) {
+int mlp_tc_split_params(const MlpPlan& p, const float* params, float* ws, int passes,
+                        cudaStream_t st) {
   int rc = check_dims(p);
   if (rc) return rc;
-  rc = split_params(p, params, ws, passes, st);
+  return split_params(p, params, ws, passes, st);
+}
+
+int mlp_tc_fwd(const float* X, int M, const MlpPlan& p, const float* params,
+               const uint8_t* mask, float* ws, float* scores, int passes, cudaStream_t st) {
+  return mlp_tc_fwd_from(0, X, M, p, params, mask, ws, scores, passes, st);
+}
+
+// Layers first_layer .. L-1 and the output layer.  first_layer > 0: `X` is the activation
+// that feeds Dense `first_layer` (the caller produced it and already split the parameters).
+int mlp_tc_fwd_from(int first_layer, const float* X, int M, const MlpPlan& p,
+                    const float* params, const uint8_t* mask, float* ws, float* scores,
+                    int passes, cudaStream_t st) {
+  int rc = check_dims(p);
   if (rc) return rc;
+  if (first_layer == 0) {
+    rc = split_params(p, params, ws, passes, st);
+    if (rc) return rc;
+  }
   const int L = p.n_dense - 1;
   const float* whi = passes == 3 ? ws + p.whi_off : params;
   const float* wlo = passes == 3 ? ws + p.wlo_off : nullptr;
   const float* in = X;
-  if (p.input_bn) {
+  if (p.input_bn && first_layer == 0) {
     rc = mlp_input_bn_fwd(X, M, p, params, ws, st);
     if (rc) return rc;
     in = ws + p.xin_off;
   }
-  for (int d = 0; d < L; ++d) {
+  for (int d = first_layer; d < L; ++d) {
     tc::GemmDesc g{};
     g.A = in; g.lda = p.dims[d];
     g.B = whi + p.w_off[d]; g.ldb = p.dims[d + 1];
@@ -89,6 +106,15 @@ int mlp_tc_fwd(const float* X, int M, const MlpPlan& p, const float* params,
 int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
                const float* dscores, const uint8_t* mask, float* ws, float* grads,
                int passes, cudaStream_t st) {
+  return mlp_tc_bwd_until(0, nullptr, X, M, p, params, dscores, mask, ws, grads, passes, st);
+}
+
+// Backward of the output layer and of Dense L-1 .. stop_layer.  With stop_layer > 0 the
+// walk ends after producing dL/dZ of Dense stop_layer - 1 (activation mask applied, bias
+// column sums taken); `tail` then describes where that signal and its column sums live.
+int mlp_tc_bwd_until(int stop_layer, MlpBwdTail* tail, const float* X, int M, const MlpPlan& p,
+                     const float* params, const float* dscores, const uint8_t* mask,
+                     float* ws, float* grads, int passes, cudaStream_t st) {
   int rc = check_dims(p);
   if (rc) return rc;
   const int L = p.n_dense - 1;
@@ -125,7 +151,7 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
   const float* bsrc = oslots + (((size_t)p.dims[L] * p.dims[L + 1] + p.dims[L + 1] + 3) & ~(size_t)3);
   int bslots = p.out_slots;
   size_t bstride = p.oslot_stride;
-  for (int d = L - 1; d >= 0; --d) {
+  for (int d = L - 1; d >= stop_layer; --d) {
     const int Kin = p.dims[d], Nout = p.dims[d + 1];
     const float* A = d > 0 ? ws + p.act_off[d - 1] : X0;
     if (p.post()) {
@@ -197,6 +223,14 @@ int mlp_tc_bwd(const float* X, int M, const MlpPlan& p, const float* params,
       float* t = dz_cur; dz_cur = dz_nxt; dz_nxt = t;
     }
   }
+  if (tail) {
+    tail->dz = dz_cur;
+    tail->dz_other = dz_nxt;
+    tail->bias_src = bsrc;
+    tail->bias_slots = bslots;
+    tail->bias_stride = bstride;
+  }
+  if (stop_layer > 0) return TFR_OK;
   if (p.input_bn) return mlp_input_bn_bwd(X, M, p, params, ws, dz_cur, grads, st);
   return TFR_OK;
 }

@@ -377,8 +377,11 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const int nchunk = (args.n_umma + 31) >> 5;
         int my_last = -1;
+        // (128-row blocks past GM — the second block of the last pair — are not stored: the
+        // partial of a split is roundup(GM, 128) rows)
         for (int idx = half; idx < MT * nchunk; idx += 2)
-          if (n0 + (idx % nchunk) * 32 < args.GN) my_last = idx;
+          if (n0 + (idx % nchunk) * 32 < args.GN && m0 + (idx / nchunk) * BM < args.GM)
+            my_last = idx;
         if (my_last < 0) {
           tc_fence_before();
           mbar_arrive(&acc_empty[ab]);
@@ -387,7 +390,7 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
         for (int idx = half; idx <= my_last; idx += 2) {
           const int mt = idx / nchunk, c0 = (idx % nchunk) * 32;
-          if (n0 + c0 >= args.GN) continue;
+          if (n0 + c0 >= args.GN || m0 + mt * BM >= args.GM) continue;
           uint32_t v[32];
           tmem_ld32(tmem_d0 + mt * args.acc_cols + c0, v);
           tmem_ld_wait();

@@ -52,3 +52,128 @@ def shard_lists(num_lists, group=None):
                      (num_lists, w))
   per = num_lists // w
   return slice(r * per, (r + 1) * per)
+
+
+def bind_to_gpu_numa_node(device_index):
+  """Pins this process (and therefore the pinned host buffers it allocates afterwards:
+  first-touch) to the CPUs of the NUMA node the GPU hangs off.  With 8 ranks on a
+  two-socket box, unbound ranks push half of their H2D traffic across the socket link.
+  Returns {'node': k, 'cpus': n} or None when the topology cannot be read."""
+  import os
+  try:
+    props = torch.cuda.get_device_properties(device_index)
+    bdf = '%04x:%02x:%02x.0' % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+    with open('/sys/bus/pci/devices/%s/numa_node' % bdf) as f:
+      node = int(f.read().strip())
+    if node < 0:
+      return None
+    with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+      cpus = set()
+      for part in f.read().strip().split(','):
+        if '-' in part:
+          a, b = part.split('-')
+          cpus.update(range(int(a), int(b) + 1))
+        elif part:
+          cpus.add(int(part))
+    allowed = cpus & os.sched_getaffinity(0)
+    if not allowed:
+      return None
+    os.sched_setaffinity(0, allowed)
+    return {'node': node, 'cpus': len(allowed)}
+  except (OSError, AttributeError, ValueError):
+    return None
+
+
+class _DeviceArray(object):
+  """Zero-copy torch view of raw device memory (the `__cuda_array_interface__`)."""
+
+  def __init__(self, ptr, n, typestr):
+    self.__cuda_array_interface__ = {'shape': (n,), 'typestr': typestr,
+                                     'data': (ptr, False), 'version': 2}
+
+
+class FusedGradReducer(object):
+  """Peer-memory plumbing of the fused all-reduce + optimizer kernel (csrc/dp_fused.cu, K7).
+
+  Owns, per rank: two gradient slots of `n` floats and a flag pad in IPC-shareable device
+  memory; maps every peer's slots and pad (CUDA IPC handles exchanged once through the
+  process group: torch.distributed is plumbing, the collective itself is our kernel).
+  `grads(step)` is the torch view of this step's local slot — the scorer backward writes
+  straight into it — and `step(...)` launches the kernel.  One node, <= 16 ranks.
+  """
+
+  MAX_RANKS = 16
+
+  def __init__(self, n, device, group=None):
+    import ctypes
+    from ranking_b200 import _C
+    self._C = _C
+    self.group = group
+    self.world = world_size(group)
+    self.rank = rank(group)
+    if self.world > self.MAX_RANKS:
+      raise ValueError('fused all-reduce supports at most %d ranks' % self.MAX_RANKS)
+    self.n = int(n)
+    self.device = torch.device(device)
+    self.n_pad = (self.n + 63) // 64 * 64
+    slot_bytes = self.n_pad * 4
+    total = 2 * slot_bytes + 256           # two gradient slots + the flag pad
+    self._slot_bytes = slot_bytes
+    with torch.cuda.device(self.device):
+      ptr = ctypes.c_void_p()
+      handle = (ctypes.c_ubyte * 64)()
+      _C.check(_C.lib.tfr_dp_alloc(total, ctypes.byref(ptr), handle))
+      self._base = ptr.value
+      handles = [None] * self.world
+      if self.world > 1:
+        dist.all_gather_object(handles, bytes(handle), group=group)
+      else:
+        handles[0] = bytes(handle)
+      self._peer_base = []
+      for r in range(self.world):
+        if r == self.rank:
+          self._peer_base.append(self._base)
+        else:
+          p = ctypes.c_void_p()
+          hb = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+          _C.check(_C.lib.tfr_dp_open(hb, ctypes.byref(p)))
+          self._peer_base.append(p.value)
+    self._views = [
+        torch.as_tensor(_DeviceArray(self._base + s * slot_bytes, self.n, '<f4'),
+                        device=self.device) for s in range(2)]
+    ptr_arr = ctypes.c_void_p * self.world
+    self._grad_tabs = [ptr_arr(*[b + s * slot_bytes for b in self._peer_base])
+                       for s in range(2)]
+    self._flag_tab = ptr_arr(*[b + 2 * slot_bytes for b in self._peer_base])
+    self.epoch = 0
+    if self.world > 1:
+      dist.barrier(group=group)      # every mapping exists before the first flag is written
+
+  def grads(self, step=None):
+    """Local gradient slot of step `step` (default: the next step)."""
+    e = self.epoch + 1 if step is None else step
+    return self._views[e % 2]
+
+  def step(self, params, accum, kind, lr, eps, summed_out=None):
+    """All ranks: sum the gradient slots over NVLink peer loads, scale by 1 / world and
+    apply the optimizer — one kernel."""
+    _C = self._C
+    self.epoch += 1
+    _C.check(_C.lib.tfr_allreduce_optimizer_step(
+        self._grad_tabs[self.epoch % 2], self._flag_tab, self.rank, self.world,
+        self.epoch & 0xFFFFFFFF, _C.ptr(params), _C.ptr(accum), _C.ptr(summed_out), self.n,
+        kind, lr, eps, 1.0 / self.world, _C.stream()))
+
+  def close(self):
+    _C = self._C
+    if self._base is None:
+      return
+    torch.cuda.synchronize(self.device)
+    if self.world > 1:
+      dist.barrier(group=self.group)
+    for r, p in enumerate(self._peer_base):
+      if r != self.rank:
+        _C.lib.tfr_dp_close(p)
+    self._views = None
+    _C.lib.tfr_dp_free(self._base)
+    self._base = None

@@ -176,6 +176,8 @@ class Tower(torch.nn.Module):
       raise ValueError('precision must be one of %s' % sorted(_PRECISIONS))
     self.precision = precision
     self._precision = _PRECISIONS[precision]
+    # the bf16 mode reads its inputs (and keeps its activations) as bf16 in HBM
+    self.input_dtype = torch.bfloat16 if precision == 'bf16' else torch.float32
 
   def kernel(self, i):
     a, b, _ = self.offsets[i]
@@ -207,7 +209,7 @@ class Tower(torch.nn.Module):
                                                         x.shape[-1]))
     if x.requires_grad:
       raise NotImplementedError('gradients w.r.t. tower inputs are not computed')
-    x = x.reshape(-1, self.input_dim).float().contiguous()
+    x = x.reshape(-1, self.input_dim).to(self.input_dtype).contiguous()
     m8 = None if mask is None else mask.reshape(-1).to(torch.uint8).contiguous()
     out = _TowerFn.apply(x, self.flat, m8, self)
     return out.reshape(*lead, self.output_units)

@@ -12,8 +12,11 @@ mode in the reference shuffles the valid items with TF's RNG (model.py:316-322);
 that stream is not reproducible, so the permutation is an explicit, optional
 input (identity = the reference's PREDICT-mode behaviour, model_test.py:171-185).
 """
+import ctypes
+
 import torch
 
+from ranking_b200 import _C
 from ranking_b200 import utils as tfr_utils
 
 
@@ -40,6 +43,51 @@ def _form_group_indices(is_valid, group_size, permutation=None):
   return idx, mask
 
 
+class _GroupTowerFn(torch.autograd.Function):
+  """logits [B, N] = folded groupwise tower (tfr_group_mlp_fwd / bwd, csrc/mlp_group.cu)."""
+
+  @staticmethod
+  def forward(ctx, x, flat, idx, gmask, tower):
+    b, n, _ = x.shape
+    g, gs = idx.shape[1], idx.shape[2]
+    cfg = tower._run_cfg()
+    nbytes = _C.lib.tfr_group_mlp_workspace_bytes(ctypes.byref(cfg), b, n, g, gs)
+    if nbytes == 0:
+      raise ValueError(_C.last_error())
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    logits = torch.empty(b, n, dtype=torch.float32, device=x.device)
+    _C.check(_C.lib.tfr_group_mlp_fwd(_C.ptr(x), b, n, g, gs, _C.ptr(idx), _C.ptr(gmask),
+                                      ctypes.byref(cfg), _C.ptr(flat), _C.ptr(ws),
+                                      _C.ptr(logits), tower._precision, _C.stream()))
+    ctx.tower, ctx.cfg, ctx.ws = tower, cfg, ws
+    ctx.save_for_backward(x, flat, idx, gmask)
+    return logits
+
+  @staticmethod
+  def backward(ctx, g_out):
+    x, flat, idx, gmask = ctx.saved_tensors
+    b, n, _ = x.shape
+    g, gs = idx.shape[1], idx.shape[2]
+    grads = torch.empty_like(flat)
+    _C.check(_C.lib.tfr_group_mlp_bwd(_C.ptr(x), b, n, g, gs, _C.ptr(idx), _C.ptr(gmask),
+                                      ctypes.byref(ctx.cfg), _C.ptr(flat),
+                                      _C.ptr(g_out.contiguous()), _C.ptr(ctx.ws),
+                                      _C.ptr(grads), ctx.tower._precision, _C.stream()))
+    return None, grads, None, None, None
+
+
+def fold_supported(score_fn, group_size, d):
+  """The first-layer fold serves tower group score functions on the
+  tensor-core path with >= 1 hidden layer and no BN / Dropout."""
+  t = getattr(score_fn, 'tower', None)
+  return (t is not None and t.precision in ('tf32x3', 'tf32') and
+          len(t.hidden_layer_dims) >= 1 and not t.use_batch_norm and
+          not t.input_batch_norm and t.dropout == 0.0 and
+          t.input_dim == group_size * d and t.output_units == group_size and
+          d % 4 == 0 and t.hidden_layer_dims[0] % 4 == 0 and
+          all(h % 4 == 0 for h in t.hidden_layer_dims))
+
+
 class GroupwiseRankingModel(torch.nn.Module):
   """`group_score_fn`: module/callable [B*G, group_size, D] -> [B*G, group_size]."""
 
@@ -49,6 +97,7 @@ class GroupwiseRankingModel(torch.nn.Module):
       raise ValueError('Invalid group_size %d' % group_size)
     self._group_size = group_size
     self._score_fn = group_score_fn
+    self.fold = True   # False: always materialise the gathered features (reference plan)
 
   def compute_logits(self, example_features, is_valid, num_shuffles=1,
                      permutations=None):
@@ -65,6 +114,11 @@ class GroupwiseRankingModel(torch.nn.Module):
     idx = torch.cat(idx_list, 1)
     gmask = torch.cat(mask_list, 1)
     g = idx.shape[1]
+    if self.fold and fold_supported(self._score_fn, gs, d):
+      # K8: the gathered [B, G, gs, D] tensor is never formed (csrc/mlp_group.cu)
+      return _GroupTowerFn.apply(x.float().contiguous(), self._score_fn.tower.flat,
+                                 idx.to(torch.int32).contiguous(),
+                                 gmask.to(torch.uint8).contiguous(), self._score_fn.tower)
     gathered = torch.gather(x, 1, idx.reshape(b, g * gs, 1).expand(-1, -1, d))
     scores = self._score_fn(gathered.reshape(b * g, gs, d)).reshape(b, g, gs)
     smask = gmask.unsqueeze(2).expand(-1, -1, gs)

@@ -23,14 +23,23 @@ _OPT = {'sgd': 0, 'adagrad': 1}
 
 
 class RankingTrainer(object):
-  """Owns the static buffers of one training configuration [B, N, D]."""
+  """Owns the static buffers of one training configuration [B, N, D].
+
+  collective: how the data-parallel gradient sum is done when world_size > 1
+    'fused' (default on CUDA ranks of one node): the all-reduce is part of the optimizer
+            kernel — peer loads over NVLink, one flag round (csrc/dp_fused.cu, K7);
+    'nccl'  one ncclAllReduce of the flat gradient, then the optimizer kernel.
+  """
 
   def __init__(self, tower, loss, optimizer='adagrad', learning_rate=0.001,
-               epsilon=1e-7, initial_accumulator_value=0.1, process_group=None):
+               epsilon=1e-7, initial_accumulator_value=0.1, process_group=None,
+               collective='fused', keep_summed_grads=False):
     if optimizer not in _OPT:
       raise ValueError('optimizer must be one of %s' % sorted(_OPT))
     if not hasattr(loss, 'fused_fwd_bwd'):
       raise ValueError('loss must be a ranking_b200.keras.losses object')
+    if collective not in ('fused', 'nccl'):
+      raise ValueError("collective must be 'fused' or 'nccl'")
     self.tower = tower
     self.loss = loss
     self.opt_kind = _OPT[optimizer]
@@ -39,9 +48,16 @@ class RankingTrainer(object):
     dev = tower.flat.device
     self.device = dev
     self.accum = torch.full_like(tower.flat.data, initial_accumulator_value)
-    self.grads = torch.zeros_like(tower.flat.data)
     self.group = process_group
     self.world = dp.world_size(process_group)
+    self.reducer = None
+    if self.world > 1 and collective == 'fused':
+      self.reducer = dp.FusedGradReducer(tower.flat.numel(), dev, process_group)
+      self.grads = self.reducer.grads()
+      self.summed = torch.zeros_like(tower.flat.data) if keep_summed_grads else None
+    else:
+      self.grads = torch.zeros_like(tower.flat.data)
+      self.summed = None
     self._shape = None
     self.launches_per_step = None
 
@@ -55,50 +71,136 @@ class RankingTrainer(object):
     self.dscores = torch.empty(b, n, dtype=torch.float32, device=dev)
     self.per_list = torch.empty(2, b, dtype=torch.float32, device=dev)
     self.total2 = torch.zeros(2, dtype=torch.float32, device=dev)
-    self.ws = self.tower._new_workspace(m)
+    self.ws = self._new_workspace(b, n)
     self._shape = (b, n)
+
+  def _new_workspace(self, b, n):
+    return self.tower._new_workspace(b * n)
+
+  def _prep_x(self, x):
+    t = self.tower
+    if x.dtype != t.input_dtype or not x.is_contiguous():
+      x = x.to(t.input_dtype).contiguous()   # bf16 mode wants bf16 features in HBM
+    return x
+
+  # -- scorer forward / backward (overridden by the groupwise trainer) ----------
+  def _forward(self, x, y_true, m8, cfg, training):
+    b, n, _ = x.shape
+    t = self.tower
+    _C.check(_C.lib.tfr_mlp_fwd(_C.ptr(x), b * n, cfg, _C.ptr(t.flat.data),
+                                _C.ptr(m8), _C.ptr(self.ws), _C.ptr(self.scores),
+                                t._precision, _C.stream()))
+
+  def _backward(self, x, m8, cfg, grads):
+    b, n, _ = x.shape
+    t = self.tower
+    _C.check(_C.lib.tfr_mlp_bwd(_C.ptr(x), b * n, cfg, _C.ptr(t.flat.data),
+                                _C.ptr(self.dscores), _C.ptr(m8), _C.ptr(self.ws),
+                                _C.ptr(grads), t._precision, _C.stream()))
+
+  def _apply(self, grads):
+    """Gradient sum over the replicas + optimizer update."""
+    t = self.tower
+    if self.reducer is not None:
+      self.reducer.step(t.flat.data, self.accum, self.opt_kind, self.lr, self.eps,
+                        summed_out=self.summed)
+      return
+    dp.all_reduce_sum_(grads, self.group)   # 'nccl': the one collective of the step
+    _C.check(_C.lib.tfr_optimizer_step(
+        _C.ptr(t.flat.data), _C.ptr(grads), _C.ptr(self.accum), grads.numel(),
+        self.opt_kind, self.lr, self.eps, dp.replica_grad_scale(self.group), _C.stream()))
 
   # -- one step on device-resident inputs -------------------------------------
   def train_step(self, x, y_true, sample_weight=None, mask=None):
-    """x [B, N, D] fp32 (device), y_true [B, N] (label < 0 = padding).
-    Returns the scalar loss as a 0-d device tensor (no host sync)."""
+    """x [B, N, D] (device; fp32, or bf16 in the bf16 mode), y_true [B, N] (label < 0 =
+    padding).  Returns the scalar loss as a 0-d device tensor (no host sync)."""
     b, n, d = x.shape
     self._ensure(b, n)
-    t = self.tower
-    m = b * n
-    st = _C.stream()
-    run_cfg = t._run_cfg(training=True)
+    x = self._prep_x(x)
+    run_cfg = self.tower._run_cfg(training=True)
     cfg = ctypes.byref(run_cfg)
     m8 = None
     if mask is not None:
       m8 = mask.reshape(-1).to(torch.uint8).contiguous()
-    _C.check(_C.lib.tfr_mlp_fwd(_C.ptr(x), m, cfg, _C.ptr(t.flat.data),
-                                _C.ptr(m8), _C.ptr(self.ws), _C.ptr(self.scores),
-                                t._precision, st))
+    grads = self.reducer.grads() if self.reducer is not None else self.grads
+    self.grads = grads
+    self._forward(x, y_true, m8, cfg, True)
     self.loss.fused_fwd_bwd(y_true, self.scores, sample_weight, self.dscores,
                             self.per_list, self.total2)
-    _C.check(_C.lib.tfr_mlp_bwd(_C.ptr(x), m, cfg, _C.ptr(t.flat.data),
-                                _C.ptr(self.dscores), _C.ptr(m8), _C.ptr(self.ws),
-                                _C.ptr(self.grads), t._precision, st))
-    dp.all_reduce_sum_(self.grads, self.group)   # the one collective of the step
-    _C.check(_C.lib.tfr_optimizer_step(
-        _C.ptr(t.flat.data), _C.ptr(self.grads), _C.ptr(self.accum),
-        self.grads.numel(), self.opt_kind, self.lr, self.eps,
-        dp.replica_grad_scale(self.group), st))
+    self._backward(x, m8, cfg, grads)
+    self._apply(grads)
     return self.total2[0]
 
   # -- evaluation --------------------------------------------------------------
   @torch.no_grad()
-  def predict(self, x, mask=None):
+  def predict(self, x, mask=None, y_true=None):
     b, n, d = x.shape
     self._ensure(b, n)
-    t = self.tower
+    x = self._prep_x(x)
     m8 = None if mask is None else mask.reshape(-1).to(torch.uint8).contiguous()
-    _C.check(_C.lib.tfr_mlp_fwd(_C.ptr(x), b * n,
-                                ctypes.byref(t._run_cfg(training=False)),
-                                _C.ptr(t.flat.data), _C.ptr(m8), _C.ptr(self.ws),
-                                _C.ptr(self.scores), t._precision, _C.stream()))
+    cfg = ctypes.byref(self.tower._run_cfg(training=False))
+    self._forward(x, y_true, m8, cfg, False)
     return self.scores
+
+
+class GroupwiseRankingTrainer(RankingTrainer):
+  """Fused step for groupwise scoring (tfr.model._GroupwiseRankingModel, model.py:273-421):
+  `tower` is the group score function over the concatenated member features
+  (input_dim = group_size * D, output_units = group_size).  Group formation, the folded
+  first layer, the scatter-average and their backward run in csrc/mlp_group.cu; the
+  [B, G, group_size, D] gather of the reference is never formed.  Validity = label >= 0
+  (model.py `_infer_sizes`); `permutations` ([num_shuffles, B, N] int, optional) are the
+  shuffles of the valid-first order (identity = the reference's PREDICT mode)."""
+
+  def __init__(self, tower, loss, group_size, num_shuffles=1, **kw):
+    super().__init__(tower, loss, **kw)
+    if group_size <= 0:
+      raise ValueError('Invalid group_size %d' % group_size)
+    if tower.output_units != group_size or tower.input_dim % group_size:
+      raise ValueError('the group score tower needs input_dim = group_size * D and '
+                       'output_units = group_size')
+    self.group_size = int(group_size)
+    self.num_shuffles = int(num_shuffles)
+    self.permutations = None
+
+  def _new_workspace(self, b, n):
+    g = self.num_shuffles * n
+    nbytes = _C.lib.tfr_group_mlp_workspace_bytes(ctypes.byref(self.tower._cfg), b, n, g,
+                                                  self.group_size)
+    if nbytes == 0:
+      raise ValueError(_C.last_error())
+    dev = self.device
+    self.idx = torch.empty(b, g, self.group_size, dtype=torch.int32, device=dev)
+    self.gmask = torch.empty(b, g, dtype=torch.uint8, device=dev)
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+  def _forward(self, x, y_true, m8, cfg, training):
+    b, n, _ = x.shape
+    t = self.tower
+    if y_true is None:
+      valid = torch.ones(b, n, dtype=torch.uint8, device=self.device)
+    else:
+      valid = (y_true >= 0).to(torch.uint8).contiguous()
+    perm = self.permutations
+    if perm is not None:
+      perm = perm.to(torch.int32).contiguous()
+    g = self.num_shuffles * n
+    st = _C.stream()
+    _C.check(_C.lib.tfr_group_indices(_C.ptr(valid), _C.ptr(perm), b, n, self.num_shuffles,
+                                      self.group_size, _C.ptr(self.idx), _C.ptr(self.gmask),
+                                      st))
+    _C.check(_C.lib.tfr_group_mlp_fwd(_C.ptr(x), b, n, g, self.group_size, _C.ptr(self.idx),
+                                      _C.ptr(self.gmask), cfg, _C.ptr(t.flat.data),
+                                      _C.ptr(self.ws), _C.ptr(self.scores), t._precision, st))
+
+  def _backward(self, x, m8, cfg, grads):
+    b, n, _ = x.shape
+    t = self.tower
+    g = self.num_shuffles * n
+    _C.check(_C.lib.tfr_group_mlp_bwd(_C.ptr(x), b, n, g, self.group_size, _C.ptr(self.idx),
+                                      _C.ptr(self.gmask), cfg, _C.ptr(t.flat.data),
+                                      _C.ptr(self.dscores), _C.ptr(self.ws), _C.ptr(grads),
+                                      t._precision, _C.stream()))
 
 
 class HostBatchPipeline(object):
@@ -110,13 +212,14 @@ class HostBatchPipeline(object):
     self.trainer = trainer
     dev = trainer.device
     self.copy_stream = torch.cuda.Stream(device=dev)
-    self.x = [torch.empty(b, n, d, dtype=torch.float32, device=dev)
-              for _ in range(2)]
+    xdt = trainer.tower.input_dtype    # bf16 mode: features travel and live as bf16
+    self.x = [torch.empty(b, n, d, dtype=xdt, device=dev) for _ in range(2)]
     self.y = [torch.empty(b, n, dtype=torch.float32, device=dev) for _ in range(2)]
     self.ready = [torch.cuda.Event() for _ in range(2)]
     self.free = [torch.cuda.Event() for _ in range(2)]
+    self.done = [torch.cuda.Event() for _ in range(2)]
     self.loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
-    self.h2d_bytes = (b * n * d + b * n) * 4
+    self.h2d_bytes = b * n * d * self.x[0].element_size() + b * n * 4
     self.d2h_bytes = 4
     self._slot = 0
     self._primed = False
@@ -128,9 +231,11 @@ class HostBatchPipeline(object):
       self.y[slot].copy_(y_host, non_blocking=True)
       self.ready[slot].record(self.copy_stream)
 
-  def run(self, host_batches):
+  def run(self, host_batches, sample_weight=None):
     """host_batches: sequence of (x_pinned [B,N,D], y_pinned [B,N]).  Returns the
-    list of per-step losses (python floats)."""
+    list of per-step losses (python floats).  The loss of step k is copied to its
+    pinned slot right after the step and READ one step late (after step k + 1 has been
+    queued), so the host never drains the GPU between steps."""
     tr = self.trainer
     cur = torch.cuda.current_stream()
     losses = []
@@ -142,16 +247,22 @@ class HostBatchPipeline(object):
       self.free[s].record(cur)
     slot = 0
     self._upload(slot, *nxt)
+    pending = None                   # (slot, event) of the step whose loss is in flight
     while nxt is not None:
       upcoming = next(it, None)
       if upcoming is not None:
         self._upload(slot ^ 1, *upcoming)
       cur.wait_event(self.ready[slot])
-      loss = tr.train_step(self.x[slot], self.y[slot])
+      loss = tr.train_step(self.x[slot], self.y[slot], sample_weight)
       self.free[slot].record(cur)
       self.loss_host[slot].copy_(loss, non_blocking=True)
-      cur.synchronize()          # the step's result is read on the host
-      losses.append(float(self.loss_host[slot]))
+      self.done[slot].record(cur)
+      if pending is not None:
+        pending[1].synchronize()
+        losses.append(float(self.loss_host[pending[0]]))
+      pending = (slot, self.done[slot])
       nxt = upcoming
       slot ^= 1
+    pending[1].synchronize()
+    losses.append(float(self.loss_host[pending[0]]))
     return losses

@@ -152,3 +152,203 @@ def test_k1_sort_order_equals_counting_ranks(cuda_api, oracle_api):
       _C.ptr(grad), None, _C.ptr(loss), None, None, _C.ptr(ranks), _C.stream()))
   ref = oracle_api.losses_impl._compute_ranks(scores.double(), labels >= 0)
   assert torch.equal(ranks.cpu().long(), ref)
+
+
+# ----------------------------------------------------------------------------
+# bf16 scorer tower (TFR_PREC_BF16, BASELINE config 3)
+# ----------------------------------------------------------------------------
+def _bf(t):
+  return t.bfloat16().double()
+
+
+def _emulated_bf16_tower(x, ws, bs, dscores, relu=True):
+  """fp64 restatement of the bf16 tower's arithmetic: bf16 inputs / weights / stored
+  activations and backward signals, exact accumulation.  Returns scores, flat grads."""
+  L = len(ws) - 1
+  h = [_bf(x)]
+  for d in range(L):
+    z = h[-1] @ _bf(ws[d]) + bs[d].double()
+    a = torch.relu(z) if relu else z
+    h.append(_bf(a))
+  scores = h[-1] @ ws[L].double() + bs[L].double()
+  grads_w, grads_b = [None] * (L + 1), [None] * (L + 1)
+  ds = dscores.double()
+  grads_w[L] = h[-1].t() @ ds
+  grads_b[L] = ds.sum(0)
+  dz_full = ds @ ws[L].double().t()
+  if relu:
+    dz_full = dz_full * (h[-1] > 0)
+  for d in range(L - 1, -1, -1):
+    grads_b[d] = dz_full.sum(0)            # column sums are taken before the bf16 rounding
+    dz = _bf(dz_full)
+    grads_w[d] = h[d].t() @ dz
+    if d > 0:
+      dz_full = dz @ _bf(ws[d]).t()
+      if relu:
+        dz_full = dz_full * (h[d] > 0)
+  flat = torch.cat([torch.cat([w.reshape(-1), b.reshape(-1)])
+                    for w, b in zip(grads_w, grads_b)])
+  return scores, flat
+
+
+@pytest.mark.parametrize('shape', [
+    (300, 16, [32, 16], 1),            # small, partial tiles
+    (1000, 136, [256, 128, 64], 1),    # config-2 widths
+    (4096, 256, [256, 128, 64], 1),    # config-3 widths
+    (2000, 64, [128], 2),              # two outputs
+    (700, 40, [], 1),                  # a single Dense layer: no tensor-core GEMM at all
+])
+@pytest.mark.parametrize('relu', [True, False])
+def test_tower_bf16_matches_emulation(shape, relu):
+  """bf16 tower forward + backward vs the fp64 emulation of the same roundings.
+  Tolerance: 5e-3 of the largest entry (the CUDA path accumulates in fp32: a stored
+  activation that sits on a bf16 rounding boundary may round the other way, and a
+  pre-activation within fp32 rounding of 0 may flip its ReLU mask bit; measured 1e-7 ..
+  2e-3)."""
+  import ranking_b200 as tfr
+  m, d, hidden, out = shape
+  g = torch.Generator().manual_seed(m + d)
+  x = torch.randn(m, d, generator=g)
+  tower = tfr.keras.layers.create_tower(hidden, out, activation='relu' if relu else None,
+                                        use_batch_norm=False, dropout=0, input_dim=d,
+                                        precision='bf16', seed=5)
+  with torch.no_grad():
+    for i in range(len(tower.dims) - 1):
+      tower.bias(i).uniform_(-0.2, 0.2)
+  mask = torch.rand(m, generator=g) > 0.1
+  dscores = torch.randn(m, out, generator=g)
+  ws = [tower.kernel(i).detach().cpu() for i in range(len(tower.dims) - 1)]
+  bs = [tower.bias(i).detach().cpu() for i in range(len(tower.dims) - 1)]
+  use_mask = out == 1
+  y = tower(x.cuda(), mask=mask.cuda() if use_mask else None)
+  y.backward(dscores.cuda())
+  ds_eff = dscores * mask.reshape(-1, 1).float() if use_mask else dscores
+  ref_scores, ref_grad = _emulated_bf16_tower(x, ws, bs, ds_eff, relu)
+  got = y.detach().double().cpu()
+  if use_mask:
+    assert float(got[~mask].max()) == pytest.approx(math.log(1e-10), rel=1e-6)
+    got, ref_scores = got[mask], ref_scores[mask]
+  e_s = float((got - ref_scores).abs().max() / ref_scores.abs().max())
+  e_g = float((tower.flat.grad.double().cpu() - ref_grad).abs().max() / ref_grad.abs().max())
+  print('bf16 tower', shape, relu, 'scores %.2e grads %.2e' % (e_s, e_g))
+  assert e_s <= 5e-3, e_s
+  assert e_g <= 5e-3, e_g
+
+
+def test_tower_bf16_vs_fp32_oracle(oracle_api):
+  """Stated bf16 tolerance against the fp64 ORACLE (no rounding emulation): scores within
+  2e-2 and parameter gradients within 6e-2 of the largest entry at config-3 widths
+  (measured 5e-3 / 3e-2: three layers of bf16 products, bf16 backward signals)."""
+  import ranking_b200 as tfr
+  m, d, hidden = 2048, 256, [256, 128, 64]
+  g = torch.Generator().manual_seed(9)
+  x = torch.randn(m, d, generator=g)
+  tower = tfr.keras.layers.create_tower(hidden, 1, activation='relu', use_batch_norm=False,
+                                        dropout=0, input_dim=d, precision='bf16', seed=6)
+  dscores = torch.randn(m, 1, generator=g)
+  y = tower(x.cuda())
+  y.backward(dscores.cuda())
+  params = {'dense_w': [tower.kernel(i).detach().cpu().double().requires_grad_()
+                        for i in range(4)],
+            'dense_b': [tower.bias(i).detach().cpu().double().requires_grad_()
+                        for i in range(4)]}
+  ref = oracle_api.scorer.tower_forward(x.double(), params, activation='relu')
+  ref.backward(dscores.double())
+  ref_grad = torch.cat([torch.cat([w.grad.reshape(-1), b.grad.reshape(-1)])
+                        for w, b in zip(params['dense_w'], params['dense_b'])])
+  e_s = float((y.detach().double().cpu() - ref.detach()).abs().max() / ref.abs().max())
+  e_g = float((tower.flat.grad.double().cpu() - ref_grad).abs().max() / ref_grad.abs().max())
+  print('bf16 vs fp64 oracle: scores %.2e grads %.2e' % (e_s, e_g))
+  assert e_s <= 2e-2, e_s
+  assert e_g <= 6e-2, e_g
+
+
+# ----------------------------------------------------------------------------
+# K8: groupwise scoring folded into the tower (BASELINE config 4)
+# ----------------------------------------------------------------------------
+def _group_case(b, n, d, gs, hidden, seed, precision='tf32x3'):
+  import ranking_b200 as tfr
+  g = torch.Generator().manual_seed(seed)
+  x = torch.randn(b, n, d, generator=g)
+  labels = torch.randint(0, 3, (b, n), generator=g).float()
+  lens = torch.randint(1, n + 1, (b,), generator=g)
+  labels = torch.where(torch.arange(n).unsqueeze(0) < lens.unsqueeze(1), labels,
+                       torch.full_like(labels, -1.))
+  labels[0, 1:] = -1.          # a single valid item: the window wraps onto itself
+  tower = tfr.keras.layers.create_tower(hidden, gs, activation='relu', use_batch_norm=False,
+                                        dropout=0, input_dim=gs * d, precision=precision,
+                                        seed=seed)
+  with torch.no_grad():
+    for i in range(len(tower.dims) - 1):
+      tower.bias(i).uniform_(-0.2, 0.2)
+  nl = len(tower.dims) - 1
+  params = {'dense_w': [tower.kernel(i).detach().cpu().double().clone().requires_grad_()
+                        for i in range(nl)],
+            'dense_b': [tower.bias(i).detach().cpu().double().clone().requires_grad_()
+                        for i in range(nl)]}
+  return tfr, x, labels, tower, params
+
+
+def _flat_grad(params):
+  return torch.cat([torch.cat([w.grad.reshape(-1), b.grad.reshape(-1)])
+                    for w, b in zip(params['dense_w'], params['dense_b'])])
+
+
+@pytest.mark.parametrize('shape', [(6, 9, 8, 2, [16, 8]), (5, 33, 16, 2, [32]),
+                                   (4, 40, 12, 3, [32, 16]), (16, 128, 512, 2, [256, 128, 64])])
+@pytest.mark.parametrize('shuffles', [1, 2])
+def test_groupwise_fold_matches_oracle(oracle_api, shape, shuffles):
+  """Folded first layer (csrc/mlp_group.cu) vs the oracle restatement of model.py:164-421:
+  logits, softmax loss, parameter gradients.  The last shape is a 16-list chunk of BASELINE
+  config 4 (N=128, D=512, group_size 2, 256-128-64).  Tolerances: logits / loss 1e-5,
+  gradients 5e-5 of the largest entry (3xTF32)."""
+  b, n, d, gs, hidden = shape
+  tfr, x, labels, tower, params = _group_case(b, n, d, gs, hidden, seed=b + n + d)
+  valid = labels >= 0
+  model = tfr.model.GroupwiseRankingModel(tfr.model.TowerGroupScoreFn(tower), gs)
+  assert tfr.model.fold_supported(model._score_fn, gs, d)
+  logits = model.compute_logits(x.cuda(), valid.cuda(), num_shuffles=shuffles)
+  loss = tfr.keras.losses.SoftmaxLoss()(labels.cuda(), logits)
+  loss.backward()
+
+  def score_fn(gf):
+    return oracle_api.scorer.tower_forward(gf.reshape(gf.shape[0], gs * d), params,
+                                           activation='relu')
+  ref_logits = oracle_api.scorer.groupwise_logits(x.double(), valid, gs, score_fn,
+                                                  num_shuffles=shuffles)
+  ref_loss = oracle_api.keras_losses.SoftmaxLoss()(labels.double(), ref_logits)
+  ref_loss.backward()
+  scale = float(ref_logits.abs().max())
+  assert float((logits.detach().double().cpu() - ref_logits).abs().max()) <= RTOL * scale
+  assert abs(float(loss.detach()) - float(ref_loss.detach())) <= RTOL * max(1., abs(float(ref_loss)))
+  gref = _flat_grad(params)
+  err = float((tower.flat.grad.double().cpu() - gref).abs().max() / gref.abs().max())
+  assert err <= 5e-5, err
+  # and the unfolded product path (gather materialised) agrees with the fold
+  tower.flat.grad = None
+  model.fold = False
+  logits2 = model.compute_logits(x.cuda(), valid.cuda(), num_shuffles=shuffles)
+  assert float((logits2 - logits).abs().max()) <= RTOL * scale
+
+
+def test_groupwise_fold_with_permutation(oracle_api):
+  """Caller-supplied shuffles of the valid items (the reference shuffles with TF's RNG)."""
+  b, n, d, gs = 5, 21, 8, 2
+  tfr, x, labels, tower, params = _group_case(b, n, d, gs, [16], seed=3)
+  valid = labels >= 0
+  g = torch.Generator().manual_seed(1)
+  perms = []
+  for _ in range(2):   # permute the valid-first order among the valid prefix only
+    nv = valid.sum(1)
+    perm = torch.arange(n).repeat(b, 1)
+    for r in range(b):
+      k = int(nv[r])
+      perm[r, :k] = torch.randperm(k, generator=g)
+    perms.append(perm)
+  model = tfr.model.GroupwiseRankingModel(tfr.model.TowerGroupScoreFn(tower), gs)
+  fold = model.compute_logits(x.cuda(), valid.cuda(), num_shuffles=2,
+                              permutations=[p.cuda() for p in perms])
+  model.fold = False
+  plain = model.compute_logits(x.cuda(), valid.cuda(), num_shuffles=2,
+                               permutations=[p.cuda() for p in perms])
+  assert float((fold - plain).abs().max()) <= RTOL * float(plain.abs().max())

@@ -6,11 +6,14 @@ import torch
 import ranking_b200 as tfr
 import bench
 
-B, N = 1024, 200
+B = int(os.environ.get('B', 1024))
+N = int(os.environ.get('N', 200))
 _, y = bench.make_batch(0, B, N, 8)
 y = y.cuda()
 scores = torch.randn(B, N, device='cuda')
-loss = tfr.keras.losses.get(sys.argv[1] if len(sys.argv) > 1 else 'approx_ndcg_loss')
+key = sys.argv[1] if len(sys.argv) > 1 else 'approx_ndcg_loss'
+lam = tfr.keras.losses.NDCGLambdaWeight() if len(sys.argv) > 2 and sys.argv[2] == 'ndcg' else None
+loss = tfr.keras.losses.get(key, lambda_weight=lam) if lam is not None else tfr.keras.losses.get(key)
 grad = torch.empty_like(scores)
 per_list = torch.empty(2, B, device='cuda')
 total2 = torch.zeros(2, device='cuda')
