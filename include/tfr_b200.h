@@ -371,6 +371,15 @@ int tfr_mlp_bwd(const void* X, int M, const tfr_mlp_cfg* cfg,
  * (true for rolling windows); tfr_group_mlp_check (host-synchronising) reports a
  * violation seen by the last forward.
  * ------------------------------------------------------------------------- */
+/* K9  FlattenList's circular padding (keras/layers.py:163-173, utils.py:272-356): out[b, p]
+ * = x[b, organized[p mod nv]] where organized lists the valid positions of list b in order
+ * (then the invalid ones) and nv is their count — every slot of the flattened batch holds a
+ * copy of a VALID row, which is what BatchNormalization statistics see in the reference.
+ * x / out [B, N, row_bytes] (row_bytes % 16 == 0), is_valid [B, N] uint8, idx_out [B, N]
+ * int32 (the gather indices, = utils.padded_nd_indices). */
+int tfr_circular_pad_gather(const void* x, const uint8_t* is_valid, int B, int N,
+                            int row_bytes, int32_t* idx_out, void* out, void* stream);
+
 /* Group formation on the device (model.py:164-244): is_valid [B, N] uint8; perm NULL
  * (no shuffle: the reference's PREDICT mode) or [num_shuffles, B, N] int32 permutations
  * of the valid-first order (TF's shuffle stream is not reproducible, so the shuffle is an

@@ -99,6 +99,7 @@ _SIGNATURES = {
     'tfr_mlp_workspace_bytes': (C.c_size_t, [C.POINTER(MlpCfg), _I]),
     'tfr_mlp_fwd': (_I, [_P, _I, C.POINTER(MlpCfg), _P, _P, _P, _P, _I, _P]),
     'tfr_mlp_bwd': (_I, [_P, _I, C.POINTER(MlpCfg), _P, _P, _P, _P, _P, _I, _P]),
+    'tfr_circular_pad_gather': (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     'tfr_group_indices': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),
     'tfr_group_mlp_workspace_bytes': (C.c_size_t, [C.POINTER(MlpCfg), _I, _I, _I, _I]),
     'tfr_group_mlp_fwd': (_I, [_P, _I, _I, _I, _I, _P, _P, C.POINTER(MlpCfg), _P, _P, _P, _I,

@@ -223,6 +223,22 @@ group_indices_kernel(const uint8_t* __restrict__ is_valid, const int32_t* __rest
     gmask[(size_t)b * S * N + sg] = (sg % N) < nv;
 }
 
+// K9: out[b, p, :] = in[b, idx[b, p], :] (16-byte vectors): FlattenList's circular padding
+// (keras/layers.py:163-173, utils.py:272-356) with idx from group_indices_kernel
+// (group_size 1: idx[b, p] = organized[p mod nv]).
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const uint4* __restrict__ in, const int32_t* __restrict__ idx, int N,
+                   int row_vecs, size_t total_vecs, uint4* __restrict__ out) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total_vecs;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = t / row_vecs;
+    const int v = (int)(t % row_vecs);
+    const size_t b = row / N;
+    const int src = idx[row];
+    out[t] = __ldg(in + (b * N + src) * row_vecs + v);
+  }
+}
+
 struct GroupWs {
   float* P;        // [gs][B * N, h1]  first-layer partial products / dP_j
   size_t p_stride;
@@ -291,6 +307,33 @@ extern "C" int tfr_group_indices(const uint8_t* is_valid, const int32_t* perm, i
   if (B == 0) return TFR_OK;
   group_indices_kernel<<<B, 256, (N + 16) * sizeof(int), (cudaStream_t)stream>>>(
       is_valid, perm, N, num_shuffles, gs, idx, gmask);
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
+extern "C" int tfr_circular_pad_gather(const void* x, const uint8_t* is_valid, int B, int N,
+                                       int row_bytes, int32_t* idx_out, void* out,
+                                       void* stream) {
+  TFR_REQUIRE(x && is_valid && idx_out && out, "NULL argument");
+  TFR_REQUIRE(B >= 0 && N >= 1 && N <= 8192, "circular padding: bad sizes (B=%d N=%d)", B, N);
+  TFR_REQUIRE(row_bytes > 0 && row_bytes % 16 == 0,
+              "circular padding: rows must be multiples of 16 bytes (got %d)", row_bytes);
+  TFR_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out) & 15) == 0, "circular padding: alignment");
+  if (B == 0) return TFR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  // idx[b, p] = organized[p mod max(nv, 1)]: group formation with group_size 1; the group
+  // mask lands in the tail of idx_out's buffer? no: it is not needed, write it to `out`
+  // first (it is overwritten by the gather below)
+  group_indices_kernel<<<B, 256, (N + 16) * sizeof(int), st>>>(
+      is_valid, nullptr, N, 1, 1, idx_out, static_cast<uint8_t*>(out));
+  TFR_LAUNCH_OK();
+  const int row_vecs = row_bytes / 16;
+  const size_t total = (size_t)B * N * row_vecs;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gather_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const uint4*>(x), idx_out, N,
+                                                      row_vecs, total, static_cast<uint4*>(out));
   TFR_LAUNCH_OK();
   return TFR_OK;
 }

@@ -54,6 +54,30 @@ def shard_lists(num_lists, group=None):
   return slice(r * per, (r + 1) * per)
 
 
+def cross_replica_list_weights(raw, kind, group=None):
+  """Per-list metric weights with the batch-average rule of
+  `_per_example_weights_to_per_list_weights` (metrics_impl.py:63-119) taken over the
+  GLOBAL batch: lists without relevant items get the average weight of ALL replicas'
+  lists, as a single device stepping the concatenated batch would compute it.  (Under
+  tf.distribute the reference evaluates the rule per replica — that is what the metric
+  kernel's own finalise pass does; this is the opt-in single-device-equivalent form.)
+
+  raw [B, 5] = {sum w, sum w*gain, sum gain, sum w*rel, sum rel} per list, as written by
+  tfr_rank_metrics; kind 'ndcg' uses the gain columns, 'mrr' the relevance columns.
+  Costs one 2-float all-reduce."""
+  m = 0 if kind == 'ndcg' else 1
+  sum_w, wr, r = raw[:, 0], raw[:, 1 + 2 * m], raw[:, 2 + 2 * m]
+  per = torch.where(r != 0, wr / torch.where(r != 0, r, torch.ones_like(r)),
+                    torch.zeros_like(r))
+  nz = (sum_w > 0) & (r > 0)
+  stats = torch.stack([per.sum(), nz.to(per.dtype).sum()])
+  all_reduce_sum_(stats, group)
+  avg = torch.where(stats[1] > 0, stats[0] / torch.clamp(stats[1], min=1.0),
+                    torch.ones_like(stats[0]))
+  return torch.where(sum_w > 0, torch.where(r > 0, per, avg.expand_as(per)),
+                     torch.zeros_like(per))
+
+
 def bind_to_gpu_numa_node(device_index):
   """Pins this process (and therefore the pinned host buffers it allocates afterwards:
   first-touch) to the CPUs of the NUMA node the GPU hangs off.  With 8 ranks on a

@@ -256,7 +256,14 @@ class MetricGroup(object):
   """
 
   def __init__(self, topns=(1, 3, 5, 10, None), gain_fn=None,
-               rank_discount_fn=None, ext=()):
+               rank_discount_fn=None, ext=(), cross_replica_weights=False,
+               process_group=None):
+    # cross_replica_weights: take the batch-average list weight of lists without relevant
+    # items (metrics_impl.py:101-113) over ALL replicas' batches (one 2-float all-reduce
+    # per update) instead of per replica: data-parallel evaluation then equals a single
+    # device on the concatenated batch.
+    self._cross = bool(cross_replica_weights)
+    self._group = process_group
     self.topns = tuple(topns)
     self._gain_fn = gain_fn
     self._rank_discount_fn = rank_discount_fn
@@ -278,6 +285,9 @@ class MetricGroup(object):
     o = metrics_impl.rank_metrics(y_true, y_pred, sample_weight, None,
                                   self.topns, self._gain_fn,
                                   self._rank_discount_fn, ext=self._ext)
+    if self._cross:
+      o['ndcg_w'] = dp.cross_replica_list_weights(o['raw'], 'ndcg', self._group)
+      o['mrr_w'] = dp.cross_replica_list_weights(o['raw'], 'mrr', self._group)
     if self._ext:
       parts = []
       for key in self._ext:
@@ -297,14 +307,28 @@ class MetricGroup(object):
         o['ndcg_w'].sum().reshape(1), o['mrr_w'].sum().reshape(1)])
     self._state = upd if self._state is None else self._state + upd
 
+  def _zero_state(self, device=None):
+    """A rank that saw no batch still has a state of the right width (all zeros), so that
+    every rank enters the same collectives and `result()` works on an empty evaluation."""
+    t = len(self.topns)
+    if device is None:
+      device = torch.device('cuda', torch.cuda.current_device()) if \
+          torch.cuda.is_available() else torch.device('cpu')
+    if self._state is None:
+      self._state = torch.zeros(2 * t + 2, dtype=torch.float32, device=device)
+    if self._ext and self._ext_state is None:
+      width = sum((1 if k in ('arp', 'opa') else t) + 1 for k in self._ext)
+      self._ext_state = torch.zeros(width, dtype=torch.float32, device=device)
+
   def all_reduce(self, group=None):
-    if self._state is not None:
-      dp.all_reduce_sum_(self._state, group)
+    self._zero_state()
+    dp.all_reduce_sum_(self._state, group)
     if self._ext_state is not None:
       dp.all_reduce_sum_(self._ext_state, group)
 
   def result(self):
     t = len(self.topns)
+    self._zero_state()
     s = self._state.double().cpu()
     out = {}
     if self._ext_state is not None:

@@ -5,21 +5,29 @@ shape of the reference's `ModelFitPipeline.train_and_validate`
 import os
 
 import torch
+import torch.distributed as dist
 
+from ranking_b200 import dp
 from ranking_b200.keras import metrics as keras_metrics
 
 
 def save_checkpoint(trainer, path, step):
-  """Parameters, optimizer accumulator, BN moving statistics and the step counter."""
+  """Parameters, optimizer accumulator, BN moving statistics and the step counter.
+  Data parallel: rank 0 alone writes (replicas hold identical parameters; BN statistics
+  are per replica and rank 0's are the ones kept), every rank waits for the file."""
   tower = trainer.tower
-  torch.save({'step': int(step), 'flat': tower.flat.detach().cpu(),
-              'accum': trainer.accum.cpu(), 'bn_state': tower.bn_state.cpu(),
-              'dims': list(tower.dims)}, path + '.tmp')
-  os.replace(path + '.tmp', path)      # atomic: a crash never leaves a torn file
+  if dp.rank(trainer.group) == 0:
+    tmp = '%s.tmp.%d' % (path, os.getpid())
+    torch.save({'step': int(step), 'flat': tower.flat.detach().cpu(),
+                'accum': trainer.accum.cpu(), 'bn_state': tower.bn_state.cpu(),
+                'dims': list(tower.dims)}, tmp)
+    os.replace(tmp, path)      # atomic: a crash never leaves a torn file
+  if dp.world_size(trainer.group) > 1:
+    dist.barrier(group=trainer.group)
 
 
 def load_checkpoint(trainer, path):
-  ckpt = torch.load(path, map_location='cpu')
+  ckpt = torch.load(path, map_location='cpu', weights_only=True)
   tower = trainer.tower
   if list(ckpt['dims']) != list(tower.dims):
     raise ValueError('checkpoint was written for dims %s, tower has %s' %

@@ -83,6 +83,28 @@ class RankingTrainer(object):
       x = x.to(t.input_dtype).contiguous()   # bf16 mode wants bf16 features in HBM
     return x
 
+  def _circular_pad(self, x, valid):
+    """FlattenList(circular_padding=True) (keras/layers.py:163-173): with BatchNormalization
+    in the tower the batch statistics must only see copies of VALID rows, so padded slots
+    are filled circularly with the list's valid items before the tower (K9).  Only done
+    when the tower normalises; without BN padded rows cannot influence valid ones."""
+    t = self.tower
+    if not (t.use_batch_norm or t.input_batch_norm) or valid is None:
+      return x
+    b, n, d = x.shape
+    if getattr(self, '_xg', None) is None or self._xg.shape != x.shape or \
+        self._xg.dtype != x.dtype:
+      self._xg = torch.empty_like(x)
+      self._pad_idx = torch.empty(b, n, dtype=torch.int32, device=x.device)
+    row_bytes = d * x.element_size()
+    if row_bytes % 16:
+      raise ValueError('circular padding needs feature rows that are multiples of 16 bytes')
+    v8 = valid.reshape(b, n).to(torch.uint8).contiguous()
+    _C.check(_C.lib.tfr_circular_pad_gather(_C.ptr(x), _C.ptr(v8), b, n, row_bytes,
+                                            _C.ptr(self._pad_idx), _C.ptr(self._xg),
+                                            _C.stream()))
+    return self._xg
+
   # -- scorer forward / backward (overridden by the groupwise trainer) ----------
   def _forward(self, x, y_true, m8, cfg, training):
     b, n, _ = x.shape
@@ -124,6 +146,7 @@ class RankingTrainer(object):
       m8 = mask.reshape(-1).to(torch.uint8).contiguous()
     grads = self.reducer.grads() if self.reducer is not None else self.grads
     self.grads = grads
+    x = self._circular_pad(x, mask if mask is not None else (y_true >= 0))
     self._forward(x, y_true, m8, cfg, True)
     self.loss.fused_fwd_bwd(y_true, self.scores, sample_weight, self.dscores,
                             self.per_list, self.total2)
@@ -139,6 +162,8 @@ class RankingTrainer(object):
     x = self._prep_x(x)
     m8 = None if mask is None else mask.reshape(-1).to(torch.uint8).contiguous()
     cfg = ctypes.byref(self.tower._run_cfg(training=False))
+    valid = mask if mask is not None else (None if y_true is None else y_true >= 0)
+    x = self._circular_pad(x, valid)
     self._forward(x, y_true, m8, cfg, False)
     return self.scores
 

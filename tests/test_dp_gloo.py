@@ -92,3 +92,55 @@ def test_single_process_helpers_are_noops():
   assert dp.world_size() == 1 and dp.rank() == 0
   assert dp.all_reduce_sum_(t) is t and dp.replica_grad_scale() == 1.0
   assert dp.shard_lists(8) == slice(0, 8)
+
+
+def _weights_worker(rank, world, port, out):
+  sys.path.insert(0, ROOT)
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    from ranking_b200 import dp
+    raw = _raw_rows()
+    sl = dp.shard_lists(raw.shape[0])
+    w = dp.cross_replica_list_weights(raw[sl], 'mrr')
+    gathered = [torch.zeros_like(w) for _ in range(world)]
+    dist.all_gather(gathered, w)
+    if rank == 0:
+      out.put(torch.cat(gathered))
+    dist.barrier()
+  finally:
+    dist.destroy_process_group()
+
+
+def _raw_rows():
+  # {sum w, sum w*gain, sum gain, sum w*rel, sum rel} for 6 lists: two without relevant
+  # items (one of them on each rank), one with zero weights
+  return torch.tensor([[3., 0., 0., 2.0, 2.], [3., 0., 0., 0.0, 0.], [0., 0., 0., 0.0, 1.],
+                       [4., 0., 0., 6.0, 3.], [2., 0., 0., 0.0, 0.], [5., 0., 0., 0.5, 1.]],
+                      dtype=torch.float64)
+
+
+def test_cross_replica_list_weights_equal_single_process():
+  """metrics_impl.py:63-119 over the concatenated batch == 2 ranks with the cross-replica
+  average (and != the per-replica average when the shards differ)."""
+  from oracle import metrics_impl as OM
+  raw = _raw_rows()
+  # oracle rule on the global batch: weights / relevance rows that reproduce `raw`
+  sum_w, wr, r = raw[:, 0], raw[:, 3], raw[:, 4]
+  per = torch.where(r != 0, wr / torch.where(r != 0, r, torch.ones_like(r)), torch.zeros_like(r))
+  cnt = ((sum_w > 0) & (r > 0)).double().sum()
+  avg = per.sum() / cnt
+  want = torch.where(sum_w > 0, torch.where(r > 0, per, avg.expand_as(per)), torch.zeros_like(per))
+  ctx = mp.get_context('spawn')
+  out = ctx.SimpleQueue()
+  port = 29500 + (os.getpid() % 2000) + 7
+  procs = [ctx.Process(target=_weights_worker, args=(r_, 2, port, out)) for r_ in range(2)]
+  for p in procs:
+    p.start()
+  got = out.get()
+  for p in procs:
+    p.join(timeout=60)
+    assert p.exitcode == 0
+  assert torch.allclose(got, want, rtol=1e-12)
+  del OM
