@@ -354,6 +354,7 @@ def run_gpu(args):
   w = WORKLOADS[cfg_id]
   B, N, D, gs = w['B'], w['N'], w['D'], w['group_size']
   precision = args.precision or w['precision']
+  full_affinity = os.sched_getaffinity(0)
   numa = tfr_dp.bind_to_gpu_numa_node(local_rank)   # before any pinned allocation
 
   tower = tfr.keras.layers.create_tower(HIDDEN, gs, activation='relu',
@@ -522,6 +523,7 @@ def run_gpu(args):
     }
     if world == 1 and not args.no_cpu_baseline:
       sample = args.cpu_sample_lists or min(w['cpu_sample'], 256)
+      os.sched_setaffinity(0, full_affinity)   # the CPU arm gets every host core again
       block, _ = cpu_baseline_block(cfg_id, sample, args.cpu_steps)
       line['cpu_baseline'] = block
     emit(line)

@@ -182,6 +182,32 @@ int tfr_misc_loss_fwd_bwd(const float* scores, const float* labels,
                           float* grad, float* row, float* loss, float* weight,
                           float* nonzero, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * K3c  Listwise losses of losses_impl.py outside the Keras RankingLossKey subset
+ * (SURVEY.md §8 f1), one CTA per list, nothing of size N x N in memory:
+ *   CIRCLE            CircleLoss                  losses_impl.py:1036-1116
+ *     scores are clipped to [0, 1] (no temperature); p0 = gamma, p1 = margin;
+ *     loss[b] = log1p(sum over pairs l_i > l_j of exp(gamma (a_i + c_j)));
+ *     weight[b] = list weight * (#pairs / #pairs): NaN for a list without a valid pair,
+ *     as the reference's sum(w) / count(w > 0) (:1108-1110).
+ *   NEURAL_SORT_CE    NeuralSortCrossEntropyLoss  losses_impl.py:1635-1675
+ *   NEURAL_SORT_NDCG  NeuralSortNDCGLoss          losses_impl.py:1678-1708
+ *     deterministic NeuralSort rows (losses_impl.py:1711-1801) of scores / temperature;
+ *     weight[b] = list weight * [sum of the cleaned labels > 0].
+ * loss[b] = list loss, grad = grad_scale * d loss[b] / d scores (raw scores).
+ * ------------------------------------------------------------------------- */
+typedef enum {
+  TFR_EXTRA_CIRCLE = 0,
+  TFR_EXTRA_NEURAL_SORT_CE = 1,
+  TFR_EXTRA_NEURAL_SORT_NDCG = 2
+} tfr_extra_loss;
+
+int tfr_extra_loss_fwd_bwd(const float* scores, const float* labels,
+                           const float* item_w, int w_per_item,
+                           const uint8_t* mask, int B, int N, float temperature,
+                           int kind, float p0, float p1, float grad_scale,
+                           float* grad, float* loss, float* weight, void* stream);
+
 /* OrdinalLoss (losses_impl.py:1850-1918): scores [B, N, K] (K = ordinal_size heads per
  * item), head k against [label >= k + 1] (+ the fractional part with
  * use_fraction_label); grad [B, N, K]; row / loss / weight / nonzero as for the
@@ -243,7 +269,9 @@ int tfr_rank_metrics(const float* scores, const float* labels,
  *   hits       [B, T]  HitsMetric :462-506
  *   arp        [B, 2]  {value, per-list weight = sum w l}    ARPMetric :509-536
  *   opa        [B, 2]  {value, per-list weight}              OPAMetric :708-743
- * precision / recall / map / hits use mrr_w as their per-list weight (relevance =
+ *   bpref      [B, T]  BPrefMetric :825-898, TREC form (use_trec_version=True)
+ *   bpref_alt  [B, T]  the same with R as the denominator (use_trec_version=False)
+ * precision / recall / map / hits / bpref use mrr_w as their per-list weight (relevance =
  * [label >= 1]); dcg uses ndcg_w. */
 typedef struct {
   float* dcg;
@@ -253,6 +281,8 @@ typedef struct {
   float* hits;
   float* arp;
   float* opa;
+  float* bpref;
+  float* bpref_alt;
 } tfr_metric_ext;
 
 int tfr_rank_metrics_ext(const float* scores, const float* labels,

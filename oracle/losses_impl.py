@@ -806,3 +806,110 @@ class CoupledRankDistilLoss(_ListwiseLoss):
     logprob = topk_student - torch.logsumexp(denom, dim=3)
     nll = (-logprob.sum(2)).mean(1, keepdim=True)
     return nll, nonzero_mask.to(logits.dtype).reshape(-1, 1)
+
+
+# ----------------------------------------------------------------------------
+# CircleLoss (losses_impl.py:1036-1116)
+# ----------------------------------------------------------------------------
+class CircleLoss(_ListwiseLoss):
+  """losses_impl.py:1036-1116.  Scores are clipped to [0, 1] by `get_logits`
+  (:1079-1082; no temperature); pairs (i, j) with label_i > label_j, both valid."""
+
+  def __init__(self, name=None, lambda_weight=None, gamma=64, margin=0.25):
+    super().__init__(name, lambda_weight, 1.0)
+    self._margin = margin
+    self._gamma = gamma
+
+  def get_logits(self, logits):
+    return torch.clamp(torch.as_tensor(logits), 0., 1.)
+
+  def _compute_unreduced_loss_impl(self, labels, logits, mask=None):
+    if mask is None:
+      mask = utils.is_label_valid(labels)
+    si = logits.unsqueeze(2)          # score_i of entry [b, i, j]
+    sj = logits.unsqueeze(1)
+    alpha_i = torch.relu(1 - si + self._margin).detach()       # :1090-1091
+    alpha_j = torch.relu(sj + self._margin).detach()           # :1092-1093
+    pairwise_logits = alpha_i * (1 - si - self._margin) + alpha_j * (sj - self._margin)
+    pairwise_labels, _ = _pairwise_comparison(labels, logits, mask)
+    pairwise_weights = pairwise_labels.detach()
+    losses = torch.exp(self._gamma * pairwise_logits)
+    per_list_losses = torch.log1p((losses * pairwise_weights).sum((1, 2)))
+    # :1108-1110  0 / 0 = NaN for a list without a valid pair, as in the reference
+    per_list_weights = pairwise_weights.sum((1, 2)) / (pairwise_weights > 0).to(
+        logits.dtype).sum((1, 2))
+    return per_list_losses.unsqueeze(1), per_list_weights.unsqueeze(1)
+
+
+# ----------------------------------------------------------------------------
+# NeuralSort (losses_impl.py:1635-1801)
+# ----------------------------------------------------------------------------
+def neural_sort(logits, mask=None):
+  """losses_impl.py:1711-1801: rows = ranks (valid ranks first), columns = items."""
+  logits = torch.as_tensor(logits)
+  if mask is None:
+    mask = torch.ones_like(logits, dtype=torch.bool)
+  mask = torch.as_tensor(mask)
+  logits = torch.where(mask, logits, torch.zeros_like(logits))
+  num_valid = mask.to(torch.int64).sum(1, keepdim=True)
+  logit_diff = (logits.unsqueeze(2) - logits.unsqueeze(1)).abs()
+  valid_pair = _apply_pairwise_op(torch.logical_and, mask)
+  logit_diff = torch.where(valid_pair, logit_diff, torch.zeros_like(logit_diff))
+  logit_diff_sum = logit_diff.sum(1, keepdim=True)                    # [B, 1, N]
+  masked_range = mask.to(torch.int64).cumsum(1)
+  scaling = (num_valid + 1 - 2 * masked_range).to(logits.dtype).unsqueeze(2)   # [B, N, 1]
+  p_logits = scaling * logits.unsqueeze(1) - logit_diff_sum
+  p_logits = torch.where(valid_pair, p_logits,
+                         torch.full_like(p_logits, -math.inf))
+  p_logits = torch.where(_apply_pairwise_op(torch.logical_or, mask), p_logits,
+                         torch.zeros_like(p_logits))
+  order = torch.argsort(mask.to(torch.int64), dim=1, descending=True, stable=True)
+  p_logits = torch.gather(p_logits, 1, order.unsqueeze(2).expand_as(p_logits))
+  return torch.softmax(p_logits, -1)
+
+
+class NeuralSortCrossEntropyLoss(_ListwiseLoss):
+  """losses_impl.py:1635-1675."""
+
+  def _compute_unreduced_loss_impl(self, labels, logits, mask=None):
+    if mask is None:
+      mask = utils.is_label_valid(labels)
+    labels = torch.where(mask, labels, torch.zeros_like(labels))
+    logits = torch.where(mask, logits, torch.zeros_like(logits))
+    label_sum = labels.sum(1, keepdim=True)
+    nonzero_mask = label_sum.reshape(-1) > 0.0
+    true_perm = neural_sort(labels, mask=mask)
+    smooth_perm = neural_sort(logits, mask=mask)
+    # softmax_cross_entropy_with_logits_v2(labels=true_perm, logits=log(1e-20 + P))
+    losses = -(true_perm * torch.log_softmax(torch.log(1e-20 + smooth_perm), 2)).sum(2)
+    sorted_mask = torch.sort(mask.to(logits.dtype), dim=1, descending=True).values > 0
+    losses = torch.where(sorted_mask, losses, torch.zeros_like(losses))
+    losses = _divide_no_nan(losses.sum(-1, keepdim=True),
+                            mask.to(logits.dtype).sum(-1, keepdim=True))
+    return losses, nonzero_mask.to(logits.dtype).reshape(-1, 1)
+
+
+def ndcg_perm(labels, perm_mat):
+  """losses_impl.py:137-167, perm_mat branch."""
+  ranks = torch.arange(labels.shape[1]) + 1
+  discounts = 1. / torch.log1p(ranks.to(labels.dtype))
+  gains = _safe_default_gain_fn(labels)
+  gains = (perm_mat * gains.unsqueeze(1)).sum(-1)
+  dcg = (gains * discounts).sum(-1, keepdim=True)
+  return dcg * inverse_max_dcg(labels, gain_fn=_safe_default_gain_fn)
+
+
+class NeuralSortNDCGLoss(_ListwiseLoss):
+  """losses_impl.py:1678-1708."""
+
+  def _compute_unreduced_loss_impl(self, labels, logits, mask=None):
+    if mask is None:
+      mask = utils.is_label_valid(labels)
+    labels = torch.where(mask, labels, torch.zeros_like(labels))
+    logits = torch.where(mask, logits, torch.zeros_like(logits))
+    label_sum = labels.sum(1, keepdim=True)
+    nonzero_mask = label_sum.reshape(-1) > 0.0
+    labels = torch.where(nonzero_mask.unsqueeze(1), labels,
+                         _EPSILON * torch.ones_like(labels))
+    smooth_perm = neural_sort(logits, mask=mask)
+    return -ndcg_perm(labels, smooth_perm), nonzero_mask.to(logits.dtype).reshape(-1, 1)

@@ -222,6 +222,30 @@ class MeanAveragePrecisionMetric(_RankingMetric):
                                                                   relevance)
 
 
+class BPrefMetric(_RankingMetric):
+  """metrics_impl.py:825-898."""
+
+  def __init__(self, name=None, topn=None, use_trec_version=True):
+    self._topn = topn
+    self._use_trec_version = use_trec_version
+
+  def _compute_impl(self, labels, predictions, weights, mask):
+    topn = predictions.shape[1] if self._topn is None else self._topn
+    relevance = _binary(labels)
+    irrelevance = mask.to(relevance.dtype) - relevance
+    total_relevance = relevance.sum(1, keepdim=True)
+    total_irrelevance = irrelevance.sum(1, keepdim=True)
+    sorted_relevance, sorted_irrelevance = utils.sort_by_scores(
+        predictions, [relevance, irrelevance], mask=mask, topn=topn)
+    numerator = torch.minimum(torch.cumsum(sorted_irrelevance, 1), total_relevance)
+    denominator = (torch.minimum(total_irrelevance, total_relevance)
+                   if self._use_trec_version else total_relevance)
+    bpref = L._divide_no_nan(
+        ((1. - L._divide_no_nan(numerator, denominator.expand_as(numerator))) *
+         sorted_relevance).sum(1, keepdim=True), total_relevance)
+    return bpref, _per_example_weights_to_per_list_weights(weights, relevance)
+
+
 class DCGMetric(_RankingMetric):
   """metrics_impl.py:673-705."""
 

@@ -43,7 +43,7 @@ class FeatureSpec(C.Structure):
 
 class MetricExt(C.Structure):
   _fields_ = [(k, C.c_void_p) for k in ('dcg', 'precision', 'recall', 'map', 'hits',
-                                        'arp', 'opa')]
+                                        'arp', 'opa', 'bpref', 'bpref_alt')]
 
 
 class MlpCfg(C.Structure):
@@ -76,6 +76,8 @@ _SIGNATURES = {
                                       _P]),
     'tfr_misc_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _P, _I, _I, _F, _I, _P, _P, _I, _F, _P, _P,
                                    _P, _P, _P, _P]),
+    'tfr_extra_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _P, _I, _I, _F, _I, _F, _F, _F, _P, _P, _P,
+                                    _P]),
     'tfr_ordinal_loss_fwd_bwd': (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _F, _I, _F, _P, _P, _P,
                                       _P, _P, _P]),
     'tfr_gumbel_sample': (_I, [_P, _P, _I, _I, _I, _F, C.c_uint64, _I, _P, _P, _P, _P]),

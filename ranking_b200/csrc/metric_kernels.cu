@@ -51,9 +51,9 @@ __device__ inline void bitonic_sort(unsigned long long* keys, int P) {
 }
 
 struct MetricExt {   // device copy of tfr_metric_ext (all optional)
-  float *dcg, *precision, *recall, *map, *hits, *arp, *opa;
+  float *dcg, *precision, *recall, *map, *hits, *arp, *opa, *bpref, *bpref_alt;
   __host__ __device__ bool any() const {
-    return dcg || precision || recall || map || hits || arp || opa;
+    return dcg || precision || recall || map || hits || arp || opa || bpref || bpref_alt;
   }
 };
 
@@ -199,13 +199,22 @@ rank_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ 
     block_inclusive_scan(term, N, scratch);
     for (int t = 0; t < topns.n; ++t) {
       const int cut = topns.v[t] > 0 ? min(topns.v[t], N) : N;
-      float rsum = 0.f, msum = 0.f;
+      float rsum = 0.f, msum = 0.f, bsum = 0.f, bsum_alt = 0.f;
+      // BPref (:868-893): irrelevant = valid - relevant; the valid items lead the order, so
+      // #irrelevant in the first k + 1 positions = min(k + 1, #valid) - #relevant there
+      const float n_irr = nv - s_r;
+      const float den_trec = fminf(n_irr, s_r);
       for (int k = tid; k < cut; k += blockDim.x) {
         rsum += relk[k];
         msum += term[k] / (float)(k + 1) * wk[k] * relk[k];   // precision@k at relevant k
+        const float num = fminf(fminf((float)(k + 1), nv) - term[k], s_r);
+        bsum += relk[k] * (1.f - (den_trec != 0.f ? num / den_trec : 0.f));
+        bsum_alt += relk[k] * (1.f - (s_r != 0.f ? num / s_r : 0.f));
       }
       rsum = block_sum(rsum, red);
       msum = block_sum(msum, red);
+      if (ext.bpref) bsum = block_sum(bsum, red);
+      if (ext.bpref_alt) bsum_alt = block_sum(bsum_alt, red);
       if (tid == 0) {
         const size_t o = (size_t)b * topns.n + t;
         const float vt = fminf((float)cut, nv);
@@ -214,6 +223,8 @@ rank_metrics_kernel(const float* __restrict__ scores, const float* __restrict__ 
         if (ext.recall) ext.recall[o] = s_r != 0.f ? rsum / s_r : 0.f;
         if (ext.hits) ext.hits[o] = rsum > 0.f ? 1.f : 0.f;
         if (ext.map) ext.map[o] = s_wr != 0.f ? msum / s_wr : 0.f;
+        if (ext.bpref) ext.bpref[o] = s_r != 0.f ? bsum / s_r : 0.f;
+        if (ext.bpref_alt) ext.bpref_alt[o] = s_r != 0.f ? bsum_alt / s_r : 0.f;
       }
     }
     if (ext.opa) {
@@ -447,7 +458,8 @@ extern "C" int tfr_rank_metrics_ext(const float* scores, const float* labels,
   MetricExt ext{};
   if (ext_host)
     ext = MetricExt{ext_host->dcg, ext_host->precision, ext_host->recall, ext_host->map,
-                    ext_host->hits, ext_host->arp, ext_host->opa};
+                    ext_host->hits, ext_host->arp, ext_host->opa, ext_host->bpref,
+                    ext_host->bpref_alt};
   const size_t smem = (((size_t)P * 8 + (size_t)(4 * N + 32) * 4 + N + 15) & ~(size_t)15) +
                       (ext.any() ? (size_t)(3 * N + kMetricThreads) * 4 : 0) + 16;
   if (smem > 48 * 1024)

@@ -643,6 +643,76 @@ class ListMLELoss(_MiscListwiseLoss):
 
 
 # ----------------------------------------------------------------------------
+# CircleLoss / NeuralSort losses  (tfr_extra_loss_fwd_bwd, K3c)
+# ----------------------------------------------------------------------------
+_EXTRA = {'circle': 0, 'neural_sort_ce': 1, 'neural_sort_ndcg': 2}
+
+
+class _ExtraFn(torch.autograd.Function):
+  """(loss[B], weight[B]) from one K3c launch; the gradient is produced by the same launch."""
+
+  @staticmethod
+  def forward(ctx, logits, labels, w, w_per_item, mask, temperature, kind, p0, p1):
+    b, n = logits.shape
+    grad = torch.empty_like(logits)
+    loss = torch.empty(b, dtype=torch.float32, device=logits.device)
+    weight = torch.empty_like(loss)
+    _C.check(_C.lib.tfr_extra_loss_fwd_bwd(
+        _C.ptr(logits), _C.ptr(labels), _C.ptr(w), w_per_item, _C.ptr(mask), b, n,
+        float(temperature), _EXTRA[kind], float(p0), float(p1), 1.0, _C.ptr(grad),
+        _C.ptr(loss), _C.ptr(weight), _C.stream()))
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(grad)
+    ctx.mark_non_differentiable(weight)
+    return loss, weight
+
+  @staticmethod
+  def backward(ctx, g_loss, _gw):
+    grad, = ctx.saved_tensors
+    out = None if g_loss is None else grad * g_loss.reshape(-1, 1)
+    return out, None, None, None, None, None, None, None, None
+
+
+class _ExtraListwiseLoss(_ListwiseLoss):
+  _p0 = 0.0
+  _p1 = 0.0
+
+  def _run(self, labels, logits, weights, mask, temperature):
+    labels, logits, weights, mask = self._densify(labels, logits, weights, mask)
+    labels, logits = _prep_2d(labels, logits)
+    w, wpi = _prep_weights(weights, logits)
+    m = _prep_mask(mask, logits)
+    return _ExtraFn.apply(logits, labels, w, wpi, m, temperature, self._kind, self._p0,
+                          self._p1)
+
+
+class CircleLoss(_ExtraListwiseLoss):
+  """losses_impl.py:1036-1116.  Scores are clipped to [0, 1] (`get_logits`, :1079-1082);
+  a list without a valid pair has weight 0 / 0 = NaN, as in the reference."""
+  _kind = 'circle'
+
+  def __init__(self, name=None, lambda_weight=None, gamma=64, margin=0.25, ragged=False):
+    super().__init__(name, lambda_weight, 1.0, ragged)
+    self._gamma = gamma
+    self._margin = margin
+    self._p0 = float(gamma)
+    self._p1 = float(margin)
+
+  def get_logits(self, logits):
+    return torch.clamp(logits, 0., 1.)
+
+
+class NeuralSortCrossEntropyLoss(_ExtraListwiseLoss):
+  """losses_impl.py:1635-1675."""
+  _kind = 'neural_sort_ce'
+
+
+class NeuralSortNDCGLoss(_ExtraListwiseLoss):
+  """losses_impl.py:1678-1708 (PiRank NDCG)."""
+  _kind = 'neural_sort_ndcg'
+
+
+# ----------------------------------------------------------------------------
 # GumbelSampler (losses_impl.py:540-649)
 # ----------------------------------------------------------------------------
 class _GumbelFn(torch.autograd.Function):

@@ -19,7 +19,7 @@ _DEFAULT_GAIN_FN = keras_utils.pow_minus_1            # metrics_impl.py:31
 _DEFAULT_RANK_DISCOUNT_FN = keras_utils.log2_inverse  # metrics_impl.py:33
 
 
-_EXT_KEYS = ('dcg', 'precision', 'recall', 'map', 'hits', 'arp', 'opa')
+_EXT_KEYS = ('dcg', 'precision', 'recall', 'map', 'hits', 'arp', 'opa', 'bpref', 'bpref_alt')
 
 
 def rank_metrics(labels, predictions, weights=None, mask=None, topns=(None,),
@@ -183,6 +183,16 @@ class PrecisionMetric(_ExtMetric):
 class MeanAveragePrecisionMetric(_ExtMetric):
   """metrics_impl.py:589-628."""
   _key = 'map'
+
+
+class BPrefMetric(_ExtMetric):
+  """metrics_impl.py:825-898: binary preference; `use_trec_version=False` divides the
+  count of irrelevant items ranked above a relevant one by R instead of min(R, N)."""
+
+  def __init__(self, name=None, topn=None, use_trec_version=True, ragged=False):
+    super().__init__(name, topn, ragged)
+    self._use_trec_version = use_trec_version
+    self._key = 'bpref' if use_trec_version else 'bpref_alt'
 
 
 class ARPMetric(_RankingMetric):

@@ -151,6 +151,42 @@ def _close(actual, expected):
   torch.testing.assert_close(a.reshape(e.shape), e, rtol=1e-5, atol=1e-6)
 
 
+# ---- BPref metrics_impl_test.py:1448-1610
+_BP = 1. / 2. * ((1. - 1. / 2.) + (1. - 2. / 2.))
+CASES += [
+    ('BPrefMetric', dict(topn=None), [[0., 1., 0., 1.]], [[4., 3., 2., 1.]], None, None,
+     [[_BP]], None),
+    ('BPrefMetric', dict(topn=None), [[0., 1., 0., 2.]], [[4., 3., 2., 1.]], None, None,
+     [[_BP]], None),
+    ('BPrefMetric', dict(topn=None), [[0., 0., 0.]], [[3., 2., 1.]], None, None, [[0.]], None),
+    ('BPrefMetric', dict(topn=None), [[1., 1., 1.]], [[3., 2., 1.]], None, None, [[1.]], None),
+    ('BPrefMetric', dict(topn=None, use_trec_version=False), [[1., 1., 1.]], [[3., 2., 1.]],
+     None, None, [[1.]], None),
+    ('BPrefMetric', dict(topn=None), [[0., 1., 1.]], [[3., 2., 1.]], None, None, [[0.]], None),
+    ('BPrefMetric', dict(topn=None, use_trec_version=False), [[0., 1., 1.]], [[3., 2., 1.]],
+     None, None, [[0.5]], None),
+    ('BPrefMetric', dict(topn=3), [[0., 0., 0., 1.]], [[3., 2., 1., 0.]], None, None, [[0.]],
+     None),
+    ('BPrefMetric', dict(topn=5, use_trec_version=False),
+     [[0., 1., 1., 1., 1., 0., 0., 0., 1., 1.]], [[5., 4., 3., 2., 1., 0., 0., 0., 0., 0.]],
+     None, None, [[(4. * (1. - 1. / 6.)) / 6.]], None),
+    ('BPrefMetric', dict(topn=5), [[0., 1., 1., 1., 1., 0., 0., 0., 1., 1.]],
+     [[5., 4., 3., 2., 1., 0., 0., 0., 0., 0.]], None, None, [[(4. * (1. - 1. / 4.)) / 6.]],
+     None),
+    ('BPrefMetric', dict(topn=None), [[-1., 0., -1., 1., 0., 1.]], [[6., 5., 4., 3., 2., 1.]],
+     None, None, [[_BP]], None),
+    ('BPrefMetric', dict(topn=None), [[1., 0., 2.]], [[1., 3., 2.]], [[13., 7., 29.]], None,
+     None, [[(13. + 29.) / 2.]]),
+    ('BPrefMetric', dict(topn=1), [[1., 1., 0.]], [[1., 3., 2.]], [[3., 7., 15.]], None, None,
+     [[(3. + 7.) / 2.]]),
+    ('BPrefMetric', dict(topn=None), [[0., 0., 0.]], [[1., 3., 2.]], [[3., 7., 15.]], None,
+     None, [[1.]]),
+    # ragged case :1566-1573 as padded lists
+    ('BPrefMetric', dict(topn=None), [[0., 0., 1., 0.], [0., 1., 1., -1.]],
+     [[1., 3., 2., 4.], [1., 2., 3., 0.]], None, None, [[0.], [1.]], None),
+]
+
+
 @pytest.mark.parametrize('case', range(len(CASES)))
 def test_reference_cases(api, case):
   cls, kw, labels, scores, weights, mask, want_v, want_w = CASES[case]

@@ -813,8 +813,12 @@ def test_fused_train_step_with_batch_norm(oracle_api):
     for t in leaves:
       t.grad = None
     mask = y >= 0
+    # the reference flattens with circular padding before the tower
+    # (keras/layers.py:163-173), so BatchNormalization only sees copies of valid items
+    _, flat_x = oracle_api.scorer.flatten_list({}, {'x': x.double()}, mask,
+                                               circular_padding=True)
     flat = oracle_api.scorer.tower_forward(
-        x.double().reshape(b * n, d), params, activation='relu',
+        flat_x['x'], params, activation='relu',
         use_batch_norm=True, input_batch_norm=True)
     logits = oracle_api.scorer.restore_list(flat, mask)
     ol = oloss(y.double(), logits)
