@@ -136,6 +136,10 @@ int make_mlp_plan(const tfr_mlp_cfg* cfg, int M, MlpPlan* p) {
   w += align_up(p->n_params, 64);
   p->wlo_off = w;
   w += align_up(p->n_params, 64);
+  p->wthi_off = w;
+  w += align_up(p->n_params, 64);
+  p->wtlo_off = w;
+  w += align_up(p->n_params, 64);
   p->tile_slots = 4 * 1024;   // upper bound: 4 quarters x persistent CTAs (<= SM count)
   p->tile_stride = align_up((size_t)max_hidden, 64);
   p->tile_off = w;

