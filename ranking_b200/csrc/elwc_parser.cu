@@ -276,6 +276,20 @@ extern "C" int tfr_ranking_parse(int format, const uint8_t* const* records,
   TFR_REQUIRE(n_context >= 0 && n_example >= 0, "bad feature counts");
   TFR_REQUIRE(n_example == 0 || example_out, "example_out must not be NULL");
   TFR_REQUIRE(n_context == 0 || context_out, "context_out must not be NULL");
+  TFR_REQUIRE(n_context == 0 || context_spec, "context_spec must not be NULL");
+  TFR_REQUIRE(n_example == 0 || example_spec, "example_spec must not be NULL");
+  {   // every dim >= 1 and the row widths fit an int: the offsets below index the outputs
+    long long wc = 0, we = 0;
+    for (int i = 0; i < n_context; ++i) {
+      TFR_REQUIRE(context_spec[i].dim >= 1, "context feature %d has dim %d", i, context_spec[i].dim);
+      wc += context_spec[i].dim;
+    }
+    for (int i = 0; i < n_example; ++i) {
+      TFR_REQUIRE(example_spec[i].dim >= 1, "example feature %d has dim %d", i, example_spec[i].dim);
+      we += example_spec[i].dim;
+    }
+    TFR_REQUIRE(wc < (1ll << 30) && we < (1ll << 30), "feature rows are too wide");
+  }
   int dc = 0, de = 0;
   const std::vector<Spec> cspec = make_specs(context_spec, n_context, &dc);
   const std::vector<Spec> espec = make_specs(example_spec, n_example, &de);

@@ -185,7 +185,16 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
   }
   float list_w = item_w ? (lvsum != 0.f ? wl / lvsum : 0.f) : 1.f;
   if (!nonzero) list_w = 0.f;
-  __syncthreads();
+  // Tail padding: an invalid item sits 1e3 (in units of z) below every valid one, so
+  // sigmoid(z_invalid - z_valid) and sigmoid' across that gap are exactly 0 in fp32 and its
+  // gain is 0: it changes no valid rank, no loss term and no gradient.  Tiles that lie
+  // entirely behind the last valid item are therefore skipped (lists are padded at the tail
+  // in every batch the input side produces; holes inside a list are walked as before).
+  float lastf = -1.f;
+  for (int i = tid; i < N; i += blockDim.x)
+    if (v.mv[i]) lastf = fmaxf(lastf, (float)i);
+  const int nv_hi = (int)block_max(lastf, v.red) + 1;   // (barrier: publishes z / cl as well)
+  const int tmax = (nv_hi + 31) >> 5;
 
   // pass 1: approx ranks r_i = 0.5 + sum_j sigmoid(z_j - z_i)   (:102-106)
   // [nwarps][N] cross-warp column partials (T > 0), placed after the list view
@@ -206,12 +215,14 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
     // diagonal tile pays for the j > i mask.  2 MUFU + 9 ALU per pair: MUFU-bound.
 #pragma unroll
     for (int t0 = 0; t0 < T; ++t0) {
-      const int iend = min(N, 32 * t0 + 32);
+      if (t0 >= tmax) break;
+      const int iend = min(nv_hi, 32 * t0 + 32);
       for (int i = 32 * t0 + warp; i < iend; i += nwarps) {
         const float zi = v.z[i] * kLog2e;
         float acc = 0.f;
 #pragma unroll
         for (int t = t0; t < T; ++t) {
+          if (t >= tmax) break;
           const float d = zc[t] - zi;
           const float e = exp2f_approx(-fabsf(d));
           const float big = rcp_approx(1.f + e);      // sigmoid(|d|)
@@ -238,9 +249,12 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
     __syncthreads();
     for (int i = tid; i < N; i += blockDim.x) {
       // + 0.5 of the reference (:106) + sigmoid(0) = 0.5 of the skipped j == i term
-      float acc = r[i] + 1.0f;
-      for (int w = 0; w < nwarps; ++w) acc += colpart[w * N + i];
-      r[i] = acc;
+      float acc = 1.0f;
+      if (i < nv_hi) {
+        acc += r[i];
+        for (int w = 0; w < nwarps; ++w) acc += colpart[w * N + i];
+      }
+      r[i] = acc;   // (skipped tail: any finite rank, its gain is 0)
     }
   } else {
     for (int i = warp; i < N; i += nwarps) {
@@ -307,12 +321,14 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
       }
 #pragma unroll
       for (int t0 = 0; t0 < T; ++t0) {
-        const int kend = min(N, 32 * t0 + 32);
+        if (t0 >= tmax) break;
+        const int kend = min(nv_hi, 32 * t0 + 32);
         for (int k = 32 * t0 + warp; k < kend; k += nwarps) {
           const float zk = v.z[k] * kLog2e, ck = c[k];
           float acc = 0.f;
 #pragma unroll
           for (int t = t0; t < T; ++t) {
+            if (t >= tmax) break;
             const float e = exp2f_approx(-fabsf(zk - zc[t]));   // columns past N: e = 0
             const float rc = rcp_approx(1.f + e);
             float term = (cc[t] - ck) * (e * rc * rc);           // (c_i - c_k) sigmoid'
@@ -331,8 +347,11 @@ approx_loss_kernel(const float* __restrict__ scores, const float* __restrict__ l
       }
       __syncthreads();
       for (int k = tid; k < N; k += blockDim.x) {
-        float acc = gacc[k];
-        for (int w = 0; w < nwarps; ++w) acc += colpart[w * N + k];
+        float acc = 0.f;
+        if (k < nv_hi) {
+          acc = gacc[k];
+          for (int w = 0; w < nwarps; ++w) acc += colpart[w * N + k];
+        }
         grad[(size_t)b * N + k] = v.mv[k] ? acc * gs : 0.f;
       }
     } else {

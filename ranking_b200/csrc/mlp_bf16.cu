@@ -164,6 +164,170 @@ out_bwd_bf16_kernel(const __nv_bfloat162* __restrict__ H2, int M, int K, int O,
   }
 }
 
+// ---- streaming versions for narrow last layers (K <= 128, O <= 2: the benchmark towers) ----
+// Eight lanes share a row: a lane owns 8 consecutive k (one 16-byte load) per 64-wide chunk,
+// a warp instruction covers four rows and the loop is unrolled over four of them, so a warp
+// keeps 16 rows (2 KB) in flight.  The row-per-warp kernels above move 128 B per warp and
+// load round trip: 58 us / 97 us for 34 MB at config 3 (profiles/r02_launches_c3.txt).
+constexpr int kFastK = 128, kFastO = 2;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&h)[8]) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(p[j]);
+    h[2 * j] = f.x;
+    h[2 * j + 1] = f.y;
+  }
+}
+
+template <int CPL, int O>   // CPL = 64-wide chunks per row (1 or 2)
+__global__ void __launch_bounds__(256)
+out_fwd_bf16_fast_kernel(const uint4* __restrict__ H8, int M, int K, const float* __restrict__ W,
+                         const float* __restrict__ bias, const uint8_t* __restrict__ mask,
+                         float* __restrict__ scores) {
+  const int l8 = threadIdx.x & 7;
+  const int K8 = K >> 3;
+  float w[CPL][8][O];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int o = 0; o < O; ++o) {
+        const int k = (c * 8 + l8) * 8 + j;
+        w[c][j][o] = k < K ? __ldg(W + (size_t)k * O + o) : 0.f;
+      }
+  const int rows_per_it = (gridDim.x * blockDim.x) >> 3;
+  const int iters = (M + rows_per_it - 1) / rows_per_it;   // uniform: every lane joins the shuffles
+  for (int it = 0; it < iters; ++it) {
+    const int m = it * rows_per_it + ((blockIdx.x * blockDim.x + threadIdx.x) >> 3);
+    const bool live = m < M;
+    float acc[O];
+#pragma unroll
+    for (int o = 0; o < O; ++o) acc[o] = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int k8 = c * 8 + l8;
+      if (live && k8 < K8) {
+        float h[8];
+        unpack8(__ldg(H8 + (size_t)m * K8 + k8), h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int o = 0; o < O; ++o) acc[o] = fmaf(h[j], w[c][j][o], acc[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < O; ++o) {
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+      acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 4);
+    }
+    if (live && l8 == 0) {
+#pragma unroll
+      for (int o = 0; o < O; ++o) {
+        float v = acc[o] + bias[o];
+        if (mask && O == 1 && !mask[m]) v = kLogEpsilon;
+        scores[(size_t)m * O + o] = v;
+      }
+    }
+  }
+}
+
+// Slot layout per block as out_bwd_bf16_kernel: { dW[K*O], db[O], pad to 4, csum[K] }.
+template <int CPL, int O>
+__global__ void __launch_bounds__(256)
+out_bwd_bf16_fast_kernel(const uint4* __restrict__ H8, int M, int K, const float* __restrict__ W,
+                         const float* __restrict__ dS, const uint8_t* __restrict__ mask, int act,
+                         int rows_per, uint4* __restrict__ dH8, float* __restrict__ slots,
+                         size_t slot_stride) {
+  extern __shared__ float sm[];   // [32 row groups][per]
+  const int l8 = threadIdx.x & 7, rg = threadIdx.x >> 3;   // 32 row groups of 8 lanes
+  const int K8 = K >> 3;
+  const int mbeg = blockIdx.x * rows_per, mend = min(M, mbeg + rows_per);
+  float w[CPL][8][O], dw[CPL][8][O], cs[CPL][8], db[O];
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      cs[c][j] = 0.f;
+#pragma unroll
+      for (int o = 0; o < O; ++o) {
+        const int k = (c * 8 + l8) * 8 + j;
+        w[c][j][o] = k < K ? __ldg(W + (size_t)k * O + o) : 0.f;
+        dw[c][j][o] = 0.f;
+      }
+    }
+#pragma unroll
+  for (int o = 0; o < O; ++o) db[o] = 0.f;
+#pragma unroll 4
+  for (int m = mbeg + rg; m < mend; m += 32) {
+    const bool live = !(mask && O == 1 && !mask[m]);
+    float ds[O];
+#pragma unroll
+    for (int o = 0; o < O; ++o) ds[o] = live ? __ldg(dS + (size_t)m * O + o) : 0.f;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      const int k8 = c * 8 + l8;
+      if (k8 < K8) {
+        float h[8], d[8];
+        unpack8(__ldg(H8 + (size_t)m * K8 + k8), h);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float dj = 0.f;
+#pragma unroll
+          for (int o = 0; o < O; ++o) {
+            dj = fmaf(ds[o], w[c][j][o], dj);
+            dw[c][j][o] = fmaf(h[j], ds[o], dw[c][j][o]);
+          }
+          if (act == TFR_ACT_RELU && !(h[j] > 0.f)) dj = 0.f;
+          d[j] = dj;
+          cs[c][j] += dj;
+        }
+        if (dH8) {
+          uint4 o4;
+          __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&o4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) q[j] = __floats2bfloat162_rn(d[2 * j], d[2 * j + 1]);
+          dH8[(size_t)m * K8 + k8] = o4;
+        }
+      }
+    }
+    if (l8 == 0) {
+#pragma unroll
+      for (int o = 0; o < O; ++o) db[o] += ds[o];
+    }
+  }
+  const int co = (K * O + O + 3) & ~3;
+  const int per = co + K;
+  float* mine = sm + (size_t)rg * per;
+#pragma unroll
+  for (int c = 0; c < CPL; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = (c * 8 + l8) * 8 + j;
+      if (k < K) {
+#pragma unroll
+        for (int o = 0; o < O; ++o) mine[k * O + o] = dw[c][j][o];
+        mine[co + k] = cs[c][j];
+      }
+    }
+  if (l8 == 0) {
+    for (int i = K * O + O; i < co; ++i) mine[i] = 0.f;
+#pragma unroll
+    for (int o = 0; o < O; ++o) mine[K * O + o] = db[o];
+  }
+  __syncthreads();
+  float* out = slots + (size_t)blockIdx.x * slot_stride;
+  for (int i = threadIdx.x; i < per; i += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) acc += sm[(size_t)r * per + i];
+    out[i] = acc;
+  }
+}
+
 int check_bf16(const MlpPlan& p) {
   const int L = p.n_dense - 1;
   if (p.post() || p.input_bn) {
@@ -227,6 +391,21 @@ int mlp_bf16_fwd(const void* X, int M, const MlpPlan& p, const float* params,
     in = as_bf16(ws + p.act_off[d]);
   }
   const int K = p.dims[L], O = p.dims[L + 1];
+  if (K <= kFastK && O <= kFastO) {
+    const int nb = (M + 31) / 32 < 148 * 8 ? (M + 31) / 32 : 148 * 8;   // 32 rows per block pass
+    const uint4* H8 = reinterpret_cast<const uint4*>(in);
+    const float* Wl = params + p.w_off[L];
+    const float* bl = params + p.b_off[L];
+#define TFR_OUT_FWD(C_, O_) \
+  out_fwd_bf16_fast_kernel<C_, O_><<<nb, 256, 0, st>>>(H8, M, K, Wl, bl, mask, scores)
+    if (K <= 64 && O == 1) TFR_OUT_FWD(1, 1);
+    else if (K <= 64) TFR_OUT_FWD(1, 2);
+    else if (O == 1) TFR_OUT_FWD(2, 1);
+    else TFR_OUT_FWD(2, 2);
+#undef TFR_OUT_FWD
+    TFR_LAUNCH_OK();
+    return TFR_OK;
+  }
   const int blocks = (M + 7) / 8 < 148 * 16 ? (M + 7) / 8 : 148 * 16;
   out_fwd_bf16_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat162*>(in), M,
                                               K / 2, O, params + p.w_off[L], params + p.b_off[L],
@@ -250,6 +429,28 @@ int mlp_bf16_bwd(const void* X, int M, const MlpPlan& p, const float* params,
   {
     const int K = p.dims[L], O = p.dims[L + 1];
     const void* H = L > 0 ? (const void*)as_bf16(ws + p.act_off[L - 1]) : X;
+    if (K <= kFastK && O <= kFastO) {
+      const int co = (K * O + O + 3) & ~3;
+      const size_t smem = (size_t)32 * (co + K) * sizeof(float);
+      const uint4* H8 = reinterpret_cast<const uint4*>(H);
+      uint4* dH8 = L > 0 ? reinterpret_cast<uint4*>(dz_cur) : nullptr;
+      const int actl = L > 0 ? p.activation : TFR_ACT_NONE;
+#define TFR_OUT_BWD(C_, O_)                                                                     \
+  {                                                                                             \
+    if (smem > 48 * 1024)                                                                       \
+      TFR_CUDA_OK(cudaFuncSetAttribute(out_bwd_bf16_fast_kernel<C_, O_>,                        \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    out_bwd_bf16_fast_kernel<C_, O_><<<p.out_slots, 256, smem, st>>>(                           \
+        H8, M, K, params + p.w_off[L], dscores, mask, actl, p.out_rows, dH8, oslots,            \
+        p.oslot_stride);                                                                        \
+  }
+      if (K <= 64 && O == 1) TFR_OUT_BWD(1, 1)
+      else if (K <= 64) TFR_OUT_BWD(1, 2)
+      else if (O == 1) TFR_OUT_BWD(2, 1)
+      else TFR_OUT_BWD(2, 2)
+#undef TFR_OUT_BWD
+      TFR_LAUNCH_OK();
+    } else {
     const int K2 = K / 2;
     const int KP = (K2 + 31) / 32 * 32;
     const int RL = 256 / KP;
@@ -263,6 +464,7 @@ int mlp_bf16_bwd(const void* X, int M, const MlpPlan& p, const float* params,
         L > 0 ? p.activation : TFR_ACT_NONE, p.out_rows, KP, RL,
         L > 0 ? reinterpret_cast<__nv_bfloat162*>(dz_cur) : nullptr, oslots, p.oslot_stride);
     TFR_LAUNCH_OK();
+    }
     rc = mlp_reduce2(oslots, p.out_slots, p.oslot_stride, (size_t)K * O + O, nullptr, 0, 0, 0,
                      grads + p.w_off[L], st);
     if (rc) return rc;

@@ -87,6 +87,8 @@ struct KernelArgs {
 // is what bounds these kernels: profiles/r02_tc_gemm_wait_cycles.txt) and the stage shrinks
 // enough for a 4-deep ring at N = 256.
 template <bool A_MN, bool B_MN, int PASSES, bool SPLIT_B, bool CG2 = false>
+// (18 warps: ptxas grants 96 registers per thread; 112 was tried with __maxnreg__ and the
+//  launch fails with "too many resources" — the per-warp allocation step does not fit)
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
@@ -231,7 +233,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // (pairs: box [N / 2 rows][32 k], this CTA's half of the tile)
             if (!B_MN) tma_load_2d(sB_hi(s), &tmB, &full[s], k0,
                                    n0 + (CG2 ? (int)rank * (args.n_umma >> 1) : 0));
-            else tma_load_2d(sB_hi(s) + j * box_bytes, &tmB, &full[s], n0 + 32 * j, k0);
+            else tma_load_2d(sB_hi(s) + j * box_bytes, &tmB, &full[s],
+                             n0 + (CG2 ? (int)rank * (args.n_umma >> 1) : 0) + 32 * j, k0);
           } else if (lane < nA + nB + nBlo) {
             const int j = lane - nA - nB;
             if (!B_MN) tma_load_2d(sB_lo(s), &tmBlo, &full[s], k0,
@@ -496,8 +499,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float ccol[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) ccol[k] = 0.f;
-    long long w_accfull = 0, w_ld = 0, w_smem = 0, w_st = 0, w_x = 0;
-    const long long t_start = clock64();
+    // wait-cycle counters of the profiling build live in shared memory: as registers they
+    // stayed live across the whole epilogue loop and pushed its operands onto the stack
+    long long* s_dbg = reinterpret_cast<long long*>(bars + 3 * kMaxStages + 6);   // [5]
+    const bool dbg_me = args.dbg != nullptr && threadIdx.x == kEpiWarp0 * 32;
+    if (dbg_me) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) s_dbg[i] = 0;
+    }
+    const long long t_start = args.dbg ? clock64() : 0;
     for (int tile = tile0; tile < total_tiles; tile += tstep, ++tcount) {
       int m0, n0, z, kb_begin, nkb;
       decode(tile, m0, n0, z, kb_begin, nkb);
@@ -513,7 +523,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       };
       uint32_t mword = 0, mword_next = 0;
       if (args.tma_store && args.epi == EPI_MASK_BITS) mword = load_bits(half * 32);
-      w_accfull += mbar_wait(&acc_full[ab], aph);
+      {
+        const long long wcy = mbar_wait(&acc_full[ab], aph);
+        if (dbg_me) s_dbg[0] += wcy;
+      }
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + ab * args.tmem_cols +
                               (static_cast<uint32_t>(q * 32) << 16);
@@ -597,10 +610,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<float4*>(stg + lane * 128 + (((hf * 4 + j) ^ (lane & 7)) << 4)) =
                   make_float4(x[4 * j + 0], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-            if (args.dbg) {
-              w_ld += tp1 - tp0;
-              w_smem += tpa - tp1;    // register math
-              w_st += tpb - tpa;      // wait for the staging tile
+            if (dbg_me) {
+              s_dbg[1] += tp1 - tp0;
+              s_dbg[2] += tpa - tp1;    // register math
+              s_dbg[3] += tpb - tpa;    // wait for the staging tile
             }
           }
           const long long tpc = args.dbg ? clock64() : 0;
@@ -631,7 +644,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               cacc[colb + lane] += cs;
             }
           }
-          if (args.dbg) w_x += clock64() - tpc;   // fence + store issue + column sums
+          if (dbg_me) s_dbg[4] += clock64() - tpc;   // fence + store issue + column sums
         }
         continue;   // acc_empty already signalled
       }
@@ -747,11 +760,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 8; ++i) keep[i] = keep_next[i];
           }
           __syncwarp();
-          if (args.dbg) {
+          if (dbg_me) {
             const long long tp3 = clock64();
-            w_ld += tp1 - tp0;
-            w_smem += tp2 - tp1;
-            w_st += tp3 - tp2;
+            s_dbg[1] += tp1 - tp0;
+            s_dbg[2] += tp2 - tp1;
+            s_dbg[3] += tp3 - tp2;
           }
         }
       } else {
@@ -803,13 +816,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c = lane; c < args.GN; c += 32) dst[c] = cacc[c];
       }
     }
-    if (args.dbg && threadIdx.x == kEpiWarp0 * 32) {
-      args.dbg[blockIdx.x * 12 + 6] = w_accfull;
+    if (dbg_me) {
+      args.dbg[blockIdx.x * 12 + 6] = s_dbg[0];
       args.dbg[blockIdx.x * 12 + 7] = clock64() - t_start;
-      args.dbg[blockIdx.x * 12 + 8] = w_ld;
-      args.dbg[blockIdx.x * 12 + 9] = w_smem;
-      args.dbg[blockIdx.x * 12 + 10] = w_st;
-      args.dbg[blockIdx.x * 12 + 11] = w_x;
+      args.dbg[blockIdx.x * 12 + 8] = s_dbg[1];
+      args.dbg[blockIdx.x * 12 + 9] = s_dbg[2];
+      args.dbg[blockIdx.x * 12 + 10] = s_dbg[3];
+      args.dbg[blockIdx.x * 12 + 11] = s_dbg[4];
     }
   }
   tc_fence_before();
@@ -881,10 +894,11 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
 }
 
 // CTA pairs: cluster of 2 along x (one TPC), cta_group::2 MMAs.
+template <bool MN>   // false: forward / dZ (K-major, pre-split B); true: dW (MN-major, split B)
 static int launch_pairs(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo,
                         const CUtensorMap& tmC, const KernelArgs& ka, dim3 grid, size_t smem,
                         cudaStream_t st) {
-  auto kern = tc_gemm_kernel<false, false, 3, false, true>;
+  auto kern = tc_gemm_kernel<MN, MN, 3, MN, true>;
   TFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -916,7 +930,14 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
 
   // N tiling: one tile if it fits a single UMMA (N <= 256), else tiles of 256.
   static const int n_cap = getenv("TFR_TC_NCAP") ? atoi(getenv("TFR_TC_NCAP")) : 256;
-  const int n_umma = g.GN <= n_cap ? ((g.GN + 15) / 16) * 16 : n_cap;
+  static const bool no_pairs = getenv("TFR_TC_NO_PAIRS") != nullptr;
+  static const bool no_pairs_mn = getenv("TFR_TC_NO_PAIRS_MN") != nullptr;
+  // dW GEMMs as CTA pairs: each CTA stages its 128 rows of the M side and HALF of the N side
+  // (whole 32-column boxes), so N is rounded up to a multiple of 64.
+  const bool want_pairs_mn = !no_pairs && !no_pairs_mn && g.passes == 3 && g.a_mn && g.b_mn &&
+                             g.split_b && g.GM > BM && (g.GN + 63) / 64 * 64 <= n_cap;
+  const int n_umma = want_pairs_mn ? (g.GN + 63) / 64 * 64
+                                   : (g.GN <= n_cap ? ((g.GN + 15) / 16) * 16 : n_cap);
   const int n_tiles = (g.GN + n_umma - 1) / n_umma;
   // Stage depth in k: the 128 B swizzle pins K-major tiles to 32 fp32 of k; MN-major tiles
   // may use 16 k-rows, which halves the stage and doubles the ring depth (the dW GEMMs
@@ -941,11 +962,13 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
                 acc_bufs * acc_cols + 2 * 64 <= 512;
   if (!a_tmem) acc_bufs = 2;
   // CTA pairs (see the kernel's CG2 note): forward / dZ GEMMs with one n tile.
-  static const bool no_pairs = getenv("TFR_TC_NO_PAIRS") != nullptr;
   const int m_tiles_all = (g.GM + BM - 1) / BM;
-  const bool cg2 = !no_pairs && g.passes == 3 && a_tmem_k && !g.b_mn && n_tiles == 1 &&
-                   (g.splits <= 1) && n_umma % 32 == 0 && m_tiles_all >= 4;
-  if (cg2) b_tile_bytes = (n_umma / 2) * 128;   // this CTA's half of the B tile
+  const bool cg2_k = !no_pairs && g.passes == 3 && a_tmem_k && !g.b_mn && n_tiles == 1 &&
+                     (g.splits <= 1) && n_umma % 32 == 0 && m_tiles_all >= 4;
+  const bool cg2_mn = want_pairs_mn && a_tmem && n_tiles == 1;
+  const bool cg2 = cg2_k || cg2_mn;
+  if (cg2_k) b_tile_bytes = (n_umma / 2) * 128;          // this CTA's half of the B tile
+  if (cg2_mn) b_tile_bytes = (n_umma / 64) * bk * 128;   // ... as whole [32 k][32 n] boxes
   int stage_bytes = a_tmem ? a_tile_bytes + b_tile_bytes * copies
                            : (a_tile_bytes + b_tile_bytes) * copies;
   int splits = g.splits < 1 ? 1 : g.splits;
@@ -1062,7 +1085,7 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   }
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
   if (cg2) {
-    const int pair_tiles = (ka.m_tiles + 1) / 2;
+    const int pair_tiles = (ka.m_tiles + 1) / 2 * ka.n_tiles * splits;
     const int pairs = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
     grid = dim3(2 * pairs);
   }
@@ -1071,7 +1094,8 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
                       256 /*barriers*/;
   if (g.colsum_slots_out) *g.colsum_slots_out = kEpiWarps * (int)grid.x;
 
-  if (cg2) return launch_pairs(tmA, tmB, tmBlo, tmC, ka, grid, smem, st);
+  if (cg2) return cg2_mn ? launch_pairs<true>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st)
+                         : launch_pairs<false>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st);
 #define TFR_TC_LAUNCH(AMN, BMN, P, SB) \
   return launch<AMN, BMN, P, SB>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st)
   const int key = (g.a_mn ? 8 : 0) | (g.b_mn ? 4 : 0) | (g.passes == 3 ? 2 : 0) |

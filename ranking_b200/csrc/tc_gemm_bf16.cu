@@ -152,8 +152,12 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------- TMA producer ----
-    if (lane == 0) {
+    // Converged warp: lane 0 arms the stage barrier, every box of the stage is issued by its
+    // own lane in one warp instruction (the dW layout has 2 MT + N / 64 boxes of 8 KB).
+    {
       const uint32_t tx_bytes = a_bytes + args.b_tile_bytes;
+      const int nA = MN ? 2 * MT : 1;
+      const int nB = MN ? args.b_tile_bytes / 8192 : 1;
       uint32_t it = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         int m0, n0, z, kb_begin, nkb;
@@ -162,17 +166,16 @@ bf16_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], tx_bytes);
+          if (lane == 0) mbar_expect_tx(&full[s], tx_bytes);
+          __syncwarp();
           const int k0 = (kb_begin + kb) * BK;
-          if (!MN) {
-            tma_load_2d(sA(s), &tmA, &full[s], k0, m0);     // box {64 k, 128 rows}
-            tma_load_2d(sB(s), &tmB, &full[s], k0, n0);     // box {64 k, n_umma rows}
-          } else {
-            for (int i = 0; i < 2 * MT; ++i)                // boxes {64 m, 64 k}
-              tma_load_2d(sA(s) + i * 8192, &tmA, &full[s], m0 + 64 * i, k0);
-            const int nbox = args.b_tile_bytes / 8192;
-            for (int j = 0; j < nbox; ++j)                  // boxes {64 n, 64 k}
-              tma_load_2d(sB(s) + j * 8192, &tmB, &full[s], n0 + 64 * j, k0);
+          if (lane < nA) {
+            if (!MN) tma_load_2d(sA(s), &tmA, &full[s], k0, m0);     // box {64 k, 128 rows}
+            else tma_load_2d(sA(s) + lane * 8192, &tmA, &full[s], m0 + 64 * lane, k0);   // {64 m, 64 k}
+          } else if (lane < nA + nB) {
+            const int j = lane - nA;
+            if (!MN) tma_load_2d(sB(s), &tmB, &full[s], k0, n0);     // box {64 k, n_umma rows}
+            else tma_load_2d(sB(s) + j * 8192, &tmB, &full[s], n0 + 64 * j, k0);         // {64 n, 64 k}
           }
         }
       }

@@ -50,8 +50,10 @@ class _RankingMetric(object):
 
   def all_reduce(self, group=None):
     """Data-parallel evaluation: SUM the (sum v*w, sum w) pair across ranks."""
-    if self._state is not None:
-      dp.all_reduce_sum_(self._state, group)
+    if self._state is None:   # a rank that saw no batch still has to enter the collective
+      dev = 'cuda' if torch.cuda.is_available() else 'cpu'
+      self._state = torch.zeros(2, dtype=torch.float32, device=dev)
+    dp.all_reduce_sum_(self._state, group)
 
   def result(self):
     if self._state is None:

@@ -33,10 +33,15 @@ if len(sys.argv) > 3:
     v = float(v.replace(',', ''))
     return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
   ir, iw, ik = head.index('dram__bytes_read.sum'), head.index('dram__bytes_write.sum'), head.index('Kernel Name')
-  gemm = sum(to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in rows[2:]
-             if 'tc_gemm' in r[ik] or 'out_layer' in r[ik])
-  loss = sum(to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in rows[2:]
-             if 'approx_loss' in r[ik])
-  json.dump({'source': sys.argv[2] + ' (ncu --set full, one training step, B=1024 N=200 D=136, tf32x3)',
-             'scorer_gemm_dram_bytes_per_step': int(gemm),
-             'approx_loss_dram_bytes_per_step': int(loss)}, open(sys.argv[3], 'w'), indent=1)
+  def total(pred):
+    return int(sum(to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]) for r in rows[2:]
+                   if pred(r[ik])))
+  # the scorer: GEMM engines, output-layer kernels, group gather / scatter, their reductions
+  scorer = lambda k: any(t in k for t in ('gemm_kernel', 'out_layer', 'out_fwd', 'out_bwd', 'group_',
+                                          'reduce', 'split_params', 'shadow_params'))
+  loss = lambda k: any(t in k for t in ('approx_loss', 'pairwise_tri', 'pairwise_loss', 'softmax_loss'))
+  json.dump({'source': sys.argv[2] + ' (ncu --set full, one training step of the bench workload)',
+             'scorer_gemm_dram_bytes_per_step': total(scorer),
+             'loss_dram_bytes_per_step': total(loss),
+             'all_kernels_dram_bytes_per_step': total(lambda k: True)},
+            open(sys.argv[3], 'w'), indent=1)
