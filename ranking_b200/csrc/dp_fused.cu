@@ -54,10 +54,13 @@ allreduce_optimizer_kernel(PeerTable t, int rank, int world, uint32_t epoch,
   }
   if (threadIdx.x < world) {
     const uint32_t* mine = t.flags[rank] + threadIdx.x;
-    long long spins = 0;
-    // epochs only grow; "not yet" is a smaller value (wrap-safe signed distance)
+    unsigned long long t0, now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    // epochs only grow; "not yet" is a smaller value (wrap-safe signed distance).  A peer that
+    // never arrives (a crashed rank) must trap, not hang the GPU: 5 s of wall clock.
     while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-      if (++spins > (1ll << 31)) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > 5000000000ull) {
         printf("tfr all-reduce: rank %d timed out waiting for rank %d (epoch %u)\n", rank,
                (int)threadIdx.x, epoch);
         __trap();

@@ -632,10 +632,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (args.colsum) {
             // lane = column: sum the 32 rows of the staged block (rows past GM are zero)
             const float* tbf = reinterpret_cast<const float*>(stg);
-            float cs = 0.f;
+            float cs4[4] = {0.f, 0.f, 0.f, 0.f};   // four chains: the adds are latency-bound
 #pragma unroll
             for (int r = 0; r < 32; ++r)
-              cs += tbf[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
+              cs4[r & 3] += tbf[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
+            const float cs = (cs4[0] + cs4[1]) + (cs4[2] + cs4[3]);
             if (args.colsum_regs) {
               const int ci = c0 >> 5;
 #pragma unroll

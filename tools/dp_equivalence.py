@@ -20,20 +20,22 @@ y = torch.randint(0, 5, (b, n), generator=g).float().cuda()
 y[:, n - 6:] = -1.
 
 
-def make():
+def make(collective):
   t = tfr.keras.layers.create_tower([32, 16], 1, activation='relu', use_batch_norm=False,
                                     dropout=0, input_dim=d, seed=11)
   return t, tfr.train.RankingTrainer(t, tfr.keras.losses.get('approx_ndcg_loss'),
-                                     optimizer='adagrad', learning_rate=0.1)
+                                     optimizer='adagrad', learning_rate=0.1,
+                                     collective=collective)
 
 
-tower, trainer = make()
+COLLECTIVE = os.environ.get('TFR_COLLECTIVE', 'fused')   # the K7 kernel by default
+tower, trainer = make(COLLECTIVE)
 tfr.dp.broadcast_(tower.flat.data)
 sl = tfr.dp.shard_lists(b)
 loss = trainer.train_step(x[sl], y[sl])
 torch.cuda.synchronize()
 if rank == 0:
-  ref_tower, ref_trainer = make()
+  ref_tower, ref_trainer = make('nccl')   # no peer-memory reducer: rank 0 steps alone
   ref_trainer.world = 1
   ref_trainer.group = None
   # single-process reference: no collective (use a trainer whose dp hooks are no-ops)
@@ -48,6 +50,6 @@ if rank == 0:
               ref_tower.flat.data.abs().max())
   print('max rel param diff', err)
   assert err < 1e-5, err
-  print('DP_EQUIVALENCE_OK')
+  print('DP_EQUIVALENCE_OK', COLLECTIVE)
 dist.barrier()
 dist.destroy_process_group()

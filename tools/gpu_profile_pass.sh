@@ -21,6 +21,10 @@ done
 timeout 300 ncu --set full --clock-control none -f -k regex:rank_metrics -c 2 -o /tmp/${TAG}_k4 \
   python tools/metric_only.py > gpurun_out/${TAG}_full_k4.log 2>&1
 python tools/ncu_summary.py /tmp/${TAG}_k4.ncu-rep gpurun_out/${TAG}_k4_ncu_full_summary.csv >> gpurun_out/${TAG}_full_k4.log 2>&1
+for g in fwd1 dz1 dw1; do
+  timeout 300 ncu --set full --import-source on --clock-control none -f -k regex:tc_gemm -c 1 \
+    -o gpurun_out/${TAG}_hot_$g python tools/gemm_only.py $g > gpurun_out/${TAG}_hot_$g.log 2>&1
+done
 timeout 300 python tools/tc_wait_profile.py > gpurun_out/${TAG}_tc_gemm_wait_cycles.txt 2>&1
 [ -x build/mma_rate ] && timeout 120 ./build/mma_rate > gpurun_out/${TAG}_mma_rate.txt 2>&1
 ls -la gpurun_out | tail -30
