@@ -386,11 +386,19 @@ extern "C" int tfr_group_mlp_fwd(const float* X, int B, int N, int G, int gs, co
   for (int j = 0; j < gs; ++j) {
     tc::GemmDesc g{};
     g.A = X; g.lda = D;
-    g.B = whi + p.w_off[0] + (size_t)j * D * H; g.ldb = H;
-    g.B_lo = wlo ? wlo + p.w_off[0] + (size_t)j * D * H : nullptr;
+    if (passes == 3) {
+      // slot j of W_1^T [H, gs * D] (pre-split transposes, K-major): columns j D .. (j + 1) D
+      g.B = ws + p.wthi_off + p.w_off[0] + (size_t)j * D; g.ldb = gs * D;
+      g.B_lo = ws + p.wtlo_off + p.w_off[0] + (size_t)j * D;
+      g.b_mn = 0;
+    } else {
+      g.B = whi + p.w_off[0] + (size_t)j * D * H; g.ldb = H;
+      g.B_lo = nullptr;
+      g.b_mn = 1;
+    }
     g.C = gw.P + (size_t)j * gw.p_stride; g.ldc = H;
     g.GM = (int)bn; g.GN = H; g.GK = D;
-    g.a_mn = 0; g.b_mn = 1; g.passes = passes; g.split_b = 0;
+    g.a_mn = 0; g.passes = passes; g.split_b = 0;
     g.epi = tc::EPI_STORE; g.act = TFR_ACT_NONE; g.splits = 1;
     rc = tc::gemm(g, st);
     if (rc) return rc;

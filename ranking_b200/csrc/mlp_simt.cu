@@ -338,6 +338,87 @@ out_layer_bwd2_o1_kernel(const float4* __restrict__ H4, int M, int K4,
   }
 }
 
+// The same float4 streaming for 2 <= O <= 4 outputs (groupwise scoring: O = group_size): the
+// slot layout is the generic one, { dW[K * O] (k-major, o fastest), db[O], pad to 4, csum[K] }.
+template <int O>
+__global__ void __launch_bounds__(256)
+out_layer_bwd2_vec_kernel(const float4* __restrict__ H4, int M, int K4, const float* __restrict__ W,
+                          const float* __restrict__ dS, int act, int rows_per, int RL,
+                          float4* __restrict__ dH4, float* __restrict__ slots,
+                          size_t slot_stride) {
+  extern __shared__ float sm[];   // [RL][round4(K * O + O) + K]
+  const int k4 = threadIdx.x % K4, rl = threadIdx.x / K4;
+  const int K = K4 * 4;
+  const int mbeg = blockIdx.x * rows_per, mend = min(M, mbeg + rows_per);
+  const bool active = rl < RL;
+  float w[4][O], dw[4][O], cs[4], db[O];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    cs[i] = 0.f;
+#pragma unroll
+    for (int o = 0; o < O; ++o) {
+      w[i][o] = active ? __ldg(W + (size_t)(4 * k4 + i) * O + o) : 0.f;
+      dw[i][o] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < O; ++o) db[o] = 0.f;
+  if (active) {
+#pragma unroll 4
+    for (int m = mbeg + rl; m < mend; m += RL) {
+      float ds[O];
+#pragma unroll
+      for (int o = 0; o < O; ++o) ds[o] = __ldg(dS + (size_t)m * O + o);
+      const float4 h4 = H4[(size_t)m * K4 + k4];
+      const float h[4] = {h4.x, h4.y, h4.z, h4.w};
+      float dh[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float d = 0.f;
+#pragma unroll
+        for (int o = 0; o < O; ++o) {
+          d = fmaf(ds[o], w[i][o], d);
+          dw[i][o] = fmaf(h[i], ds[o], dw[i][o]);
+        }
+        if (act == TFR_ACT_RELU && !(h[i] > 0.f)) d = 0.f;
+        dh[i] = d;
+      }
+      if (dH4) {
+        dH4[(size_t)m * K4 + k4] = make_float4(dh[0], dh[1], dh[2], dh[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cs[i] += dh[i];
+      }
+      if (k4 == 0) {
+#pragma unroll
+        for (int o = 0; o < O; ++o) db[o] += ds[o];
+      }
+    }
+  }
+  const int co = (K * O + O + 3) & ~3;
+  const int per = co + K;
+  if (active) {
+    float* mine = sm + (size_t)rl * per;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int o = 0; o < O; ++o) mine[(4 * k4 + i) * O + o] = dw[i][o];
+      mine[co + 4 * k4 + i] = cs[i];
+    }
+    if (k4 == 0) {
+      for (int i = K * O + O; i < co; ++i) mine[i] = 0.f;
+#pragma unroll
+      for (int o = 0; o < O; ++o) mine[K * O + o] = db[o];
+    }
+  }
+  __syncthreads();
+  float* out = slots + (size_t)blockIdx.x * slot_stride;
+  for (int i = threadIdx.x; i < per; i += blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < RL; ++r) acc += sm[(size_t)r * per + i];
+    out[i] = acc;
+  }
+}
+
 // dst[z][dst_off + i] = sum_{g < group} src[z * group + g][src_off + i], i < n.
 __global__ void __launch_bounds__(256)
 regroup_sum_kernel(const float* __restrict__ src, int slots_in, size_t src_stride,
@@ -494,6 +575,29 @@ int mlp_out_layer_bwd2(const float* H, int M, int K, int O, const float* W, cons
     out_layer_bwd2_o1_kernel<<<blocks, 256, smem, st>>>(
         reinterpret_cast<const float4*>(H), M, K4, reinterpret_cast<const float4*>(W), dS, mask,
         act, rows_per, RL, reinterpret_cast<float4*>(dH), slots, slot_stride);
+    TFR_LAUNCH_OK();
+    return TFR_OK;
+  }
+  if (O >= 2 && O <= 4 && !mask && K % 4 == 0 && K <= 1024 &&
+      (reinterpret_cast<uintptr_t>(H) & 15) == 0 &&
+      (!dH || (reinterpret_cast<uintptr_t>(dH) & 15) == 0)) {
+    const int K4 = K / 4;
+    const int RL = 256 / K4;
+    const int blocks = (M + rows_per - 1) / rows_per;
+    const size_t smem = (size_t)RL * (((K * O + O + 3) & ~3) + K) * sizeof(float);
+#define TFR_OUT_VEC(O_)                                                                         \
+  {                                                                                             \
+    if (smem > 48 * 1024)                                                                       \
+      TFR_CUDA_OK(cudaFuncSetAttribute(out_layer_bwd2_vec_kernel<O_>,                           \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    out_layer_bwd2_vec_kernel<O_><<<blocks, 256, smem, st>>>(                                   \
+        reinterpret_cast<const float4*>(H), M, K4, W, dS, act, rows_per, RL,                    \
+        reinterpret_cast<float4*>(dH), slots, slot_stride);                                     \
+  }
+    if (O == 2) TFR_OUT_VEC(2)
+    else if (O == 3) TFR_OUT_VEC(3)
+    else TFR_OUT_VEC(4)
+#undef TFR_OUT_VEC
     TFR_LAUNCH_OK();
     return TFR_OK;
   }

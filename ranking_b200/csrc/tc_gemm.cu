@@ -86,13 +86,18 @@ struct KernelArgs {
 // block drop from 16 + 2 * 128 N to 16 + 128 N KB (the per-SM ingest rate, ~35-40 B / cycle,
 // is what bounds these kernels: profiles/r02_tc_gemm_wait_cycles.txt) and the stage shrinks
 // enough for a 4-deep ring at N = 256.
-template <bool A_MN, bool B_MN, int PASSES, bool SPLIT_B, bool CG2 = false>
+// FAST_EPI >= 0 fixes the epilogue at compile time (row-major TMA-store path only): 1 = bias +
+// ReLU (+ sign bits), 3 = ReLU mask from sign bits (+ column sums).  The generic kernel keeps
+// every store path alive in one function, which costs the hot loop registers (96 per thread
+// with 18 warps) — the forward / dZ GEMMs are bound by exactly that loop.
+template <bool A_MN, bool B_MN, int PASSES, bool SPLIT_B, bool CG2 = false, int FAST_EPI = -1>
 // (18 warps: ptxas grants 96 registers per thread; 112 was tried with __maxnreg__ and the
 //  launch fails with "too many resources" — the per-warp allocation step does not fit)
 __global__ void __launch_bounds__(kThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
                const KernelArgs args) {
+  constexpr bool kFastOuter = FAST_EPI >= 0;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms.
   // (pointer arithmetic, not an integer round trip: keeps the shared address space so
@@ -482,6 +487,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     };
     const int half = ew >> 2;                 // which of the two warps of the quarter
+    constexpr bool kFast = FAST_EPI >= 0;
+    // FAST_EPI 0 / 1 / 3: TMA-store path with that epilogue; 4: the other store paths only
+    // (transposed / split-K partials of the dW GEMMs), plain store
+    const bool tma_store = kFast ? (FAST_EPI != 4) : (args.tma_store != 0);
+    const int epi = kFast ? (FAST_EPI == 4 ? (int)EPI_STORE : FAST_EPI) : args.epi;
+    const int act = FAST_EPI == 1 ? (int)TFR_ACT_RELU : args.act;
     float* tb = reinterpret_cast<float*>(epi_smem) + (ew & 3) * (32 * 37);
     // per-warp running column sums over all tiles of this CTA (one slot per CTA and
     // quarter instead of one per tile: 592 slots to reduce instead of 6400)
@@ -522,7 +533,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                    : 0u;
       };
       uint32_t mword = 0, mword_next = 0;
-      if (args.tma_store && args.epi == EPI_MASK_BITS) mword = load_bits(half * 32);
+      if (tma_store && epi == EPI_MASK_BITS) mword = load_bits(half * 32);
       {
         const long long wcy = mbar_wait(&acc_full[ab], aph);
         if (dbg_me) s_dbg[0] += wcy;
@@ -531,7 +542,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tmem_d = tmem_base + ab * args.tmem_cols +
                               (static_cast<uint32_t>(q * 32) << 16);
       float* C = args.C + static_cast<size_t>(z) * args.split_stride;
-      if (args.tma_store) {
+      if (tma_store) {
         // Row-major output through TMA: lane = row; each 32-column chunk is drained in two
         // 16-column halves (register budget: 96/thread with 18 warps).  Bias / ReLU / mask
         // run in registers, the block goes to a 128B-swizzled [32][32] staging tile
@@ -551,7 +562,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
         for (int c0 = half * 32; c0 <= last_c0; c0 += 64) {
           const int colb = n0 + c0;
-          if (args.epi == EPI_MASK_BITS) mword_next = load_bits(c0 + 64);
+          if (epi == EPI_MASK_BITS) mword_next = load_bits(c0 + 64);
           uint32_t word_out = 0;
 #pragma unroll 1
           for (int hf = 0; hf < 2; ++hf) {
@@ -572,14 +583,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 16; ++j) x[j] = 0.f;
             }
-            if (args.epi == EPI_BIAS_ACT) {
+            if (epi == EPI_BIAS_ACT) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float4 b4 = *reinterpret_cast<const float4*>(sbias + colh + 4 * j);
                 x[4 * j + 0] += b4.x; x[4 * j + 1] += b4.y;
                 x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
               }
-              if (args.act == TFR_ACT_RELU) {
+              if (act == TFR_ACT_RELU) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.f);
               }
@@ -589,7 +600,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < 16; ++j) w16 |= (x[j] > 0.f ? 1u : 0u) << j;
                 word_out |= w16 << (hf * 16);
               }
-            } else if (args.epi == EPI_MASK_BITS) {
+            } else if (epi == EPI_MASK_BITS) {
               const uint32_t w16 = mword >> (hf * 16);
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -617,7 +628,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           const long long tpc = args.dbg ? clock64() : 0;
-          if (args.epi == EPI_BIAS_ACT && args.bits_out) {
+          if (epi == EPI_BIAS_ACT && args.bits_out) {
             if (args.GN - colb < 32) word_out &= (1u << (args.GN - colb)) - 1u;   // columns >= GN
             if (row < args.GM)
               args.bits_out[static_cast<size_t>(colb >> 5) * args.GM + row] = word_out;
@@ -677,7 +688,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float4* tb4 = reinterpret_cast<float4*>(tb);
         const int rows_here = min(32, args.GM - (m0 + q * 32));
         const int r4 = lane >> 3, c4 = lane & 7;
-        const bool masked = args.epi == EPI_MASK_POS && args.act == TFR_ACT_RELU;
+        const bool masked = epi == EPI_MASK_POS && act == TFR_ACT_RELU;
         const size_t rstep = static_cast<size_t>(4) * args.ldc;
         const size_t row_off = static_cast<size_t>(m0 + q * 32 + r4) * args.ldc;
         // ReLU mask source for one 32x32 block: 8 independent 16-byte loads.
@@ -701,7 +712,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int col = n0 + c0 + c4 * 4;
           const bool col_ok = (c0 + c4 * 4 < args.n_umma) && col < args.GN;
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (args.epi == EPI_BIAS_ACT && col_ok)
+          if (epi == EPI_BIAS_ACT && col_ok)
             bv = __ldg(reinterpret_cast<const float4*>(args.bias + col));
           tmem_ld_wait();
           const long long tp1 = args.dbg ? clock64() : 0;
@@ -724,9 +735,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 x = xs[i];
-            if (args.epi == EPI_BIAS_ACT) {
+            if (epi == EPI_BIAS_ACT) {
               x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
-              if (args.act == TFR_ACT_RELU) {
+              if (act == TFR_ACT_RELU) {
                 x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f);
                 x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
               }
@@ -780,15 +791,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           const int col = n0 + c0 + lane;
           const bool col_ok = (c0 + lane < args.n_umma) && col < args.GN;
-          const float bv = (args.epi == EPI_BIAS_ACT && col_ok) ? __ldg(args.bias + col) : 0.f;
+          const float bv = (epi == EPI_BIAS_ACT && col_ok) ? __ldg(args.bias + col) : 0.f;
           const size_t off0 = static_cast<size_t>(m0 + q * 32) * args.ldc + col;
           float csum = 0.f;
           for (int rr = 0; rr < rows_here; ++rr) {
             float x = tb[rr * 37 + lane];
-            if (args.epi == EPI_BIAS_ACT) {
+            if (epi == EPI_BIAS_ACT) {
               x += bv;
-              if (args.act == TFR_ACT_RELU) x = fmaxf(x, 0.f);
-            } else if (args.epi == EPI_MASK_POS && args.act == TFR_ACT_RELU && col_ok) {
+              if (act == TFR_ACT_RELU) x = fmaxf(x, 0.f);
+            } else if (epi == EPI_MASK_POS && act == TFR_ACT_RELU && col_ok) {
               if (!(__ldg(args.aux + off0 + static_cast<size_t>(rr) * args.ldc) > 0.f)) x = 0.f;
             }
             if (col_ok) {
@@ -803,7 +814,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       arrive_acc_empty(ab);   // all epilogue threads arrive: buffer is free
     }
-    if (args.tma_store && lane == 0) bulk_wait_all();
+    if ((kFastOuter ? (FAST_EPI != 4) : (args.tma_store != 0)) && lane == 0) bulk_wait_all();
     if (args.colsum) {
       __syncwarp();
       float* dst = args.colsum + static_cast<size_t>(blockIdx.x * kEpiWarps + ew) * args.colsum_stride;
@@ -895,11 +906,13 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
 }
 
 // CTA pairs: cluster of 2 along x (one TPC), cta_group::2 MMAs.
-template <bool MN>   // false: forward / dZ (K-major, pre-split B); true: dW (MN-major, split B)
+// MN = false: forward / dZ (K-major, pre-split B); true: dW (MN-major, split B).
+// FE: compile-time epilogue (see FAST_EPI), -1 = generic.
+template <bool MN, int FE>
 static int launch_pairs(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBlo,
                         const CUtensorMap& tmC, const KernelArgs& ka, dim3 grid, size_t smem,
                         cudaStream_t st) {
-  auto kern = tc_gemm_kernel<MN, MN, 3, MN, true>;
+  auto kern = tc_gemm_kernel<MN, MN, 3, MN, true, FE>;
   TFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -1095,8 +1108,32 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
                       256 /*barriers*/;
   if (g.colsum_slots_out) *g.colsum_slots_out = kEpiWarps * (int)grid.x;
 
-  if (cg2) return cg2_mn ? launch_pairs<true>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st)
-                         : launch_pairs<false>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st);
+  if (cg2) {
+    static const bool no_fast_epi = getenv("TFR_TC_NO_FAST_EPI") != nullptr;
+    if (cg2_mn) {
+      if (!no_fast_epi && !ka.tma_store && g.epi == EPI_STORE)
+        return launch_pairs<true, 4>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st);
+      return launch_pairs<true, -1>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st);
+    }
+    if (!no_fast_epi && ka.tma_store && g.epi == EPI_STORE)
+      return launch_pairs<false, 0>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st);
+    if (!no_fast_epi && ka.tma_store && g.epi == EPI_BIAS_ACT && g.act == TFR_ACT_RELU)
+      return launch_pairs<false, 1>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st);
+    if (!no_fast_epi && ka.tma_store && g.epi == EPI_MASK_BITS)
+      return launch_pairs<false, 3>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st);
+    return launch_pairs<false, -1>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st);
+  }
+  {
+    static const bool no_fast_epi = getenv("TFR_TC_NO_FAST_EPI") != nullptr;
+    if (!no_fast_epi && g.a_mn && g.b_mn && g.passes == 3 && g.split_b && !ka.tma_store &&
+        g.epi == EPI_STORE) {   // single-CTA dW GEMM (one 128-row block): plain-store kernel
+      auto kern = tc_gemm_kernel<true, true, 3, true, false, 4>;
+      TFR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, kThreads, smem, st>>>(tmA, tmB, tmBlo, tmC, ka);
+      TFR_LAUNCH_OK();
+      return TFR_OK;
+    }
+  }
 #define TFR_TC_LAUNCH(AMN, BMN, P, SB) \
   return launch<AMN, BMN, P, SB>(tmA, tmB, tmBlo, tmC, ka, grid, smem, st)
   const int key = (g.a_mn ? 8 : 0) | (g.b_mn ? 4 : 0) | (g.passes == 3 ? 2 : 0) |
