@@ -73,6 +73,8 @@ struct KernelArgs {
                        //   and the MMAs read A from there (halves the smem operand traffic)
   uint32_t a_col0;     // first TMEM column of the A region: stage s at a_col0 + 64 s
   int pf_dist;         // k blocks the producer's L2 prefetch runs ahead of its loads (0 = off)
+  int b_resident;      // pairs, pre-split K-major B: this CTA's half of B (hi + lo, every k block)
+                       //   is loaded ONCE and stays in shared memory; stages hold A only
   uint32_t acc_bufs;   // accumulator buffers in TMEM (2: epilogue overlaps the next tile;
                        //   1: long split-K tiles whose A stages need the columns)
   uint32_t tmem_alloc_cols;   // power of two >= 2 * tmem_cols (+ 64 * stages with a_tmem)
@@ -106,9 +108,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kACopies = (PASSES == 3 && !args.a_tmem) ? 2 : 1;
   constexpr int kBCopies = PASSES == 3 ? 2 : 1;
   const int a_bytes = args.a_tile_bytes * kACopies;
-  const int stage_bytes = a_bytes + args.b_tile_bytes * kBCopies;
+  const bool b_res = CG2 && !B_MN && !SPLIT_B && PASSES == 3 && args.b_resident;
+  const int stage_bytes = a_bytes + (b_res ? 0 : args.b_tile_bytes * kBCopies);
   const int S = args.stages;
-  unsigned char* epi_smem = smem + static_cast<size_t>(S) * stage_bytes;   // 4 x [32][33] floats
+  // resident B (b_res): [k block][hi | lo] right after the ring
+  unsigned char* bres = smem + static_cast<size_t>(S) * stage_bytes;
+  const int nkb_all = (args.GK + args.bk - 1) / args.bk;
+  unsigned char* epi_smem =
+      bres + (b_res ? static_cast<size_t>(nkb_all) * 2 * args.b_tile_bytes : 0);   // 4 x [32][33] floats
   float* cacc_base = reinterpret_cast<float*>(epi_smem + args.epi_smem_bytes);   // [4][colsum_cols]
   float* sbias = cacc_base + kEpiWarps * args.colsum_cols;                       // [bias_cols]
   uint64_t* bars = reinterpret_cast<uint64_t*>(
@@ -120,6 +127,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_full = bars + 3 * kMaxStages;    // [2] accumulator buffer complete
   uint64_t* acc_empty = bars + 3 * kMaxStages + 2;   // [2] accumulator buffer drained
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 4);
+  uint64_t* bres_bar = bars + 3 * kMaxStages + 11;   // resident B landed (after the debug slots)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bk = args.bk;
@@ -142,6 +150,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&split[s], CG2 ? 2 * kSplitWarps : kSplitWarps);
       mbar_init(&empty[s], 1);
     }
+    mbar_init(bres_bar, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], (CG2 ? 2 : 1) * kEpiWarps);   // one arrival per epilogue warp
@@ -187,10 +196,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // which made the producer the bottleneck of every GEMM with an MN-major operand.
     {
       const uint32_t tx_bytes =
-          args.a_tile_bytes + args.b_tile_bytes * ((PASSES == 3 && !SPLIT_B) ? 2 : 1);
+          args.a_tile_bytes +
+          (b_res ? 0 : args.b_tile_bytes * ((PASSES == 3 && !SPLIT_B) ? 2 : 1));
       const int nA = A_MN ? BM / 32 : 1;
-      const int nB = B_MN ? args.b_tile_bytes / box_bytes : 1;
-      const int nBlo = (PASSES == 3 && !SPLIT_B) ? nB : 0;
+      const int nB = b_res ? 0 : (B_MN ? args.b_tile_bytes / box_bytes : 1);
+      const int nBlo = (PASSES == 3 && !SPLIT_B && !b_res) ? nB : 0;
+      if (b_res) {
+        // this CTA's half of W^T hi / lo, all k blocks, once: the tiles then stream A only
+        if (lane == 0) mbar_expect_tx(bres_bar, (uint32_t)nkb_all * 2u * args.b_tile_bytes);
+        __syncwarp();
+        for (int l = lane; l < 2 * nkb_all; l += 32) {
+          const int kbi = l >> 1;
+          unsigned char* dst = bres + static_cast<size_t>(kbi) * 2 * args.b_tile_bytes +
+                               (l & 1) * args.b_tile_bytes;
+          tma_load_2d(dst, (l & 1) ? &tmBlo : &tmB, bres_bar, kbi * bk,
+                      (int)rank * (args.n_umma >> 1));
+        }
+      }
       uint32_t it = 0;
       long long w_empty = 0;
       const long long t_start = clock64();
@@ -288,7 +310,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           if (args.dbg) w_full += clock64() - tw0;
           const uint32_t a_hi = smem_u32(sA_hi(s)), a_lo = smem_u32(sA_lo(s));
-          const uint32_t b_hi = smem_u32(sB_hi(s)), b_lo = smem_u32(sB_lo(s));
+          const uint32_t b_hi =
+              b_res ? smem_u32(bres + static_cast<size_t>(kb_begin + kb) * 2 * args.b_tile_bytes)
+                    : smem_u32(sB_hi(s));
+          const uint32_t b_lo = b_res ? b_hi + args.b_tile_bytes : smem_u32(sB_lo(s));
           // descriptors of the stage once; a k step only adds (bytes >> 4) to the address field
           const uint64_t da_hi0 = make_smem_desc(a_hi, a_lbo, a_sbo, a_lt);
           const uint64_t da_lo0 = make_smem_desc(a_lo, a_lbo, a_sbo, a_lt);
@@ -359,6 +384,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int b_chunks = SPLIT_B ? args.b_tile_bytes / 16 : 0;
       uint32_t it = 0;
       long long w_tma = 0;
+      // resident B: a splitter's first arrival at the leader also says "my CTA's half of B
+      // has landed" (the leader's MMAs read both halves)
+      if (b_res) mbar_wait(bres_bar, 0);
       for (int tile = tile0; tile < total_tiles; tile += tstep) {
         int m0, n0, z, kb_begin, nkb;
         decode(tile, m0, n0, z, kb_begin, nkb);
@@ -985,6 +1013,23 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   if (cg2_mn) b_tile_bytes = (n_umma / 64) * bk * 128;   // ... as whole [32 k][32 n] boxes
   int stage_bytes = a_tmem ? a_tile_bytes + b_tile_bytes * copies
                            : (a_tile_bytes + b_tile_bytes) * copies;
+  // Resident B (pairs, pre-split K-major weights): if this CTA's half of W^T hi + lo over the
+  // whole K fits next to >= 2 A stages, it is loaded once per CTA instead of once per tile —
+  // the weights were 50-80 % of the bytes these GEMMs pull through TMA.
+  // Measured at config 2 (profiles/README.md, round 2): NO gain — 0.693-0.705 ms/step with
+  // resident weights (L2, L3, dZ2; dZ1 with 2 stages) against 0.686 without: the weight tiles
+  // are L2 hits shared by all CTAs and were not what bounds these GEMMs any more.  Opt-in.
+  static const bool no_b_resident = getenv("TFR_TC_B_RESIDENT") == nullptr;
+  const size_t b_res_bytes = (size_t)((g.GK + bk - 1) / bk) * 2 * b_tile_bytes;
+  const int a_stage_bytes = a_tmem ? a_tile_bytes : a_tile_bytes * copies;
+  bool b_resident = false;
+  static const int bres_min_stages =
+      getenv("TFR_TC_BRES_MIN_STAGES") ? atoi(getenv("TFR_TC_BRES_MIN_STAGES")) : 2;
+  if (cg2_k && !no_b_resident &&
+      b_res_bytes + (size_t)bres_min_stages * a_stage_bytes + 35 * 1024 <= 227 * 1024) {
+    b_resident = true;
+    stage_bytes = a_stage_bytes;
+  }
   int splits = g.splits < 1 ? 1 : g.splits;
   // TMA-store epilogue: row-major, unsplit output with 16-byte aligned rows.
   static const bool no_tma_store = getenv("TFR_TC_NO_TMA_STORE") != nullptr;
@@ -1002,7 +1047,12 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   const size_t fixed2 = kEpiSmemBytes2 + (kEpiWarps * colsum_cols + bias_cols) * sizeof(float);
   const size_t budget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/;
   const int epi_smem_bytes = tma_store ? kEpiSmemBytes2 : kEpiSmemBytes;
-  int stages = (int)((budget - (tma_store ? fixed2 : fixed1)) / stage_bytes);
+  const size_t resident = b_resident ? b_res_bytes : 0;
+  if (b_resident && budget < (tma_store ? fixed2 : fixed1) + resident + 2 * (size_t)stage_bytes) {
+    set_error("tc gemm: internal: resident B does not fit");   // (excluded by the test above)
+    return TFR_UNSUPPORTED;
+  }
+  int stages = (int)((budget - (tma_store ? fixed2 : fixed1) - resident) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (a_tmem) {
     const int room = (512 - (int)(acc_bufs * acc_cols)) / 64;   // A stages that fit tensor memory
@@ -1044,6 +1094,7 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
   ka.tmem_cols = acc_cols;     // per accumulator buffer; the kernel allocates two
   ka.a_tmem = a_tmem ? 1 : 0;
   ka.acc_bufs = acc_bufs;
+  ka.b_resident = b_resident ? 1 : 0;
   {
     static const int pf_env = getenv("TFR_TC_PREFETCH") ? atoi(getenv("TFR_TC_PREFETCH")) : -1;
     // Measured (profiles/README.md, round 2): prefetching ahead LOSES 3-5 % on the dW GEMMs —
@@ -1103,7 +1154,7 @@ int gemm(const GemmDesc& g, cudaStream_t st) {
     const int pairs = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
     grid = dim3(2 * pairs);
   }
-  const size_t smem = (size_t)stages * stage_bytes + epi_smem_bytes +
+  const size_t smem = (size_t)stages * stage_bytes + resident + epi_smem_bytes +
                       (kEpiWarps * colsum_cols + bias_cols) * sizeof(float) + 1024 /*align*/ +
                       256 /*barriers*/;
   if (g.colsum_slots_out) *g.colsum_slots_out = kEpiWarps * (int)grid.x;
