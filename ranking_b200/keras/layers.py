@@ -72,7 +72,7 @@ class Tower(torch.nn.Module):
   statistics, as Keras' `training` argument does."""
 
   def __init__(self, input_dim, hidden_layer_dims, output_units, activation=None,
-               precision='fp32', seed=None, device='cuda', input_batch_norm=False,
+               precision=None, seed=None, device='cuda', input_batch_norm=False,
                use_batch_norm=False, batch_norm_moment=0.999, dropout=0.0,
                batch_norm_epsilon=1e-3):
     super().__init__()
@@ -172,6 +172,11 @@ class Tower(torch.nn.Module):
     return self.bn_state[a:a + w_], self.bn_state[b:b + w_]
 
   def set_precision(self, precision):
+    if precision is None or precision == 'auto':
+      # tensor cores whenever the layer widths allow it: the fp32-faithful 3xTF32 engine
+      # needs every Dense input width to be a multiple of 4
+      ok = all(d % 4 == 0 for d in self.dims[:-1])
+      precision = 'tf32x3' if ok else 'fp32'
     if precision not in _PRECISIONS:
       raise ValueError('precision must be one of %s' % sorted(_PRECISIONS))
     self.precision = precision
@@ -218,8 +223,11 @@ class Tower(torch.nn.Module):
 def create_tower(hidden_layer_dims, output_units, activation=None,
                  input_batch_norm=False, use_batch_norm=True,
                  batch_norm_moment=0.999, dropout=0.5, name=None,
-                 input_dim=None, precision='fp32', seed=None, **kwargs):
+                 input_dim=None, precision=None, seed=None, **kwargs):
   """keras/layers.py:26-77.  Same arguments and defaults as the reference.
+
+  `precision`: None (default) = 'tf32x3' (tcgen05, fp32-faithful) when every Dense input
+  width is a multiple of 4, else 'fp32' (FFMA); 'tf32', 'bf16' on request.
 
   BatchNormalization (batch statistics in `train()` mode, moving statistics in
   `eval()` mode) and Dropout run as HBM-bound passes next to the Dense GEMMs
