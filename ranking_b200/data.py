@@ -330,3 +330,71 @@ def elwc_batches(paths, batch_size, list_size, context_feature_spec, example_fea
         buf = []
   if buf and not drop_remainder:
     yield flush()
+
+
+class Prefetcher(object):
+  """Runs a batch iterator (e.g. `elwc_batches(..., pin_memory=True)`: TFRecord read +
+  native ELWC decode into pinned buffers) in a background thread, `depth` batches ahead, so
+  that the host-side input work overlaps the device step.  `HostBatchPipeline.run` takes any
+  iterable of (x_pinned, y_pinned), so
+
+      pipe.run(Prefetcher(elwc_batches(paths, B, N, ctx_spec, ex_spec, 'label'), depth=4))
+
+  is the whole input path of the reference's `make_dataset` -> `model.fit`
+  (keras/pipeline.py:505-632) for dense features.  The decoder releases the GIL (it is a C
+  call), so one thread here plus the decoder's own threads keep the cores busy.  Exceptions of
+  the producer are re-raised at the consumer; `close()` (or exhausting / deleting the
+  iterator) stops the thread."""
+
+  _END = object()
+
+  def __init__(self, batches, depth=2):
+    import queue
+    import threading
+    if depth < 1:
+      raise ValueError('depth must be >= 1')
+    self._q = queue.Queue(maxsize=int(depth))
+    self._stop = threading.Event()
+    self._exc = None
+    self._thread = threading.Thread(target=self._run, args=(iter(batches),), daemon=True)
+    self._thread.start()
+
+  def _put(self, item):
+    import queue
+    while not self._stop.is_set():
+      try:
+        self._q.put(item, timeout=0.1)
+        return True
+      except queue.Full:
+        continue
+    return False
+
+  def _run(self, it):
+    try:
+      for batch in it:
+        if not self._put(batch):
+          return
+    except BaseException as e:   # noqa: BLE001  (handed to the consumer)
+      self._exc = e
+    self._put(self._END)
+
+  def __iter__(self):
+    return self
+
+  def __next__(self):
+    if self._stop.is_set():
+      raise StopIteration
+    item = self._q.get()
+    if item is self._END:
+      self._stop.set()
+      if self._exc is not None:
+        raise self._exc
+      raise StopIteration
+    return item
+
+  def close(self):
+    self._stop.set()
+    self._thread.join(timeout=5.0)
+
+  def __del__(self):
+    self._stop.set()

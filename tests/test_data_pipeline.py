@@ -331,3 +331,61 @@ def test_example_in_example_and_sequence_example_formats():
   got = data.parse_from_example_in_example([outer.SerializeToString()], 4, spec_c, spec_e)
   for k in ('context', 'examples', 'sizes', 'mask'):
     assert torch.equal(got[k], want[k]), k
+
+
+def test_prefetcher_order_exceptions_and_close():
+  """data.Prefetcher: same batches in the same order, producer exceptions re-raised at the
+  consumer, close() stops a producer that is blocked on a full queue."""
+  import time
+  from ranking_b200 import data as D
+  assert list(D.Prefetcher(iter(range(50)), depth=3)) == list(range(50))
+  assert list(D.Prefetcher([], depth=1)) == []
+
+  def boom():
+    yield 1
+    yield 2
+    raise RuntimeError('decode failed')
+
+  p = D.Prefetcher(boom(), depth=2)
+  got = [next(p), next(p)]
+  assert got == [1, 2]
+  try:
+    next(p)
+    assert False, 'expected the producer exception'
+  except RuntimeError as e:
+    assert 'decode failed' in str(e)
+
+  def endless():
+    i = 0
+    while True:
+      yield i
+      i += 1
+
+  p = D.Prefetcher(endless(), depth=2)
+  assert next(p) == 0
+  p.close()
+  time.sleep(0.05)
+  assert not p._thread.is_alive()
+  try:
+    D.Prefetcher(iter([]), depth=0)
+    assert False
+  except ValueError:
+    pass
+
+
+def test_prefetcher_feeds_elwc_batches(tmp_path):
+  """Prefetched ELWC batches equal the synchronous iterator's."""
+  import torch
+  from ranking_b200 import data as D
+  recs = []
+  for b in range(10):
+    ex = [{'f': [float(b), float(i)], 'label': [float(i % 3)]} for i in range(1 + b % 4)]
+    recs.append(D.encode_elwc({'c': [0.5 * b]}, ex))
+  path = str(tmp_path / 'elwc.tfrecord')
+  D.write_tfrecords(path, recs)
+  args = (path, 4, 5, {'c': (1, 0.)}, {'f': (2, 0.), 'label': (1, -1.)}, 'label')
+  plain = list(D.elwc_batches(*args, drop_remainder=False, pin_memory=False))
+  pre = list(D.Prefetcher(D.elwc_batches(*args, drop_remainder=False, pin_memory=False), depth=2))
+  assert len(plain) == len(pre) == 3
+  for (x0, y0), (x1, y1) in zip(plain, pre):
+    assert torch.equal(x0, x1) and torch.equal(y0, y1)
