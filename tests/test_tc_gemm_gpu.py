@@ -125,6 +125,29 @@ def test_tc_gemm_epilogues_and_splits():
   assert err <= 2e-6, err
 
 
+@pytest.mark.parametrize('gm', [512, 600, 657, 1280])
+@pytest.mark.parametrize('gn,gk', [(256, 136), (128, 256), (64, 128)])
+def test_tc_gemm_cta_pairs_kmajor(gm, gn, gk):
+  """Forward / dZ GEMM shapes that run as CTA pairs (cta_group::2, K-major pre-split weights,
+  >= 4 row blocks): even and odd block counts (600 rows = 5 blocks: the last pair has a
+  phantom half), ragged last blocks (657), every compile-time epilogue (store, bias + ReLU +
+  sign bits, mask from sign bits)."""
+  for epi, act, bits in ((0, 0, False), (1, 1, True), (3, 1, False)):
+    err, _, _ = run_gemm(gm, gn, gk, 0, 0, 3, 0, epi=epi, act=act, want_bits=bits, seed=gm + gn)
+    assert err <= 2e-6, (gm, gn, gk, epi, err)
+
+
+@pytest.mark.parametrize('shape', [(256, 136, 4096, 1, 4), (256, 128, 4096, 0, 8),
+                                   (384, 136, 2048, 1, 3), (640, 64, 1536, 0, 5)])
+def test_tc_gemm_cta_pairs_dw(shape):
+  """dW GEMM shapes that run as CTA pairs (MN-major operands split on the fly, M side through
+  tensor memory, N rounded up to 64): 2, 3 (phantom half) and 5 row blocks, split-K partials,
+  transposed and direct stores."""
+  gm, gn, gk, transposed, splits = shape
+  err, _, _ = run_gemm(gm, gn, gk, 1, 1, 3, 1, transposed=transposed, splits=splits, seed=gm)
+  assert err <= 2e-6, (shape, err)
+
+
 if __name__ == '__main__':
   # Diagnostic mode: print everything, never stop.
   import traceback
