@@ -389,3 +389,71 @@ def test_prefetcher_feeds_elwc_batches(tmp_path):
   assert len(plain) == len(pre) == 3
   for (x0, y0), (x1, y1) in zip(plain, pre):
     assert torch.equal(x0, x1) and torch.equal(y0, y1)
+
+
+def test_pipeline_hparams_validation():
+  """pipeline.PipelineHparams: the reference's field names and defaults
+  (keras/pipeline.py:312-334); unsupported choices raise ValueError."""
+  from ranking_b200 import pipeline as P
+  hp = P.PipelineHparams(model_dir='/tmp/x', num_epochs=2, steps_per_epoch=5, validation_steps=2,
+                         learning_rate=0.01, loss='softmax_loss')
+  hp.validate()
+  assert hp.steps_per_execution == 10 and hp.best_exporter_metric == 'loss'
+  assert hp.early_stopping_patience == 0 and not hp.export_best_model
+  import dataclasses
+  for bad in (dict(optimizer='adam'), dict(loss={'a': 'softmax_loss'}), dict(num_epochs=0),
+              dict(loss_weights={'a': 1.0})):
+    try:
+      dataclasses.replace(hp, **bad).validate()
+      assert False, bad
+    except ValueError:
+      pass
+
+
+@pytest.mark.gpu
+def test_model_fit_pipeline_train_and_validate(tmp_path):
+  """ModelFitPipeline: epochs x (steps, validation), history, checkpoint resume, best
+  checkpoint, early stopping."""
+  import torch
+  import ranking_b200 as tfr
+  from ranking_b200 import pipeline as P
+  g = torch.Generator().manual_seed(0)
+  w_true = torch.randn(8, generator=g)
+
+  def batches():
+    gg = torch.Generator().manual_seed(1)
+    while True:
+      x = torch.randn(16, 12, 8, generator=gg)
+      y = ((x @ w_true) > 0.5).float() + ((x @ w_true) > 1.5).float()
+      y[:, -2:] = -1.
+      yield x, y
+
+  def tower_fn():
+    return tfr.keras.layers.create_tower([16, 8], 1, activation='relu', use_batch_norm=False,
+                                         dropout=0, input_dim=8, seed=5)
+
+  hp = P.PipelineHparams(model_dir=str(tmp_path), num_epochs=3, steps_per_epoch=20,
+                         validation_steps=2, learning_rate=0.1, loss='approx_ndcg_loss',
+                         export_best_model=True, best_exporter_metric='metric/ndcg_5',
+                         best_exporter_metric_higher_better=True)
+  pipe = P.ModelFitPipeline(tower_fn, batches, batches, hp)
+  hist = pipe.train_and_validate()
+  assert [h['epoch'] for h in hist] == [1, 2, 3] and hist[-1]['step'] == 60
+  assert hist[-1]['metric/ndcg_5'] > hist[0]['metric/ndcg_5'] - 0.05
+  assert hist[-1]['train_loss'] <= hist[0]['train_loss'] + 0.02   # (it learns; noise-tolerant)
+  import os
+  assert os.path.exists(os.path.join(str(tmp_path), 'ckpt.pt'))
+  assert os.path.exists(os.path.join(str(tmp_path), 'best_checkpoint', 'ckpt.pt'))
+  # resume: nothing left to do for the same hparams; two more epochs when asked for five
+  pipe2 = P.ModelFitPipeline(tower_fn, batches, batches,
+                             __import__('dataclasses').replace(hp, num_epochs=5))
+  hist2 = pipe2.train_and_validate()
+  assert [h['epoch'] for h in hist2] == [4, 5] and hist2[-1]['step'] == 100
+  # early stopping on a metric that cannot improve
+  hp3 = __import__('dataclasses').replace(hp, model_dir=str(tmp_path / 'es'), num_epochs=6,
+                                          learning_rate=0.0, early_stopping_patience=2,
+                                          best_exporter_metric='loss',
+                                          best_exporter_metric_higher_better=False,
+                                          export_best_model=False)
+  hist3 = P.ModelFitPipeline(tower_fn, batches, batches, hp3).train_and_validate()
+  assert len(hist3) == 3      # epoch 1 sets the best, epochs 2 and 3 do not improve
