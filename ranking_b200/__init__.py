@@ -10,6 +10,7 @@ without the built library raises).
 from ranking_b200 import _C  # noqa: F401  (fails loudly if the .so is missing)
 from ranking_b200 import keras
 from ranking_b200 import losses_impl
+from ranking_b200 import losses
 from ranking_b200 import metrics_impl
 from ranking_b200 import utils
 from ranking_b200 import dp
