@@ -12,6 +12,7 @@ from ranking_b200 import keras
 from ranking_b200 import losses_impl
 from ranking_b200 import losses
 from ranking_b200 import metrics_impl
+from ranking_b200 import metrics
 from ranking_b200 import utils
 from ranking_b200 import dp
 from ranking_b200 import model
